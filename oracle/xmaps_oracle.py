@@ -1,0 +1,337 @@
+"""CPU oracle for the X-maps per-event depth path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``x-maps_b200/`` (the product) may import this
+module; it is used by ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` as the checker and as the timed CPU baseline.
+
+It restates, in NumPy (and OpenCV for the two dense image ops the reference itself
+delegates to OpenCV), the algorithm of fraunhoferhhi/X-maps for SURVEY.md §8 rows A0-A5
+plus the "next" rows N1 (colourise) and N3 (X-map build).  Every function cites the
+reference lines it follows (paths relative to ``/root/reference``).
+
+Parity status: PINNED.  The reference is pure Python and imports in the authoring
+container, so ``tests/golden/generate_golden.py`` runs the *real* reference on seeded
+inputs and commits its outputs under ``tests/golden/``; ``tests/test_oracle_golden.py``
+checks this restatement against those vectors bit-for-bit.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+# Metavision EventCD record: 16-byte AoS, t in microseconds.
+EVENT_DTYPE = np.dtype(
+    {
+        "names": ["x", "y", "p", "t"],
+        "formats": ["<u2", "<u2", "<i2", "<i8"],
+        "offsets": [0, 2, 4, 8],
+        "itemsize": 16,
+    }
+)
+
+VIEW_PROJECTOR = 0
+VIEW_CAMERA = 1
+
+
+@dataclass
+class OracleTables:
+    """Read-only tables of one calibration (what the reference keeps on CamProjMaps /
+    XMapsDisparity, python/cam_proj_calibration.py:143-172, python/x_maps_disparity.py:35-67)."""
+
+    lut_x: np.ndarray  # [cam_h, cam_w] int16   disp_cam_mapx_i16
+    lut_y: np.ndarray  # [cam_h, cam_w] int16   disp_cam_mapy_i16
+    x_map: np.ndarray  # [rect_h, xmap_w] int16 proj_x_map (value = x_rect + X_OFFSET, 0 = undefined)
+    remap_xy: np.ndarray  # [proj_h, proj_w, 2] int16 disp_proj_mapxy_i16 (ch0 = x_rect, ch1 = y_rect)
+    rect_w: int
+    rect_h: int
+    t_px_scale: int  # X_MAP_WIDTH - 1
+    x_offset: int  # 4242
+    depth_scale: float  # P2[0, 3] (float64)
+    dilate: int = 7
+
+    @property
+    def cam_h(self):
+        return self.lut_x.shape[0]
+
+    @property
+    def cam_w(self):
+        return self.lut_x.shape[1]
+
+    @property
+    def proj_h(self):
+        return self.remap_xy.shape[0]
+
+    @property
+    def proj_w(self):
+        return self.remap_xy.shape[1]
+
+
+# --------------------------------------------------------------------------------------
+# A0  polarity mask
+# --------------------------------------------------------------------------------------
+def polarity_mask(events: np.ndarray) -> np.ndarray:
+    """Keep positive events, order preserved.
+
+    Reference: ``PolarityFilterAlgorithm(1).process_events`` (closed Metavision binary; call
+    site python/depth_reprojection_pipe.py:43,114).  Restated as ``p == 1`` exactly as the
+    reference restates it itself in python/frame_event_filter.py:21,47,72,104.
+    """
+    return events[events["p"] == 1]
+
+
+# --------------------------------------------------------------------------------------
+# A1  rectify event pixels through the int16 LUT
+# --------------------------------------------------------------------------------------
+def rectify_i16(tables: OracleTables, events) -> Tuple[np.ndarray, np.ndarray]:
+    """python/cam_proj_calibration.py:277-281 (rectify_cam_coords_i16)."""
+    ys = np.asarray(events["y"])
+    xs = np.asarray(events["x"])
+    return tables.lut_x[ys, xs], tables.lut_y[ys, xs]
+
+
+# --------------------------------------------------------------------------------------
+# A2  X-map lookup -> disparity
+# --------------------------------------------------------------------------------------
+def time_to_xmap_column(t: np.ndarray, t_px_scale: int, t_min=None, t_max=None) -> np.ndarray:
+    """python/x_maps_disparity.py:12-19.
+
+    float64 arithmetic, two roundings (divide, multiply) then round-half-even, then a cast
+    to int16.  ``t`` may be int64 microseconds (live path) or float (eval path,
+    python/eval/compute_depth_x_maps.py:91).  A frame whose timestamps are all equal gives
+    0/0 = NaN for every event; NumPy's NaN -> int16 cast yields 0 on x86-64, which is the
+    behaviour restated (and tested) here.
+    """
+    t = np.asarray(t)
+    lo = t.min() if t_min is None else t_min
+    hi = t.max() if t_max is None else t_max
+    with np.errstate(invalid="ignore", divide="ignore"):
+        norm = (t - lo) / (hi - lo)
+        col = np.rint(norm * t_px_scale)
+        col = np.where(np.isnan(col), 0.0, col)
+        return col.astype(np.int16)
+
+
+def event_disparity(tables: OracleTables, xcr: np.ndarray, ycr: np.ndarray, t: np.ndarray):
+    """python/x_maps_disparity.py:9-32 (compute_disparity).
+
+    Returns ``(disp[M] int16, inlier_mask[N] bool)``; ``disp`` is compacted to the inliers.
+    Note the last X-map row is excluded (``ycr < H - 1``), and that an undefined X-map cell
+    (value 0) drops out because ``0 - xcr - X_OFFSET < 0`` whenever ``xcr > -X_OFFSET``.
+    """
+    if len(t) == 0:
+        return np.zeros(0, np.int16), np.zeros(0, bool)
+    col = time_to_xmap_column(t, tables.t_px_scale)
+    y_ok = (ycr >= 0) & (ycr < tables.x_map.shape[0] - 1)
+    x_proj = tables.x_map[ycr[y_ok], col[y_ok]]
+    # int16 arithmetic with wrap-around, as NumPy does for int16 - int16 - small python int
+    disp = (x_proj.astype(np.int32) - xcr[y_ok].astype(np.int32) - tables.x_offset).astype(np.int16)
+    keep = disp >= 0
+    mask = y_ok.copy()
+    mask[y_ok] = keep
+    return disp[keep], mask
+
+
+# --------------------------------------------------------------------------------------
+# A3  scatter into a disparity map (last write wins)
+# --------------------------------------------------------------------------------------
+def _last_write_wins_scatter(shape, rows, cols, values) -> np.ndarray:
+    """``m[rows, cols] = values`` with the reference's semantics made explicit: for duplicate
+    targets the *last* occurrence (highest event index) is kept.  Implemented without relying
+    on NumPy's unspecified duplicate-assignment order: sort-free reverse-unique."""
+    out = np.zeros(shape, dtype=np.float32)
+    if len(values) == 0:
+        return out
+    flat = rows.astype(np.int64) * shape[1] + cols.astype(np.int64)
+    # first occurrence in the reversed sequence == last occurrence in the original
+    _, first_rev = np.unique(flat[::-1], return_index=True)
+    winners = len(flat) - 1 - first_rev
+    out.reshape(-1)[flat[winners]] = values[winners].astype(np.float32)
+    return out
+
+
+def scatter_projector_view(tables: OracleTables, xcr, ycr, mask, disp) -> np.ndarray:
+    """python/cam_proj_calibration.py:299-303 (compute_disp_map_projector_view).
+
+    ``xpr = int16(rint(xcr + disp))`` is int16 + int16 (wraps), i.e. ``x_proj - X_OFFSET``.
+    Negative indices follow NumPy's wrap-around; out-of-range ones raise IndexError as the
+    reference does.
+    """
+    xpr = (xcr[mask].astype(np.int32) + disp.astype(np.int32)).astype(np.int16).astype(np.int64)
+    ypr = ycr[mask].astype(np.int64)
+    h, w = tables.rect_h, tables.rect_w
+    if len(xpr) and (xpr.min() < -w or xpr.max() >= w or ypr.min() < -h or ypr.max() >= h):
+        raise IndexError("scatter target outside the rectified disparity map")
+    xpr = np.where(xpr < 0, xpr + w, xpr)
+    ypr = np.where(ypr < 0, ypr + h, ypr)
+    return _last_write_wins_scatter((h, w), ypr, xpr, disp)
+
+
+def scatter_camera_view(tables: OracleTables, events, mask, disp) -> np.ndarray:
+    """python/cam_proj_calibration.py:312-317 (compute_disp_map_camera_view)."""
+    xs = np.asarray(events["x"])[mask]
+    ys = np.asarray(events["y"])[mask]
+    return _last_write_wins_scatter((tables.cam_h, tables.cam_w), ys, xs, disp)
+
+
+# --------------------------------------------------------------------------------------
+# A4  7x7 dilate + nearest remap rect -> projector
+# --------------------------------------------------------------------------------------
+def dilate_remap(tables: OracleTables, rect_disp_map: np.ndarray, use_cv2: bool = True) -> np.ndarray:
+    """python/disp_to_depth.py:76-97 (remap_rectified_disp_map_to_proj).
+
+    ``cv2.dilate`` with a k x k all-ones kernel = windowed max, anchor at the centre, taps that
+    fall outside the image ignored; ``cv2.remap`` INTER_NEAREST with a CV_16SC2 map and
+    BORDER_CONSTANT(0) = plain gather, 0 where the source coordinate is outside the image.
+    ``use_cv2=False`` is a dependency-free restatement used to cross-check the OpenCV one.
+    """
+    k = tables.dilate
+    if use_cv2:
+        import cv2
+
+        dil = cv2.dilate(rect_disp_map, np.ones((k, k), dtype=np.uint8))
+        return cv2.remap(
+            dil,
+            map1=tables.remap_xy,
+            map2=None,
+            interpolation=cv2.INTER_NEAREST,
+            borderMode=cv2.BORDER_CONSTANT,
+        )
+    r = k // 2
+    h, w = rect_disp_map.shape
+    pad = np.full((h + 2 * r, w + 2 * r), -np.inf, dtype=np.float32)
+    pad[r : r + h, r : r + w] = rect_disp_map
+    rows = pad[:, 0:w].copy()
+    for dx in range(1, k):
+        np.maximum(rows, pad[:, dx : dx + w], out=rows)
+    dil = rows[0:h].copy()
+    for dy in range(1, k):
+        np.maximum(dil, rows[dy : dy + h], out=dil)
+    mx = tables.remap_xy[..., 0].astype(np.int64)
+    my = tables.remap_xy[..., 1].astype(np.int64)
+    inside = (mx >= 0) & (mx < w) & (my >= 0) & (my < h)
+    out = np.zeros(mx.shape, dtype=np.float32)
+    out[inside] = dil[my[inside], mx[inside]]
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# A5  disparity -> metric depth
+# --------------------------------------------------------------------------------------
+def disparity_to_depth(disp_map: np.ndarray, depth_scale: float) -> np.ndarray:
+    """python/disp_to_depth.py:46-63 (disparity_to_depth_rectified).
+
+    ``depth = 0 if d == 0 else max(P[0,3] / d, 1e-9)``: float64 divide, float64 max, stored as
+    float32 (one rounding, round-to-nearest-even).
+    """
+    d = disp_map.astype(np.float64)
+    with np.errstate(divide="ignore"):
+        z = np.maximum(np.float64(depth_scale) / d, 1e-9)
+    z[disp_map == 0] = 0.0
+    return z.astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# whole path (driver = python/depth_reprojection_pipe.py:121-167 up to the depth frame)
+# --------------------------------------------------------------------------------------
+def frame_disparity_map(tables: OracleTables, events, view: int, apply_polarity: bool = True, use_cv2: bool = True):
+    evs = polarity_mask(events) if apply_polarity else events
+    xcr, ycr = rectify_i16(tables, evs)
+    disp, mask = event_disparity(tables, xcr, ycr, np.asarray(evs["t"]))
+    if view == VIEW_CAMERA:
+        return scatter_camera_view(tables, evs, mask, disp)
+    rect = scatter_projector_view(tables, xcr, ycr, mask, disp)
+    return dilate_remap(tables, rect, use_cv2=use_cv2)
+
+
+def frame_depth(tables: OracleTables, events, view: int, apply_polarity: bool = True, use_cv2: bool = True):
+    """Polarity mask -> rectify -> X-map disparity -> scatter -> (dilate + remap) -> depth."""
+    return disparity_to_depth(
+        frame_disparity_map(tables, events, view, apply_polarity, use_cv2), tables.depth_scale
+    )
+
+
+# --------------------------------------------------------------------------------------
+# N1  colourise (tail of process_ev_frame)
+# --------------------------------------------------------------------------------------
+def clip_normalize_u8(depth: np.ndarray, z_near: float, z_far: float) -> np.ndarray:
+    """python/disp_to_depth.py:7-21.  Numba types ``(val - min) / range`` in float32 and the
+    following ``* 255`` (an int64 literal) in float64; the result is truncated to uint8."""
+    lo, hi = np.float32(z_near), np.float32(z_far)
+    rng = np.float32(hi - lo)
+    clipped = np.maximum(np.minimum(depth.astype(np.float32), hi), lo)
+    frac = ((clipped - lo) / rng).astype(np.float32)
+    val = frac.astype(np.float64) * 255.0
+    out = val.astype(np.int64).astype(np.uint8)
+    out[depth == 0] = 0
+    return out
+
+
+def turbo_lut_bgr() -> np.ndarray:
+    """256 x 3 uint8 BGR table of ``cv2.COLORMAP_TURBO`` (python/disp_to_depth.py:36)."""
+    import cv2
+
+    return cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), cv2.COLORMAP_TURBO).reshape(256, 3)
+
+
+def colorize(disp_map: np.ndarray, depth_scale: float, z_near: float, z_far: float) -> np.ndarray:
+    """python/disp_to_depth.py:99-115 (colorize_depth_from_disp) incl. apply_white_mask :24-31."""
+    u8 = clip_normalize_u8(disparity_to_depth(disp_map, depth_scale), z_near, z_far)
+    bgr = turbo_lut_bgr()[u8]
+    bgr[u8 == 0] = 255
+    return bgr
+
+
+# --------------------------------------------------------------------------------------
+# N3  setup-time tables the reference builds itself (no OpenCV involved)
+# --------------------------------------------------------------------------------------
+def linear_projector_time_map(proj_w: int, proj_h: int, scan_upwards: bool) -> np.ndarray:
+    """python/proj_time_map.py:6-19."""
+    ys, xs = np.mgrid[0:proj_h, 0:proj_w]
+    if scan_upwards:
+        ys = ys[::-1]
+    return ((xs * proj_h + ys) / (proj_w * proj_h)).astype(np.float32)
+
+
+def build_x_map(time_map: np.ndarray, x_map_width: int, t_px_scale: int, x_offset: int, num_scanlines: int):
+    """python/x_map.py:5-55 (compute_x_map_from_time_map).
+
+    For each (y, t_coord): argmin over x of |t - time_map[y, x]| in float64 (first minimum wins,
+    cells equal to 0 are undefined and skipped); accept only if the minimum is
+    <= 2 / num_scanlines.  ``t_coord == 0`` is skipped entirely.  Returns (x_map int16, t_diffs f32).
+    """
+    h, w = time_map.shape
+    x_map = np.zeros((h, x_map_width), dtype=np.int16)
+    t_diffs = np.zeros((h, x_map_width), dtype=np.float32)
+    max_t_diff = 2 / num_scanlines
+    tm = time_map.astype(np.float64)
+    undefined = time_map == 0
+    for t_coord in range(1, x_map_width):
+        t = t_coord / t_px_scale
+        if t == 0:
+            continue
+        diff = np.abs(t - tm)
+        diff[undefined] = np.inf
+        best = np.argmin(diff, axis=1)
+        best_val = diff[np.arange(h), best]
+        ok = np.isfinite(best_val) & (best_val <= max_t_diff)
+        x_map[ok, t_coord] = (best[ok] + x_offset).astype(np.int16)
+        t_diffs[ok, t_coord] = best_val[ok].astype(np.float32)
+    return x_map, t_diffs
+
+
+# --------------------------------------------------------------------------------------
+# seeded synthetic event generators shared by tests and bench
+# --------------------------------------------------------------------------------------
+def synth_events(seed: int, n: int, cam_w: int, cam_h: int, frame_us: int = 16666, p_on: float = 0.9, t0: int = 0):
+    """Uniform-pixel, time-sorted ("homogeneous Poisson conditioned on N") frame.  The draw order
+    is part of the contract: x, y, p, t."""
+    rng = np.random.default_rng(seed)
+    x = rng.integers(0, cam_w, n)
+    y = rng.integers(0, cam_h, n)
+    p = rng.random(n) < p_on
+    t = np.sort(rng.integers(0, frame_us, n))
+    ev = np.zeros(n, dtype=EVENT_DTYPE)
+    ev["x"], ev["y"], ev["p"], ev["t"] = x, y, p, t + t0
+    return ev
