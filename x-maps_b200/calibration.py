@@ -193,6 +193,8 @@ class CamProjMaps:
         """The device context holding this calibration's tables (created on first use)."""
         from .engine import DepthEngine, TableSet
 
+        if self._x_map is None:
+            raise RuntimeError("no X-map registered yet: construct XMapsDisparity(cam_proj_maps=...) first")
         if self._engine is None or (device is not None and self._engine.device_index != _dev_index(device)):
             t_px_scale, x_offset = self._x_map_consts if self._x_map_consts else (0, 0)
             tables = TableSet(
@@ -209,36 +211,102 @@ class CamProjMaps:
                 lut_y_f32=self.disp_cam_mapy_f32,
             )
             self._engine = DepthEngine(tables, device=device)
+            from .lazy import register_engine
+
+            register_engine(self._engine)
         return self._engine
 
     # ------------------------------------------------------------------ per-frame operators
+    def _ticket(self, events):
+        """Frame ticket for ``events`` (re-used while the same event object flows through the stages)."""
+        from .events import DeviceEvents
+        from .lazy import FrameTicket, as_device_events
+
+        last = getattr(self, "_last_ticket", None)
+        if last is not None and last[0] is events:
+            return last[1]
+        dev = events if isinstance(events, DeviceEvents) else as_device_events(events)
+        ticket = FrameTicket(self.engine(dev.device), dev)
+        self._last_ticket = (events, ticket)
+        return ticket
+
     def rectify_cam_coords_i16(self, events):
         """Reference :277-281.  Returns lazy device columns (x_rect, y_rect) bound to ``events``."""
-        from .lazy import as_device_events
+        from .lazy import DeviceArray
 
-        dev = as_device_events(events)
-        return self.engine(dev.device).rectify_i16(dev)
+        t = self._ticket(events)
+        n = len(t.events)
+        return (
+            DeviceArray(lambda: t.rect_i16()[0], length=n, ticket=t, role="x_rect_i16"),
+            DeviceArray(lambda: t.rect_i16()[1], length=n, ticket=t, role="y_rect_i16"),
+        )
 
     def rectify_cam_coords_f32(self, events):
         """Reference :272-275."""
-        from .lazy import as_device_events
+        from .lazy import DeviceArray
 
-        dev = as_device_events(events)
-        return self.engine(dev.device).rectify_f32(dev)
+        t = self._ticket(events)
+        cache = {}
+
+        def both():
+            if "v" not in cache:
+                cache["v"] = t.engine.rectify_f32(t.events)
+            return cache["v"]
+
+        n = len(t.events)
+        return (
+            DeviceArray(lambda: both()[0], length=n, ticket=t, role="x_rect_f32"),
+            DeviceArray(lambda: both()[1], length=n, ticket=t, role="y_rect_f32"),
+        )
 
     def compute_disp_map_projector_view(self, ev_x_rect_i16, ev_y_rect_i16, inlier_mask, ev_disparity_f32):
-        """Reference :299-303.  The arguments are the handles produced by
-        ``XMapsDisparity.compute_event_disparity``; the fused kernel scatters straight from the
-        event buffer, so they only identify the frame."""
-        return self.engine().disp_map_projector_view(ev_x_rect_i16, ev_y_rect_i16, inlier_mask, ev_disparity_f32)
+        """Reference :299-303.  With the handles produced by ``XMapsDisparity.compute_event_disparity``
+        nothing is computed yet (the fused kernel scatters straight from the event buffer);
+        with plain arrays the stage-by-stage kernels run."""
+        import torch
+
+        from .lazy import DeviceArray, LazyDispMap, to_tensor
+
+        ticket = getattr(ev_disparity_f32, "ticket", None)
+        if ticket is not None and getattr(ev_disparity_f32, "role", "") == "disparity":
+            return LazyDispMap(ticket, "rect")
+        eng = self.engine()
+        xr = to_tensor(ev_x_rect_i16, eng.device, torch.int16)
+        yr = to_tensor(ev_y_rect_i16, eng.device, torch.int16)
+        m = to_tensor(inlier_mask, eng.device).bool()
+        d = to_tensor(ev_disparity_f32, eng.device, torch.int16)
+        xpr = (xr[m] + d).to(torch.int16)
+        c = self.calib
+        return DeviceArray.of(eng.scatter_last_wins(yr[m].contiguous(), xpr.contiguous(), d, c.rect_image_height, c.rect_image_width))
 
     def compute_disp_map_camera_view(self, events, inlier_mask, ev_disparity_f32):
         """Reference :312-317."""
-        return self.engine().disp_map_camera_view(events, inlier_mask, ev_disparity_f32)
+        import torch
+
+        from .lazy import DeviceArray, LazyDispMap, to_tensor
+
+        ticket = getattr(ev_disparity_f32, "ticket", None)
+        if ticket is not None and getattr(ev_disparity_f32, "role", "") == "disparity":
+            return LazyDispMap(ticket, "cam")
+        t = self._ticket(events)
+        eng = t.engine
+        m = to_tensor(inlier_mask, eng.device).bool()
+        d = to_tensor(ev_disparity_f32, eng.device, torch.int16)
+        x = t.events["x"][m].to(torch.int16).contiguous()
+        y = t.events["y"][m].to(torch.int16).contiguous()
+        return DeviceArray.of(eng.scatter_last_wins(y, x, d, self.calib.camera_height, self.calib.camera_width))
 
     def construct_point_cloud(self, xpr_f32, ypr_f32, disp_f32):
         """Reference :319-331: ``Q @ [x + d, y, -d, 1]`` in float32, dehomogenised, y and z negated."""
-        return self.engine().point_cloud(xpr_f32, ypr_f32, disp_f32, self.Q)
+        import torch
+
+        from .lazy import DeviceArray, to_tensor
+
+        eng = self.engine()
+        x = to_tensor(xpr_f32, eng.device, torch.float32)
+        y = to_tensor(ypr_f32, eng.device, torch.float32)
+        d = to_tensor(disp_f32, eng.device, torch.float32)
+        return DeviceArray.of(eng.point_cloud(x, y, d, self.Q))
 
 
 def _dev_index(device):

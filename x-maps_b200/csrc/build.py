@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Build ``x-maps_b200/libxmaps_b200.so`` (the C-ABI library) for sm_100a with nvcc.
+
+    python x-maps_b200/csrc/build.py [--force] [--verbose]
+
+The library links the CUDA runtime statically and has no Python / torch dependency.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+OUT = os.path.join(PKG, "libxmaps_b200.so")
+SOURCES = ["xm_capi.cu"]
+DEPS = SOURCES + ["xm_device.cuh", "xm_frame_kernels.cuh", "xm_stage_kernels.cuh", os.path.join("..", "..", "include", "xmaps_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(os.path.join(HERE, d)) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    proc = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
+    if verbose or proc.returncode:
+        sys.stderr.write(proc.stdout + proc.stderr)
+    if proc.returncode:
+        raise RuntimeError("nvcc failed building libxmaps_b200.so")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

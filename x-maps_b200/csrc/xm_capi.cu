@@ -1,0 +1,819 @@
+// xm_capi.cu — C ABI of the B200-native X-maps depth path (include/xmaps_b200.h).
+//
+// Plain pointers and sizes only; no torch types.  The context owns device copies of the
+// calibration tables (re-packed for the kernels), the 64-bit scatter map and a small state block;
+// event buffers and outputs belong to the caller.  Every entry point returns a status code and
+// records a thread-local message for xm_last_error().
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/xmaps_b200.h"
+#include "xm_stage_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define XM_CUDA(expr)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e__ = (expr);                                                                           \
+        if (e__ != cudaSuccess) return fail(XM_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define XM_LAUNCHED()                                                                                   \
+    do {                                                                                                \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                             \
+        cudaError_t e__ = cudaGetLastError();                                                           \
+        if (e__ != cudaSuccess) return fail(XM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e__)); \
+    } while (0)
+
+// 256-entry BGR table of OpenCV's COLORMAP_TURBO is supplied by the host side at context creation
+// (xm_ctx_set_colormap); until then XM_OUT_BGR is refused.
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+struct XmCtx {
+    int device = 0;
+    int sm_count = 148;
+    int cam_w = 0, cam_h = 0, rect_w = 0, rect_h = 0, proj_w = 0, proj_h = 0;
+    int xmap_w = 0, xmap_h = 0, col_stride = 0, t_px_scale = 0, x_offset = 0, dilate = 7;
+    double depth_scale = 0.0;
+    int* d_lut_xy = nullptr;
+    float* d_lut_x_f32 = nullptr;
+    float* d_lut_y_f32 = nullptr;
+    short* d_xmap_t = nullptr;
+    short2* d_remap_xy = nullptr;
+    unsigned char* d_turbo = nullptr;
+    bool have_turbo = false;
+    unsigned long long* d_map = nullptr;
+    long long map_cells = 0;
+    xm::FrameState* d_state = nullptr;
+    unsigned epoch = 0;
+    // compaction scratch
+    unsigned* d_counts = nullptr;
+    long long counts_cap = 0;
+    // staging for xm_frame_host
+    void* d_stage_ev = nullptr;
+    long long stage_ev_cap = 0;
+    void* d_stage_out = nullptr;
+    long long stage_out_cap = 0;
+    // options
+    int opt_stage_xmap = 1;
+    int opt_auto_fixup = 1;
+    int opt_lookahead = 1;
+    int opt_ctas_per_sm = 0;  // 0 = occupancy query
+    int opt_smem_cols_bytes = 40 * 1024;
+    int opt_region_cells = 64 * 64;
+    // per-kernel CUDA-event timing (option "profile"): pairs around K1 and K2 of every frame
+    int opt_profile = 0;
+    std::vector<cudaEvent_t> prof_events;  // 3 per frame: before K1, after K1 (+ fix-up), after K2
+    size_t prof_used = 0;
+    double prof_k1_ms = 0.0, prof_k2_ms = 0.0;
+    long long prof_frames = 0;
+    // derived
+    int ev_occ_i64 = 0, ev_occ_f64 = 0;
+    int ev_smem = 0, cap_cols = 0;
+};
+
+namespace {
+
+unsigned next_epoch(XmCtx* c, unsigned count, cudaStream_t s, cudaError_t* err) {
+    // epochs live in the top 16 bits of a key; 0 means "never written".  On wrap the map is cleared.
+    *err = cudaSuccess;
+    if (c->epoch + count > 0xffffu) {
+        *err = cudaMemsetAsync(c->d_map, 0, static_cast<size_t>(c->map_cells) * 8, s);
+        c->epoch = 0;
+    }
+    unsigned e = c->epoch + 1;
+    c->epoch += count;
+    return e;
+}
+
+int configure_event_kernels(XmCtx* c) {
+    int cols = 0;
+    if (c->opt_stage_xmap && c->col_stride > 0) cols = c->opt_smem_cols_bytes / (c->col_stride * 2);
+    if (cols > c->xmap_w) cols = c->xmap_w;
+    c->cap_cols = cols;
+    c->ev_smem = 256 + cols * c->col_stride * 2;
+    XM_CUDA(cudaFuncSetAttribute(xm::events_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->ev_smem));
+    XM_CUDA(cudaFuncSetAttribute(xm::events_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->ev_smem));
+    XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ev_occ_i64, xm::events_kernel<false>, xm::kEvThreads, c->ev_smem));
+    XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ev_occ_f64, xm::events_kernel<true>, xm::kEvThreads, c->ev_smem));
+    if (c->ev_occ_i64 < 1 || c->ev_occ_f64 < 1) return fail(XM_ERR_UNSUPPORTED, "event kernel does not fit an SM (smem %d B)", c->ev_smem);
+    return XM_OK;
+}
+
+int upload_xmap(XmCtx* c, const int16_t* h_x_map, int rows, int cols, int t_px_scale, int x_offset) {
+    if (!h_x_map || rows <= 0 || cols <= 0) return fail(XM_ERR_INVALID_ARG, "x_map: bad shape %d x %d", rows, cols);
+    // asserts of the reference (x_maps_disparity.py:52-53)
+    if (rows > 32767) return fail(XM_ERR_TABLE_RANGE, "x_map has %d rows, int16 indices allow 32767", rows);
+    if (cols > 32767) return fail(XM_ERR_TABLE_RANGE, "x_map has %d time columns, int16 indices allow 32767", cols);
+    const int stride = (rows + 7) & ~7;  // 16-byte multiple: one column range = one bulk copy
+    std::vector<short> t(static_cast<size_t>(cols) * stride, 0);
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) t[static_cast<size_t>(x) * stride + y] = h_x_map[static_cast<size_t>(y) * cols + x];
+    if (c->d_xmap_t) cudaFree(c->d_xmap_t);
+    c->d_xmap_t = nullptr;
+    XM_CUDA(cudaMalloc(&c->d_xmap_t, t.size() * sizeof(short)));
+    XM_CUDA(cudaMemcpy(c->d_xmap_t, t.data(), t.size() * sizeof(short), cudaMemcpyHostToDevice));
+    c->xmap_w = cols;
+    c->xmap_h = rows;
+    c->col_stride = stride;
+    c->t_px_scale = t_px_scale;
+    c->x_offset = x_offset;
+    return configure_event_kernels(c);
+}
+
+int grid_for(long long n, int threads, int per_thread, int max_blocks) {
+    long long b = (n + static_cast<long long>(threads) * per_thread - 1) / (static_cast<long long>(threads) * per_thread);
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return static_cast<int>(b);
+}
+
+xm::OutputSpec make_output(const XmCtx* c, int kind, double depth_scale, float z_near, float z_far) {
+    xm::OutputSpec o;
+    o.kind = kind;
+    o.depth_scale = depth_scale;
+    o.z_near = z_near;
+    o.z_far = z_far;
+    o.turbo_bgr = c->d_turbo;
+    return o;
+}
+
+// Launches K0 for one frame.  `epoch` is the epoch K1 will use.
+int launch_bounds(XmCtx* c, const void* d_events, long long n, uint32_t flags, int time_bounds, long long t_min, long long t_max,
+                  unsigned epoch, cudaStream_t s) {
+    const int polarity = (flags & XM_FLAG_POLARITY) ? 1 : 0;
+    const bool f64 = (flags & XM_FLAG_TIME_F64) != 0;
+    const int4* ev = static_cast<const int4*>(d_events);
+    const int mode = time_bounds == XM_TBOUNDS_SORTED ? 0 : 1;
+    xm::bounds_init_kernel<<<1, 64, 0, s>>>(ev, n, polarity, mode, t_min, t_max, epoch, c->d_state);
+    XM_LAUNCHED();
+    if (time_bounds == XM_TBOUNDS_REDUCE) {
+        int grid = grid_for(n, 256, 8, c->sm_count * 8);
+        if (f64)
+            xm::bounds_reduce_kernel<true><<<grid, 256, 0, s>>>(ev, n, polarity, 0, c->d_state);
+        else
+            xm::bounds_reduce_kernel<false><<<grid, 256, 0, s>>>(ev, n, polarity, 0, c->d_state);
+        XM_LAUNCHED();
+    }
+    return XM_OK;
+}
+
+int check_frame_args(const XmCtx* c, const XmFrameArgs* a) {
+    if (!c || !a) return fail(XM_ERR_INVALID_ARG, "null context or arguments");
+    if (a->n_events < 0) return fail(XM_ERR_INVALID_ARG, "n_events = %lld", static_cast<long long>(a->n_events));
+    if (a->n_events > 0xffffffffLL) return fail(XM_ERR_UNSUPPORTED, "n_events = %lld exceeds 2^32 - 1 per frame", static_cast<long long>(a->n_events));
+    if (a->n_events > 0 && !a->d_events) return fail(XM_ERR_INVALID_ARG, "d_events is NULL");
+    if (reinterpret_cast<uintptr_t>(a->d_events) & 15) return fail(XM_ERR_INVALID_ARG, "d_events must be 16-byte aligned");
+    if (a->view != XM_VIEW_PROJECTOR && a->view != XM_VIEW_CAMERA) return fail(XM_ERR_INVALID_ARG, "unknown view %d", a->view);
+    if (a->time_bounds < XM_TBOUNDS_REDUCE || a->time_bounds > XM_TBOUNDS_GIVEN) return fail(XM_ERR_INVALID_ARG, "unknown time_bounds %d", a->time_bounds);
+    if (a->output < XM_OUT_DEPTH || a->output > XM_OUT_BGR) return fail(XM_ERR_INVALID_ARG, "unknown output %d", a->output);
+    if (a->flags & ~(XM_FLAG_POLARITY | XM_FLAG_TIME_F64)) return fail(XM_ERR_INVALID_ARG, "unknown flags 0x%x", a->flags);
+    if (!c->d_xmap_t) return fail(XM_ERR_NO_XMAP, "no X-map: supply XmTables.x_map or call xm_ctx_set_xmap");
+    if (a->view == XM_VIEW_PROJECTOR && !c->d_remap_xy) return fail(XM_ERR_INVALID_ARG, "projector view needs XmTables.remap_xy");
+    if (a->output == XM_OUT_BGR && !c->have_turbo) return fail(XM_ERR_INVALID_ARG, "XM_OUT_BGR needs a colour map (xm_ctx_set_colormap)");
+    return XM_OK;
+}
+
+// profile support: drain recorded event triples into the accumulators (synchronises)
+int profile_drain(XmCtx* c) {
+    for (size_t i = 0; i + 2 < c->prof_used + 0 && i + 2 < c->prof_events.size() + 0; i += 3) {
+        float a = 0.f, b = 0.f;
+        XM_CUDA(cudaEventSynchronize(c->prof_events[i + 2]));
+        XM_CUDA(cudaEventElapsedTime(&a, c->prof_events[i], c->prof_events[i + 1]));
+        XM_CUDA(cudaEventElapsedTime(&b, c->prof_events[i + 1], c->prof_events[i + 2]));
+        c->prof_k1_ms += a;
+        c->prof_k2_ms += b;
+        c->prof_frames += 1;
+    }
+    c->prof_used = 0;
+    return XM_OK;
+}
+
+int profile_mark(XmCtx* c, cudaStream_t s) {
+    if (c->prof_used == c->prof_events.size()) {
+        if (c->prof_events.size() >= 3 * 4096) {
+            int rc = profile_drain(c);
+            if (rc) return rc;
+        } else {
+            for (int i = 0; i < 3 * 64; ++i) {
+                cudaEvent_t e;
+                XM_CUDA(cudaEventCreate(&e));
+                c->prof_events.push_back(e);
+            }
+        }
+    }
+    XM_CUDA(cudaEventRecord(c->prof_events[c->prof_used++], s));
+    return XM_OK;
+}
+
+int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
+    if (!a->d_out) return fail(XM_ERR_INVALID_ARG, "d_out is NULL");
+    const bool f64 = (a->flags & XM_FLAG_TIME_F64) != 0;
+    const bool assumed = a->time_bounds != XM_TBOUNDS_REDUCE;
+    const bool fixup = assumed && c->opt_auto_fixup;
+    cudaError_t err;
+    const unsigned epoch = next_epoch(c, fixup ? 2u : 1u, s, &err);
+    XM_CUDA(err);
+
+    int rc = launch_bounds(c, a->d_events, a->n_events, a->flags, a->time_bounds, a->t_min, a->t_max, epoch, s);
+    if (rc) return rc;
+
+    xm::EventParams p;
+    p.events = static_cast<const int4*>(a->d_events);
+    p.n = a->n_events;
+    p.polarity = (a->flags & XM_FLAG_POLARITY) ? 1 : 0;
+    p.lut_xy = c->d_lut_xy;
+    p.cam_w = c->cam_w;
+    p.cam_h = c->cam_h;
+    p.xmap_t = c->d_xmap_t;
+    p.xmap_w = c->xmap_w;
+    p.xmap_h = c->xmap_h;
+    p.col_stride = c->col_stride;
+    p.t_px_scale = c->t_px_scale;
+    p.x_offset = c->x_offset;
+    p.rect_w = c->rect_w;
+    p.rect_h = c->rect_h;
+    p.view = a->view;
+    p.map = c->d_map;
+    p.epoch = epoch;
+    p.state = c->d_state;
+    p.cap_cols = c->cap_cols;
+    p.lookahead = c->opt_lookahead;
+    p.conditional = 0;
+    p.verify = assumed ? 1 : 0;
+    p.arm_fixup = fixup ? 1 : 0;
+
+    if (c->opt_profile) {
+        rc = profile_mark(c, s);
+        if (rc) return rc;
+    }
+    if (a->n_events > 0) {
+        const int occ = c->opt_ctas_per_sm > 0 ? c->opt_ctas_per_sm : (f64 ? c->ev_occ_f64 : c->ev_occ_i64);
+        const int grid = grid_for(a->n_events, xm::kEvThreads, xm::kEvPerThread, c->sm_count * occ);
+        if (f64)
+            xm::events_kernel<true><<<grid, xm::kEvThreads, c->ev_smem, s>>>(p);
+        else
+            xm::events_kernel<false><<<grid, xm::kEvThreads, c->ev_smem, s>>>(p);
+        XM_LAUNCHED();
+        if (fixup) {
+            // runs only if K1 found an event outside the assumed bounds (state->redo)
+            const int rgrid = grid_for(a->n_events, 256, 8, c->sm_count * 8);
+            if (f64)
+                xm::bounds_reduce_kernel<true><<<rgrid, 256, 0, s>>>(p.events, p.n, p.polarity, 1, c->d_state);
+            else
+                xm::bounds_reduce_kernel<false><<<rgrid, 256, 0, s>>>(p.events, p.n, p.polarity, 1, c->d_state);
+            XM_LAUNCHED();
+            p.conditional = 1;
+            p.verify = 0;
+            p.arm_fixup = 0;
+            p.epoch = epoch + 1;
+            if (f64)
+                xm::events_kernel<true><<<grid, xm::kEvThreads, c->ev_smem, s>>>(p);
+            else
+                xm::events_kernel<false><<<grid, xm::kEvThreads, c->ev_smem, s>>>(p);
+            XM_LAUNCHED();
+        }
+    }
+
+    if (c->opt_profile) {
+        rc = profile_mark(c, s);
+        if (rc) return rc;
+    }
+    xm::EpilogueParams q;
+    q.map = c->d_map;
+    q.state = c->d_state;
+    q.remap_xy = c->d_remap_xy;
+    q.rect_w = c->rect_w;
+    q.rect_h = c->rect_h;
+    q.radius = c->dilate / 2;
+    q.region_cap = c->opt_region_cells;
+    q.out = make_output(c, a->output, c->depth_scale, a->z_near, a->z_far);
+    q.dst = a->d_out;
+    if (a->view == XM_VIEW_CAMERA) {
+        q.out_w = c->cam_w;
+        q.out_h = c->cam_h;
+        const int grid = grid_for(static_cast<long long>(c->cam_w) * c->cam_h, 256, 2, c->sm_count * 8);
+        xm::epilogue_camera_kernel<<<grid, 256, 0, s>>>(q);
+    } else {
+        q.out_w = c->proj_w;
+        q.out_h = c->proj_h;
+        dim3 grid((c->proj_w + xm::kTile - 1) / xm::kTile, (c->proj_h + xm::kTile - 1) / xm::kTile);
+        xm::epilogue_projector_kernel<<<grid, 256, static_cast<size_t>(c->opt_region_cells) * 4, s>>>(q);
+    }
+    XM_LAUNCHED();
+    if (c->opt_profile) {
+        rc = profile_mark(c, s);
+        if (rc) return rc;
+    }
+    return XM_OK;
+}
+
+size_t output_bytes(const XmCtx* c, int view, int output) {
+    const size_t px = view == XM_VIEW_CAMERA ? static_cast<size_t>(c->cam_w) * c->cam_h : static_cast<size_t>(c->proj_w) * c->proj_h;
+    return output == XM_OUT_BGR ? px * 3 : px * 4;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int xm_abi_version(void) { return XM_ABI_VERSION; }
+const char* xm_last_error(void) { return g_last_error.c_str(); }
+int64_t xm_launch_count(void) { return g_launches.load(); }
+
+int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
+    if (!t || !out) return fail(XM_ERR_INVALID_ARG, "null tables or out pointer");
+    *out = nullptr;
+    if (t->cam_w <= 0 || t->cam_h <= 0 || t->rect_w <= 0 || t->rect_h <= 0)
+        return fail(XM_ERR_INVALID_ARG, "camera / rectified size must be positive");
+    if (!t->lut_x || !t->lut_y) return fail(XM_ERR_INVALID_ARG, "lut_x / lut_y are required");
+    if (t->remap_xy && (t->proj_w <= 0 || t->proj_h <= 0)) return fail(XM_ERR_INVALID_ARG, "projector size must be positive");
+    if (t->dilate < 1 || (t->dilate & 1) == 0 || t->dilate > 31) return fail(XM_ERR_INVALID_ARG, "dilate must be odd, 1..31");
+    if (t->rect_w > 32767 || t->rect_h > 32767) return fail(XM_ERR_TABLE_RANGE, "rectified image exceeds int16 coordinates");
+    int n_dev = 0;
+    XM_CUDA(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail(XM_ERR_INVALID_ARG, "device %d of %d", device, n_dev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(XM_ERR_CUDA, "cannot select device %d", device);
+
+    XmCtx* c = new XmCtx();
+    c->device = device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(XM_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    }
+    c->sm_count = prop.multiProcessorCount;
+    c->cam_w = t->cam_w;
+    c->cam_h = t->cam_h;
+    c->rect_w = t->rect_w;
+    c->rect_h = t->rect_h;
+    c->proj_w = t->proj_w;
+    c->proj_h = t->proj_h;
+    c->dilate = t->dilate;
+    c->depth_scale = t->depth_scale;
+
+    int rc = XM_OK;
+    auto bail = [&](int code) {
+        xm_ctx_destroy(c);
+        return code;
+    };
+    const size_t cam_px = static_cast<size_t>(t->cam_w) * t->cam_h;
+    {
+        std::vector<int> packed(cam_px);
+        for (size_t i = 0; i < cam_px; ++i)
+            packed[i] = static_cast<int>((static_cast<unsigned>(static_cast<unsigned short>(t->lut_y[i])) << 16) |
+                                         static_cast<unsigned short>(t->lut_x[i]));
+        if (cudaMalloc(&c->d_lut_xy, cam_px * 4) != cudaSuccess ||
+            cudaMemcpy(c->d_lut_xy, packed.data(), cam_px * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(XM_ERR_CUDA, "uploading the rectification LUT failed: %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    if (t->lut_x_f32 && t->lut_y_f32) {
+        if (cudaMalloc(&c->d_lut_x_f32, cam_px * 4) != cudaSuccess || cudaMalloc(&c->d_lut_y_f32, cam_px * 4) != cudaSuccess ||
+            cudaMemcpy(c->d_lut_x_f32, t->lut_x_f32, cam_px * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(c->d_lut_y_f32, t->lut_y_f32, cam_px * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(XM_ERR_CUDA, "uploading the float LUT failed: %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    if (t->remap_xy) {
+        const size_t bytes = static_cast<size_t>(t->proj_w) * t->proj_h * 4;
+        if (cudaMalloc(&c->d_remap_xy, bytes) != cudaSuccess ||
+            cudaMemcpy(c->d_remap_xy, t->remap_xy, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(XM_ERR_CUDA, "uploading the remap table failed: %s", cudaGetErrorString(cudaGetLastError())));
+    }
+    c->map_cells = static_cast<long long>(t->rect_w) * t->rect_h;
+    if (static_cast<long long>(cam_px) > c->map_cells) c->map_cells = static_cast<long long>(cam_px);
+    if (cudaMalloc(&c->d_map, static_cast<size_t>(c->map_cells) * 8) != cudaSuccess ||
+        cudaMemset(c->d_map, 0, static_cast<size_t>(c->map_cells) * 8) != cudaSuccess ||
+        cudaMalloc(&c->d_state, sizeof(xm::FrameState)) != cudaSuccess ||
+        cudaMemset(c->d_state, 0, sizeof(xm::FrameState)) != cudaSuccess || cudaMalloc(&c->d_turbo, 768) != cudaSuccess ||
+        cudaMemset(c->d_turbo, 0, 768) != cudaSuccess)
+        return bail(fail(XM_ERR_CUDA, "allocating the scatter map failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (t->x_map) {
+        if (t->xmap_w <= 0) return bail(fail(XM_ERR_INVALID_ARG, "xmap_w must be positive"));
+        rc = upload_xmap(c, t->x_map, t->rect_h, t->xmap_w, t->t_px_scale, t->x_offset);
+        if (rc) return bail(rc);
+    }
+    *out = c;
+    return XM_OK;
+}
+
+int xm_ctx_destroy(XmCtx* c) {
+    if (!c) return XM_OK;
+    DeviceGuard guard(c->device);
+    cudaFree(c->d_lut_xy);
+    cudaFree(c->d_lut_x_f32);
+    cudaFree(c->d_lut_y_f32);
+    cudaFree(c->d_xmap_t);
+    cudaFree(c->d_remap_xy);
+    cudaFree(c->d_turbo);
+    cudaFree(c->d_map);
+    cudaFree(c->d_state);
+    cudaFree(c->d_counts);
+    cudaFree(c->d_stage_ev);
+    cudaFree(c->d_stage_out);
+    for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+    delete c;
+    return XM_OK;
+}
+
+int xm_ctx_set_xmap(XmCtx* c, const int16_t* h_x_map, int32_t rows, int32_t cols, int32_t t_px_scale, int32_t x_offset) {
+    if (!c) return fail(XM_ERR_INVALID_ARG, "null context");
+    DeviceGuard guard(c->device);
+    XM_CUDA(cudaDeviceSynchronize());
+    return upload_xmap(c, h_x_map, rows, cols, t_px_scale, x_offset);
+}
+
+int xm_ctx_set_colormap(XmCtx* c, const uint8_t* h_bgr256) {
+    if (!c || !h_bgr256) return fail(XM_ERR_INVALID_ARG, "null context or table");
+    DeviceGuard guard(c->device);
+    XM_CUDA(cudaMemcpy(c->d_turbo, h_bgr256, 768, cudaMemcpyHostToDevice));
+    c->have_turbo = true;
+    return XM_OK;
+}
+
+int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
+    if (!c || !key) return fail(XM_ERR_INVALID_ARG, "null context or key");
+    DeviceGuard guard(c->device);
+    const int v = static_cast<int>(value);
+    if (!strcmp(key, "stage_xmap")) {
+        c->opt_stage_xmap = v != 0;
+        return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
+    }
+    if (!strcmp(key, "smem_cols_bytes")) {
+        if (v < 0 || v > 200 * 1024) return fail(XM_ERR_INVALID_ARG, "smem_cols_bytes out of range");
+        c->opt_smem_cols_bytes = v;
+        return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
+    }
+    if (!strcmp(key, "auto_fixup")) {
+        c->opt_auto_fixup = v != 0;
+        return XM_OK;
+    }
+    if (!strcmp(key, "lookahead")) {
+        if (v < 0) return fail(XM_ERR_INVALID_ARG, "lookahead must be >= 0");
+        c->opt_lookahead = v;
+        return XM_OK;
+    }
+    if (!strcmp(key, "ctas_per_sm")) {
+        if (v < 0 || v > 32) return fail(XM_ERR_INVALID_ARG, "ctas_per_sm out of range");
+        c->opt_ctas_per_sm = v;
+        return XM_OK;
+    }
+    if (!strcmp(key, "profile")) { /* 1: time K1 / K2 of every frame with CUDA events; 0: stop; -1: reset */
+        int rc = profile_drain(c);
+        if (rc) return rc;
+        if (v < 0) {
+            c->prof_k1_ms = c->prof_k2_ms = 0.0;
+            c->prof_frames = 0;
+        } else {
+            c->opt_profile = v != 0;
+        }
+        return XM_OK;
+    }
+    if (!strcmp(key, "epoch")) { /* test hook: jump the scatter-map epoch (e.g. next to the 16-bit wrap) */
+        if (v < 0 || v > 0xffff) return fail(XM_ERR_INVALID_ARG, "epoch out of range");
+        XM_CUDA(cudaDeviceSynchronize());
+        XM_CUDA(cudaMemset(c->d_map, 0, static_cast<size_t>(c->map_cells) * 8));
+        c->epoch = static_cast<unsigned>(v);
+        return XM_OK;
+    }
+    if (!strcmp(key, "region_cells")) {
+        if (v < 0 || v > 48 * 1024 / 4) return fail(XM_ERR_INVALID_ARG, "region_cells out of range");
+        c->opt_region_cells = v;
+        return XM_OK;
+    }
+    return fail(XM_ERR_INVALID_ARG, "unknown option '%s'", key);
+}
+
+int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
+    if (!c || !key || !value) return fail(XM_ERR_INVALID_ARG, "null argument");
+    if (!strcmp(key, "stage_xmap")) *value = c->opt_stage_xmap;
+    else if (!strcmp(key, "smem_cols_bytes")) *value = c->opt_smem_cols_bytes;
+    else if (!strcmp(key, "auto_fixup")) *value = c->opt_auto_fixup;
+    else if (!strcmp(key, "lookahead")) *value = c->opt_lookahead;
+    else if (!strcmp(key, "ctas_per_sm")) *value = c->opt_ctas_per_sm;
+    else if (!strcmp(key, "region_cells")) *value = c->opt_region_cells;
+    else if (!strcmp(key, "epoch")) *value = c->epoch;
+    else if (!strcmp(key, "profile")) *value = c->opt_profile;
+    else if (!strcmp(key, "profile_k1_ns") || !strcmp(key, "profile_k2_ns") || !strcmp(key, "profile_frames")) {
+        DeviceGuard guard(c->device);
+        int rc = profile_drain(c); /* synchronises on the recorded events */
+        if (rc) return rc;
+        if (key[9] == '1') *value = static_cast<int64_t>(c->prof_k1_ms * 1e6);
+        else if (key[9] == '2') *value = static_cast<int64_t>(c->prof_k2_ms * 1e6);
+        else *value = c->prof_frames;
+    }
+    else if (!strcmp(key, "cap_cols")) *value = c->cap_cols;          /* read-only, derived */
+    else if (!strcmp(key, "occupancy")) *value = c->ev_occ_i64;       /* read-only, derived */
+    else if (!strcmp(key, "sm_count")) *value = c->sm_count;          /* read-only */
+    else if (!strcmp(key, "event_smem_bytes")) *value = c->ev_smem;   /* read-only, derived */
+    else return fail(XM_ERR_INVALID_ARG, "unknown option '%s'", key);
+    return XM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int xm_frame(XmCtx* c, const XmFrameArgs* a, void* stream) {
+    int rc = check_frame_args(c, a);
+    if (rc) return rc;
+    DeviceGuard guard(c->device);
+    return frame_impl(c, a, static_cast<cudaStream_t>(stream));
+}
+
+int xm_frame_batch(XmCtx* c, const XmFrameArgs* a, int32_t n_frames, void* stream) {
+    if (n_frames < 0 || (n_frames > 0 && !a)) return fail(XM_ERR_INVALID_ARG, "bad batch");
+    for (int i = 0; i < n_frames; ++i) {
+        int rc = check_frame_args(c, a + i);
+        if (rc) return rc;
+    }
+    DeviceGuard guard(c->device);
+    for (int i = 0; i < n_frames; ++i) {
+        int rc = frame_impl(c, a + i, static_cast<cudaStream_t>(stream));
+        if (rc) return rc;
+    }
+    return XM_OK;
+}
+
+int xm_frame_status(XmCtx* c, XmFrameStatus* h, void* stream) {
+    if (!c || !h) return fail(XM_ERR_INVALID_ARG, "null context or status");
+    DeviceGuard guard(c->device);
+    xm::FrameState st;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    XM_CUDA(cudaMemcpyAsync(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost, s));
+    XM_CUDA(cudaStreamSynchronize(s));
+    h->n_events = 0;
+    h->n_valid = static_cast<int64_t>(st.n_valid);
+    h->n_inliers = static_cast<int64_t>(st.n_inliers);
+    h->t_min = st.t_lo_bits;
+    h->t_max = st.t_hi_bits;
+    h->flags = st.flags;
+    h->epoch = st.epoch_used;
+    h->fixup_ran = st.redo;
+    return XM_OK;
+}
+
+int xm_frame_host(XmCtx* c, const XmFrameArgs* a, const void* h_events, void* h_out, XmFrameStatus* h_status, void* stream) {
+    if (!c || !a) return fail(XM_ERR_INVALID_ARG, "null context or arguments");
+    if (a->n_events < 0 || (a->n_events > 0 && !h_events) || !h_out) return fail(XM_ERR_INVALID_ARG, "null host buffer");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long ev_bytes = static_cast<long long>(a->n_events) * 16;
+    if (ev_bytes > c->stage_ev_cap) {
+        XM_CUDA(cudaStreamSynchronize(s));
+        cudaFree(c->d_stage_ev);
+        c->d_stage_ev = nullptr;
+        c->stage_ev_cap = 0;
+        XM_CUDA(cudaMalloc(&c->d_stage_ev, static_cast<size_t>(ev_bytes)));
+        c->stage_ev_cap = ev_bytes;
+    }
+    const long long out_bytes = static_cast<long long>(output_bytes(c, a->view == XM_VIEW_CAMERA ? XM_VIEW_CAMERA : XM_VIEW_PROJECTOR, a->output));
+    if (out_bytes > c->stage_out_cap) {
+        XM_CUDA(cudaStreamSynchronize(s));
+        cudaFree(c->d_stage_out);
+        c->d_stage_out = nullptr;
+        c->stage_out_cap = 0;
+        XM_CUDA(cudaMalloc(&c->d_stage_out, static_cast<size_t>(out_bytes)));
+        c->stage_out_cap = out_bytes;
+    }
+    XmFrameArgs dev = *a;
+    dev.d_events = c->d_stage_ev ? c->d_stage_ev : reinterpret_cast<const void*>(16);
+    dev.d_out = c->d_stage_out;
+    int rc = check_frame_args(c, &dev);
+    if (rc) return rc;
+    if (ev_bytes) XM_CUDA(cudaMemcpyAsync(c->d_stage_ev, h_events, static_cast<size_t>(ev_bytes), cudaMemcpyHostToDevice, s));
+    rc = frame_impl(c, &dev, s);
+    if (rc) return rc;
+    XM_CUDA(cudaMemcpyAsync(h_out, c->d_stage_out, static_cast<size_t>(out_bytes), cudaMemcpyDeviceToHost, s));
+    if (h_status) {
+        rc = xm_frame_status(c, h_status, stream);
+        if (rc) return rc;
+        h_status->n_events = a->n_events;
+    } else {
+        XM_CUDA(cudaStreamSynchronize(s));
+    }
+    return XM_OK;
+}
+
+int xm_host_alloc(void** h_ptr, int64_t bytes) {
+    if (!h_ptr || bytes < 0) return fail(XM_ERR_INVALID_ARG, "bad host allocation request");
+    XM_CUDA(cudaHostAlloc(h_ptr, static_cast<size_t>(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+    return XM_OK;
+}
+int xm_host_free(void* h_ptr) {
+    if (h_ptr) XM_CUDA(cudaFreeHost(h_ptr));
+    return XM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage-by-stage entry points
+// ---------------------------------------------------------------------------------------------
+int xm_rectify_i16(XmCtx* c, const void* d_events, int64_t n, int16_t* d_x, int16_t* d_y, void* stream) {
+    if (!c || n < 0 || (n > 0 && (!d_events || !d_x || !d_y))) return fail(XM_ERR_INVALID_ARG, "rectify_i16: bad arguments");
+    if (n == 0) return XM_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    xm::rectify_i16_kernel<<<grid_for(n, 256, 4, c->sm_count * 8), 256, 0, s>>>(static_cast<const int4*>(d_events), n, c->d_lut_xy,
+                                                                                c->cam_w, c->cam_h, d_x, d_y, c->d_state);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
+int xm_rectify_f32(XmCtx* c, const void* d_events, int64_t n, float* d_x, float* d_y, void* stream) {
+    if (!c || n < 0 || (n > 0 && (!d_events || !d_x || !d_y))) return fail(XM_ERR_INVALID_ARG, "rectify_f32: bad arguments");
+    if (!c->d_lut_x_f32) return fail(XM_ERR_INVALID_ARG, "rectify_f32 needs XmTables.lut_x_f32 / lut_y_f32");
+    if (n == 0) return XM_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    xm::rectify_f32_kernel<<<grid_for(n, 256, 4, c->sm_count * 8), 256, 0, s>>>(
+        static_cast<const int4*>(d_events), n, c->d_lut_x_f32, c->d_lut_y_f32, c->cam_w, c->cam_h, d_x, d_y, c->d_state);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
+int xm_event_disparity(XmCtx* c, const XmFrameArgs* a, const int16_t* d_x_rect, const int16_t* d_y_rect, int16_t* d_disp_full,
+                       uint8_t* d_mask, void* stream) {
+    if (!c || !a) return fail(XM_ERR_INVALID_ARG, "null context or arguments");
+    if (a->n_events < 0 || (a->n_events > 0 && (!a->d_events || !d_disp_full || !d_mask)))
+        return fail(XM_ERR_INVALID_ARG, "event_disparity: bad arguments");
+    if ((d_x_rect == nullptr) != (d_y_rect == nullptr)) return fail(XM_ERR_INVALID_ARG, "give both or neither of d_x_rect / d_y_rect");
+    if (a->time_bounds < XM_TBOUNDS_REDUCE || a->time_bounds > XM_TBOUNDS_GIVEN) return fail(XM_ERR_INVALID_ARG, "unknown time_bounds");
+    if (!c->d_xmap_t) return fail(XM_ERR_NO_XMAP, "no X-map");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = launch_bounds(c, a->d_events, a->n_events, a->flags, a->time_bounds, a->t_min, a->t_max, c->epoch, s);
+    if (rc) return rc;
+    if (a->n_events == 0) return XM_OK;
+    xm::DisparityParams p;
+    p.events = static_cast<const int4*>(a->d_events);
+    p.n = a->n_events;
+    p.polarity = (a->flags & XM_FLAG_POLARITY) ? 1 : 0;
+    p.lut_xy = c->d_lut_xy;
+    p.cam_w = c->cam_w;
+    p.cam_h = c->cam_h;
+    p.x_rect = d_x_rect;
+    p.y_rect = d_y_rect;
+    p.xmap_t = c->d_xmap_t;
+    p.xmap_w = c->xmap_w;
+    p.xmap_h = c->xmap_h;
+    p.col_stride = c->col_stride;
+    p.t_px_scale = c->t_px_scale;
+    p.x_offset = c->x_offset;
+    p.disp_full = d_disp_full;
+    p.mask = d_mask;
+    p.state = c->d_state;
+    p.verify = a->time_bounds != XM_TBOUNDS_REDUCE;
+    const int grid = grid_for(a->n_events, 256, 4, c->sm_count * 8);
+    if (a->flags & XM_FLAG_TIME_F64)
+        xm::event_disparity_kernel<true><<<grid, 256, 0, s>>>(p);
+    else
+        xm::event_disparity_kernel<false><<<grid, 256, 0, s>>>(p);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
+int xm_compact_i16(XmCtx* c, const int16_t* d_vals, const uint8_t* d_mask, int64_t n, int16_t* d_out, int64_t* d_count, void* stream) {
+    if (!c || n < 0 || !d_count || (n > 0 && (!d_vals || !d_mask || !d_out))) return fail(XM_ERR_INVALID_ARG, "compact: bad arguments");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n == 0) {
+        XM_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
+        return XM_OK;
+    }
+    const long long blocks = (n + xm::kCompactBlock - 1) / xm::kCompactBlock;
+    if (blocks > c->counts_cap) {
+        XM_CUDA(cudaStreamSynchronize(s));
+        cudaFree(c->d_counts);
+        c->d_counts = nullptr;
+        c->counts_cap = 0;
+        XM_CUDA(cudaMalloc(&c->d_counts, static_cast<size_t>(blocks) * 4));
+        c->counts_cap = blocks;
+    }
+    xm::compact_count_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(d_mask, n, c->d_counts);
+    XM_LAUNCHED();
+    xm::compact_scan_kernel<<<1, 1024, 0, s>>>(c->d_counts, blocks, reinterpret_cast<long long*>(d_count));
+    XM_LAUNCHED();
+    xm::compact_write_kernel<short><<<static_cast<unsigned>(blocks), 256, 0, s>>>(d_vals, d_mask, n, c->d_counts, d_out);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
+int xm_scatter_last_wins(XmCtx* c, const int16_t* d_rows, const int16_t* d_cols, const int16_t* d_vals, int64_t n, int32_t h,
+                         int32_t w, float* d_map, void* stream) {
+    if (!c || n < 0 || h <= 0 || w <= 0 || !d_map || (n > 0 && (!d_rows || !d_cols || !d_vals)))
+        return fail(XM_ERR_INVALID_ARG, "scatter: bad arguments");
+    if (static_cast<long long>(h) * w > c->map_cells) return fail(XM_ERR_UNSUPPORTED, "scatter target %d x %d exceeds the context's map", h, w);
+    if (n > 0xffffffffLL) return fail(XM_ERR_UNSUPPORTED, "more than 2^32 - 1 values");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t err;
+    const unsigned epoch = next_epoch(c, 1, s, &err);
+    XM_CUDA(err);
+    if (n > 0) {
+        xm::scatter_keys_kernel<<<grid_for(n, 256, 4, c->sm_count * 8), 256, 0, s>>>(d_rows, d_cols, d_vals, n, h, w, c->d_map, epoch,
+                                                                                    c->d_state);
+        XM_LAUNCHED();
+    }
+    const long long cells = static_cast<long long>(h) * w;
+    xm::decode_map_kernel<<<grid_for(cells, 256, 4, c->sm_count * 8), 256, 0, s>>>(c->d_map, cells, epoch, d_map);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
+int xm_dilate_remap(XmCtx* c, const float* d_rect_map, float* d_proj_map, void* stream) {
+    if (!c || !d_rect_map || !d_proj_map) return fail(XM_ERR_INVALID_ARG, "dilate_remap: bad arguments");
+    if (!c->d_remap_xy) return fail(XM_ERR_INVALID_ARG, "dilate_remap needs XmTables.remap_xy");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long n = static_cast<long long>(c->proj_w) * c->proj_h;
+    xm::dilate_remap_kernel<<<grid_for(n, 256, 1, c->sm_count * 16), 256, 0, s>>>(d_rect_map, c->rect_w, c->rect_h, c->d_remap_xy,
+                                                                                 c->proj_w, c->proj_h, c->dilate / 2, d_proj_map);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
+int xm_disp_to_depth(XmCtx* c, const float* d_disp, int64_t n, double depth_scale, float* d_depth, void* stream) {
+    if (!c || n < 0 || (n > 0 && (!d_disp || !d_depth))) return fail(XM_ERR_INVALID_ARG, "disp_to_depth: bad arguments");
+    if (n == 0) return XM_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    xm::convert_kernel<<<grid_for(n, 256, 4, c->sm_count * 8), 256, 0, s>>>(d_disp, n, make_output(c, XM_OUT_DEPTH, depth_scale, 0.f, 0.f),
+                                                                            d_depth);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
+int xm_colorize(XmCtx* c, const float* d_disp, int64_t n, double depth_scale, float z_near, float z_far, uint8_t* d_bgr, void* stream) {
+    if (!c || n < 0 || (n > 0 && (!d_disp || !d_bgr))) return fail(XM_ERR_INVALID_ARG, "colorize: bad arguments");
+    if (!c->have_turbo) return fail(XM_ERR_INVALID_ARG, "colorize needs a colour map (xm_ctx_set_colormap)");
+    if (n == 0) return XM_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    xm::convert_kernel<<<grid_for(n, 256, 4, c->sm_count * 8), 256, 0, s>>>(d_disp, n, make_output(c, XM_OUT_BGR, depth_scale, z_near, z_far),
+                                                                            d_bgr);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
+int xm_point_cloud(XmCtx* c, const float* d_x, const float* d_y, const float* d_disp, int64_t n, const double* h_Q, float* d_xyz,
+                   void* stream) {
+    if (!c || n < 0 || !h_Q || (n > 0 && (!d_x || !d_y || !d_disp || !d_xyz))) return fail(XM_ERR_INVALID_ARG, "point_cloud: bad arguments");
+    if (n == 0) return XM_OK;
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    xm::Mat4f q;
+    for (int i = 0; i < 16; ++i) q.m[i] = static_cast<float>(h_Q[i]);
+    xm::point_cloud_kernel<<<grid_for(n, 256, 4, c->sm_count * 8), 256, 0, s>>>(d_x, d_y, d_disp, n, q, d_xyz);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
+int xm_build_xmap(int device, const float* d_time_map, int32_t h, int32_t w, int32_t x_map_width, int32_t t_px_scale, int32_t x_offset,
+                  int32_t num_scanlines, int16_t* d_x_map, float* d_t_diffs, void* stream) {
+    if (!d_time_map || !d_x_map || h <= 0 || w <= 0 || x_map_width <= 0 || t_px_scale <= 0 || num_scanlines <= 0)
+        return fail(XM_ERR_INVALID_ARG, "build_xmap: bad arguments");
+    // asserts of the reference (x_maps_disparity.py:52-53)
+    if (h > 32767 || w + x_offset > 32767) return fail(XM_ERR_TABLE_RANGE, "time map %d x %d (+%d) exceeds int16", h, w, x_offset);
+    if (static_cast<size_t>(w) * 4 > 200 * 1024) return fail(XM_ERR_UNSUPPORTED, "time-map row of %d floats exceeds shared memory", w);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(XM_ERR_CUDA, "cannot select device %d", device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    XM_CUDA(cudaFuncSetAttribute(xm::build_xmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w * 4));
+    xm::build_xmap_kernel<<<h, 256, static_cast<size_t>(w) * 4, s>>>(d_time_map, h, w, x_map_width, t_px_scale, x_offset, num_scanlines,
+                                                                    d_x_map, d_t_diffs);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
+}  // extern "C"

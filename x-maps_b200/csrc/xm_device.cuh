@@ -1,0 +1,208 @@
+// xm_device.cuh — device-side building blocks shared by the X-maps kernels (sm_100a).
+//
+// Everything here is integer / IEEE-exact arithmetic: the path must reproduce the reference's
+// NumPy results bit for bit, so no fast-math, explicit _rn intrinsics where a
+// fused multiply-add could otherwise be contracted.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xm {
+
+// ---------------------------------------------------------------------------------------------
+// Event record: Metavision EventCD, 16-byte AoS, read as one int4.
+//   .x = x | y << 16     .y = p (low 16 bits) | pad     .z/.w = t (int64 or float64, little endian)
+// ---------------------------------------------------------------------------------------------
+struct EventFields {
+    unsigned x, y;
+    int p;
+    long long t_bits;
+};
+
+__device__ __forceinline__ EventFields unpack_event(const int4& r) {
+    EventFields e;
+    e.x = static_cast<unsigned>(r.x) & 0xffffu;
+    e.y = static_cast<unsigned>(r.x) >> 16;
+    e.p = static_cast<int>(static_cast<short>(r.y & 0xffff));
+    e.t_bits = (static_cast<long long>(r.w) << 32) | static_cast<unsigned>(r.z);
+    return e;
+}
+
+// Streaming 128-bit load: read-only path, do not allocate in L1, evict-first in L2 so the
+// event stream (80 MB / frame) does not push the tables and the scatter map out of the 126 MB L2.
+__device__ __forceinline__ uint64_t make_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ int4 ld_event_stream(const int4* p, uint64_t policy) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(policy));
+    return r;
+}
+
+__device__ __forceinline__ int4 ld_event_plain(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Time bounds.  For float64 timestamps the bounds are kept as "sortable" int64 so that the same
+// integer atomics implement min / max (IEEE order == integer order after this mapping).
+// ---------------------------------------------------------------------------------------------
+__device__ __host__ __forceinline__ long long f64_bits_to_sortable(long long b) {
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __host__ __forceinline__ long long sortable_to_f64_bits(long long s) {
+    return s ^ ((s >> 63) & 0x7fffffffffffffffLL);
+}
+
+// Normalisation constants of one frame (python/x_maps_disparity.py:12-19).
+template <bool F64>
+struct TimeNorm {
+    long long lo_i;  // int64 mode
+    long long hi_i;
+    double lo_f;     // float64 mode
+    double hi_f;
+    double den;      // (max_t - min_t) as float64
+    double scale;    // T_PX_SCALE
+
+    __device__ __forceinline__ void init(long long lo_bits, long long hi_bits, int t_px_scale) {
+        scale = static_cast<double>(t_px_scale);
+        if (F64) {
+            lo_f = __longlong_as_double(lo_bits);
+            hi_f = __longlong_as_double(hi_bits);
+            den = __dsub_rn(hi_f, lo_f);
+            lo_i = hi_i = 0;
+        } else {
+            lo_i = lo_bits;
+            hi_i = hi_bits;
+            den = static_cast<double>(hi_bits - lo_bits);
+            lo_f = hi_f = 0.0;
+        }
+    }
+
+    // true if t lies outside [lo, hi] (only possible when the bounds were assumed, not reduced)
+    __device__ __forceinline__ bool outside(long long t_bits) const {
+        if (F64) {
+            double t = __longlong_as_double(t_bits);
+            return !(t >= lo_f && t <= hi_f);
+        }
+        return t_bits < lo_i || t_bits > hi_i;
+    }
+
+    // int16(rint(((t - min) / (max - min)) * T_PX_SCALE)) in float64, two roundings, half-even.
+    // 0/0 (all timestamps equal) is NaN in NumPy and casts to 0.
+    __device__ __forceinline__ int column(long long t_bits) const {
+        double num = F64 ? __dsub_rn(__longlong_as_double(t_bits), lo_f) : static_cast<double>(t_bits - lo_i);
+        double r = rint(__dmul_rn(__ddiv_rn(num, den), scale));
+        if (!(r == r)) return 0;
+        // clamp only guards memory safety for flagged (out-of-bounds) events
+        r = fmin(fmax(r, -32768.0), 32767.0);
+        return static_cast<int>(r);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Scatter keys: the reference's `map[rows, cols] = vals` keeps the LAST duplicate.  Each event
+// contributes key = epoch:16 | event_index:32 | disparity:16 and the map keeps the maximum, i.e.
+// the highest event index of the current frame; older frames (lower epoch) lose automatically,
+// so the map never has to be cleared between frames.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long make_key(unsigned epoch, unsigned long long index, int disp) {
+    return (static_cast<unsigned long long>(epoch) << 48) | ((index & 0xffffffffULL) << 16) |
+           static_cast<unsigned long long>(static_cast<unsigned>(disp) & 0xffffu);
+}
+
+__device__ __forceinline__ int key_disparity(unsigned long long key, unsigned epoch) {
+    return (static_cast<unsigned>(key >> 48) == epoch) ? static_cast<int>(key & 0xffffULL) : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Output conversions (python/disp_to_depth.py)
+// ---------------------------------------------------------------------------------------------
+// disparity_to_depth_rectified :46-63 — float64 divide, float64 max, one rounding to float32.
+__device__ __forceinline__ float disparity_to_depth(float d, double depth_scale) {
+    if (d == 0.0f) return 0.0f;
+    return __double2float_rn(fmax(__ddiv_rn(depth_scale, static_cast<double>(d)), 1e-9));
+}
+
+// clip_normalize_uint8_depth_frame :7-21 — float32 clip / subtract / divide, float64 * 255, truncate.
+__device__ __forceinline__ unsigned depth_to_u8(float depth, float z_near, float z_far) {
+    if (depth == 0.0f) return 0u;
+    float v = fmaxf(fminf(depth, z_far), z_near);
+    float frac = __fdiv_rn(__fsub_rn(v, z_near), __fsub_rn(z_far, z_near));
+    double scaled = __dmul_rn(static_cast<double>(frac), 255.0);
+    return static_cast<unsigned>(static_cast<int>(scaled)) & 0xffu;
+}
+
+struct OutputSpec {
+    int kind;            // XM_OUT_*
+    double depth_scale;  // P2[0,3]
+    float z_near, z_far;
+    const unsigned char* turbo_bgr;  // [256][3]
+};
+
+// Writes one pixel of the frame from an integer-valued disparity.
+__device__ __forceinline__ void emit_pixel(const OutputSpec& o, void* out, long long idx, float disp) {
+    if (o.kind == 1) {  // XM_OUT_DISPARITY
+        static_cast<float*>(out)[idx] = disp;
+    } else if (o.kind == 0) {  // XM_OUT_DEPTH
+        static_cast<float*>(out)[idx] = disparity_to_depth(disp, o.depth_scale);
+    } else {  // XM_OUT_BGR: TURBO colour map, white where there is no depth (:24-43)
+        unsigned u = depth_to_u8(disparity_to_depth(disp, o.depth_scale), o.z_near, o.z_far);
+        unsigned char* px = static_cast<unsigned char*>(out) + idx * 3;
+        if (u == 0u) {
+            px[0] = 255; px[1] = 255; px[2] = 255;
+        } else {
+            px[0] = o.turbo_bgr[u * 3 + 0];
+            px[1] = o.turbo_bgr[u * 3 + 1];
+            px[2] = o.turbo_bgr[u * 3 + 2];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk async copy (TMA) helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "XM_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra XM_DONE_%=;\n\t"
+        "bra XM_WAIT_%=;\n\t"
+        "XM_DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion signalled on the mbarrier (bytes % 16 == 0, 16 B aligned)
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+}  // namespace xm

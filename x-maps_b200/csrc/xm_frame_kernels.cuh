@@ -1,0 +1,496 @@
+// xm_frame_kernels.cuh — the per-frame hot path as sm_100a kernels.
+//
+//   K0  bounds_*        t.min() / t.max() of the polarity-masked events          (x_maps_disparity.py:12-13)
+//   K1  events_kernel   polarity mask -> rectify LUT -> time column -> X-map lookup -> disparity ->
+//                       last-write-wins scatter as a 64-bit atomicMax            (depth_reprojection_pipe.py:114,128,142,150-160)
+//   K2  epilogue_*      [7x7 dilate + nearest remap] -> depth / disparity / BGR  (disp_to_depth.py:46-115)
+//
+// Data layout in HBM (all owned by the context):
+//   lut_xy    int32 [cam_h * cam_w]        low 16 bits = x_rect, high 16 bits = y_rect (one gather per event)
+//   xmap_t    int16 [xmap_w][col_stride]   the X-map TRANSPOSED: one time column is contiguous, so the
+//                                          columns a time-sorted chunk of events needs are ONE contiguous
+//                                          range that a single 1-D bulk (TMA) copy stages into shared memory
+//   remap_xy  int16 [proj_h * proj_w][2]   (x_rect, y_rect) of every projector pixel
+//   map       u64   [max(rect, cam) cells] scatter keys  epoch:16 | event index:32 | disparity:16
+#pragma once
+#include "xm_device.cuh"
+
+namespace xm {
+
+// Device-resident per-context state block (mirrored to XmFrameStatus by xm_frame_status).
+struct FrameState {
+    long long t_lo_bits;  // bounds in use: int64, or float64 bit pattern
+    long long t_hi_bits;
+    long long red_lo;     // reduction scratch, "sortable" domain
+    long long red_hi;
+    unsigned long long n_valid;
+    unsigned long long n_inliers;
+    unsigned int flags;       // XM_STATUS_*
+    unsigned int redo;        // 1: the optimistic bounds were wrong, the fix-up pass is running / ran
+    unsigned int epoch_used;  // epoch whose keys the epilogue must read
+    unsigned int blocks_done; // last-block detection
+    unsigned int any_valid;   // reduction saw at least one valid event
+    unsigned int pad;
+};
+
+constexpr unsigned kStatusTBounds = 0x1u;
+constexpr unsigned kStatusPixelOob = 0x2u;
+constexpr unsigned kStatusScatterOob = 0x4u;
+
+constexpr int kEvThreads = 256;  // threads per CTA of the event kernels
+constexpr int kEvPerThread = 4;  // events per thread per chunk (independent 128-bit loads in flight)
+constexpr int kEvChunk = kEvThreads * kEvPerThread;
+
+struct EventParams {
+    const int4* events;
+    long long n;
+    int polarity;  // keep only p == 1
+    const int* lut_xy;
+    int cam_w, cam_h;
+    const short* xmap_t;
+    int xmap_w, xmap_h, col_stride;
+    int t_px_scale, x_offset;
+    int rect_w, rect_h;
+    int view;  // 0 projector, 1 camera
+    unsigned long long* map;
+    unsigned epoch;
+    FrameState* state;
+    int cap_cols;     // X-map columns that fit the shared-memory window (0 = never stage)
+    int lookahead;    // extra columns fetched ahead of a time-sorted stream
+    int conditional;  // 1: this launch is the fix-up pass, runs only if state->redo
+    int verify;       // 1: bounds were assumed (sorted / given) -> check every event against them
+    int arm_fixup;    // 1: the last CTA arms the fix-up pass when a violation was seen
+};
+
+__device__ __forceinline__ bool event_valid(const EventFields& e, int polarity) {
+    return !polarity || e.p == 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0a: bounds from the ends of a time-sorted frame + reset of the per-frame counters.
+//   mode 0: first / last valid event      mode 1: bounds given by the caller
+// One CTA of 64 threads: warp 0 scans forward, warp 1 backward (normally one step each).
+// ---------------------------------------------------------------------------------------------
+__global__ void bounds_init_kernel(const int4* __restrict__ events, long long n, int polarity, int mode,
+                                   long long given_lo, long long given_hi, unsigned epoch, FrameState* st) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        st->n_valid = 0;
+        st->n_inliers = 0;
+        st->flags = 0;
+        st->redo = 0;
+        st->epoch_used = epoch;
+        st->blocks_done = 0;
+        st->any_valid = 0;
+        st->red_lo = 0x7fffffffffffffffLL;
+        st->red_hi = static_cast<long long>(0x8000000000000000ULL);
+    }
+    if (mode == 1) {
+        if (threadIdx.x == 0) {
+            st->t_lo_bits = given_lo;
+            st->t_hi_bits = given_hi;
+        }
+        return;
+    }
+    long long found = -1;
+    if (warp == 0) {
+        for (long long base = 0; base < n; base += 32) {
+            long long i = base + lane;
+            bool ok = false;
+            if (i < n) ok = event_valid(unpack_event(__ldg(events + i)), polarity);
+            unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (m) {
+                found = base + (__ffs(m) - 1);
+                break;
+            }
+        }
+        if (lane == 0) st->t_lo_bits = found >= 0 ? unpack_event(__ldg(events + found)).t_bits : 0;
+    } else if (warp == 1) {
+        for (long long top = n; top > 0; top -= 32) {
+            long long i = top - 1 - lane;
+            bool ok = false;
+            if (i >= 0) ok = event_valid(unpack_event(__ldg(events + i)), polarity);
+            unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (m) {
+                found = top - 1 - (__ffs(m) - 1);
+                break;
+            }
+        }
+        if (lane == 0) st->t_hi_bits = found >= 0 ? unpack_event(__ldg(events + found)).t_bits : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0b: exact min / max over all valid events (one extra pass over the stream).  The last CTA to
+// finish publishes the result.  With conditional = 1 it only runs when the optimistic bounds of
+// K0a were found wrong by K1 (state->redo).
+// ---------------------------------------------------------------------------------------------
+template <bool F64>
+__global__ void __launch_bounds__(256) bounds_reduce_kernel(const int4* __restrict__ events, long long n, int polarity,
+                                                            int conditional, FrameState* st) {
+    if (conditional && !*reinterpret_cast<volatile unsigned*>(&st->redo)) return;
+    long long lo = 0x7fffffffffffffffLL;
+    long long hi = static_cast<long long>(0x8000000000000000ULL);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        // default L2 policy: the second pass (K1) re-reads these lines and may still find them in L2
+        EventFields e = unpack_event(ld_event_plain(events + i));
+        if (event_valid(e, polarity)) {
+            long long key = F64 ? f64_bits_to_sortable(e.t_bits) : e.t_bits;
+            lo = key < lo ? key : lo;
+            hi = key > hi ? key : hi;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        long long l2 = __shfl_xor_sync(0xffffffffu, lo, o);
+        long long h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    __shared__ unsigned s_last;
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+        atomicMin(&st->red_lo, lo);
+        atomicMax(&st->red_hi, hi);
+        st->any_valid = 1;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        long long rl = *reinterpret_cast<volatile long long*>(&st->red_lo);
+        long long rh = *reinterpret_cast<volatile long long*>(&st->red_hi);
+        bool any = rl <= rh;
+        st->t_lo_bits = any ? (F64 ? sortable_to_f64_bits(rl) : rl) : 0;
+        st->t_hi_bits = any ? (F64 ? sortable_to_f64_bits(rh) : rh) : 0;
+        st->blocks_done = 0;
+        st->n_valid = 0;
+        st->n_inliers = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: the fused per-event kernel.
+//
+// Each CTA owns one contiguous span of the event buffer and walks it in chunks of kEvChunk
+// events.  Per chunk every thread issues kEvPerThread independent 128-bit event loads followed by
+// the dependent LUT gathers; the block then agrees on the range of X-map time columns the chunk
+// needs.  For a time-sorted stream that range is 1-3 columns, which (in the transposed layout) is
+// one contiguous byte range: thread 0 stages it into shared memory with a single 1-D bulk async
+// copy (TMA) signalled on an mbarrier, and the lookups become shared-memory reads.  Chunks whose
+// range does not fit (unsorted input) read the transposed table through L2 instead.
+// ---------------------------------------------------------------------------------------------
+template <bool F64>
+__global__ void __launch_bounds__(kEvThreads, 4) events_kernel(const EventParams p) {
+    extern __shared__ __align__(128) unsigned char ev_smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ev_smem);
+    int* s_min = reinterpret_cast<int*>(ev_smem + 16);       // [2][8]
+    int* s_max = reinterpret_cast<int*>(ev_smem + 16 + 64);  // [2][8]
+    short* s_cols = reinterpret_cast<short*>(ev_smem + 256);
+
+    FrameState* st = p.state;
+    if (p.conditional && !*reinterpret_cast<volatile unsigned*>(&st->redo)) return;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+
+    TimeNorm<F64> tn;
+    tn.init(st->t_lo_bits, st->t_hi_bits, p.t_px_scale);
+
+    // span of this CTA: equal shares, boundaries on multiples of 32 events (512 B)
+    const long long per = ((p.n + gridDim.x - 1) / gridDim.x + 31) & ~31LL;
+    const long long span_lo = per * blockIdx.x < p.n ? per * blockIdx.x : p.n;
+    const long long span_hi = span_lo + per < p.n ? span_lo + per : p.n;
+
+    const uint64_t pol = make_evict_first_policy();
+    unsigned n_valid = 0, n_inl = 0, flags = 0;
+    int win_lo = 0, win_n = 0;
+    unsigned phase = 0;
+    int it = 0;
+
+    for (long long base = span_lo; base < span_hi; base += kEvChunk, ++it) {
+        int4 raw[kEvPerThread];
+        bool ok[kEvPerThread];
+#pragma unroll
+        for (int k = 0; k < kEvPerThread; ++k) {
+            long long i = base + k * kEvThreads + tid;
+            ok[k] = i < span_hi;
+            if (ok[k]) raw[k] = ld_event_stream(p.events + i, pol);
+        }
+        int col[kEvPerThread];
+        int lut[kEvPerThread];
+        int pix[kEvPerThread];
+        int cmin = 0x7fffffff, cmax = -1;
+#pragma unroll
+        for (int k = 0; k < kEvPerThread; ++k) {
+            col[k] = 0;
+            lut[k] = 0;
+            pix[k] = 0;
+            if (ok[k]) {
+                EventFields e = unpack_event(raw[k]);
+                ok[k] = event_valid(e, p.polarity);
+                if (ok[k]) {
+                    ++n_valid;
+                    if (e.x >= static_cast<unsigned>(p.cam_w) || e.y >= static_cast<unsigned>(p.cam_h)) {
+                        flags |= kStatusPixelOob;  // the reference raises IndexError here
+                        ok[k] = false;
+                    } else {
+                        pix[k] = static_cast<int>(e.y) * p.cam_w + static_cast<int>(e.x);
+                        lut[k] = __ldg(p.lut_xy + pix[k]);
+                        if (p.verify && tn.outside(e.t_bits)) flags |= kStatusTBounds;
+                        int c = tn.column(e.t_bits);
+                        if (c < 0) c += p.xmap_w;  // NumPy negative index (only reachable with wrong bounds)
+                        if (c < 0 || c >= p.xmap_w) {
+                            flags |= kStatusTBounds;
+                            c = 0;
+                        }
+                        col[k] = c;
+                        cmin = min(cmin, c);
+                        cmax = max(cmax, c);
+                    }
+                }
+            }
+        }
+        // block-wide column range of this chunk
+        cmin = __reduce_min_sync(0xffffffffu, cmin);
+        cmax = __reduce_max_sync(0xffffffffu, cmax);
+        const int buf = (it & 1) * 8;
+        if (lane == 0) {
+            s_min[buf + warp] = cmin;
+            s_max[buf + warp] = cmax;
+        }
+        __syncthreads();  // also: every thread is done reading the window of the previous chunk
+        {
+            int v0 = s_min[buf + (lane & 7)];
+            int v1 = s_max[buf + (lane & 7)];
+            cmin = __reduce_min_sync(0xffffffffu, v0);
+            cmax = __reduce_max_sync(0xffffffffu, v1);
+        }
+        if (cmax < 0) continue;  // no valid event in this chunk (uniform across the CTA)
+
+        bool from_smem = false;
+        const int need = cmax - cmin + 1;
+        if (need <= p.cap_cols) {
+            from_smem = true;
+            if (cmin < win_lo || cmax >= win_lo + win_n) {
+                win_lo = cmin;
+                win_n = min(min(need + p.lookahead, p.cap_cols), p.xmap_w - cmin);
+                if (tid == 0) {
+                    const unsigned bytes = static_cast<unsigned>(win_n) * p.col_stride * 2u;
+                    mbar_expect_tx(bar, bytes);
+                    tma_load_1d(s_cols, p.xmap_t + static_cast<long long>(win_lo) * p.col_stride, bytes, bar);
+                }
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+            }
+        }
+
+#pragma unroll
+        for (int k = 0; k < kEvPerThread; ++k) {
+            if (!ok[k]) continue;
+            const int xcr = static_cast<short>(lut[k] & 0xffff);
+            const int ycr = lut[k] >> 16;
+            if (ycr < 0 || ycr >= p.xmap_h - 1) continue;  // x_maps_disparity.py:23 (last row excluded)
+            int xp;
+            if (from_smem)
+                xp = s_cols[(col[k] - win_lo) * p.col_stride + ycr];
+            else
+                xp = __ldg(p.xmap_t + static_cast<long long>(col[k]) * p.col_stride + ycr);
+            const int disp = static_cast<short>(xp - xcr - p.x_offset);  // int16 arithmetic wraps
+            if (disp < 0) continue;
+            ++n_inl;
+            long long cell;
+            if (p.view == 1) {
+                cell = pix[k];
+            } else {
+                int xpr = static_cast<short>(xcr + disp);
+                int ypr = ycr;
+                if (xpr < 0) xpr += p.rect_w;  // NumPy negative index wraps once
+                if (xpr < 0 || xpr >= p.rect_w || ypr >= p.rect_h) {
+                    flags |= kStatusScatterOob;  // the reference raises IndexError here
+                    continue;
+                }
+                cell = static_cast<long long>(ypr) * p.rect_w + xpr;
+            }
+            const unsigned long long idx = static_cast<unsigned long long>(base + k * kEvThreads + tid);
+            atomicMax(p.map + cell, make_key(p.epoch, idx, disp));
+        }
+    }
+
+    // per-CTA statistics -> one atomic per warp
+    n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+    n_inl = __reduce_add_sync(0xffffffffu, n_inl);
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0) {
+        if (n_valid) atomicAdd(&st->n_valid, static_cast<unsigned long long>(n_valid));
+        if (n_inl) atomicAdd(&st->n_inliers, static_cast<unsigned long long>(n_inl));
+        if (flags) atomicOr(&st->flags, flags);
+    }
+    if (p.arm_fixup) {
+        // last CTA: if any event violated the assumed bounds, arm the fix-up pass
+        __shared__ unsigned s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (s_last && tid == 0) {
+            __threadfence();
+            unsigned f = *reinterpret_cast<volatile unsigned*>(&st->flags);
+            st->blocks_done = 0;
+            if (f & kStatusTBounds) {
+                st->redo = 1;
+                st->epoch_used = p.epoch + 1;
+                st->flags = f & ~(kStatusPixelOob | kStatusScatterOob);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 (camera view): decode the key of every camera pixel and emit.
+// ---------------------------------------------------------------------------------------------
+struct EpilogueParams {
+    const unsigned long long* map;
+    const FrameState* state;
+    const short2* remap_xy;
+    int rect_w, rect_h;
+    int out_w, out_h;  // projector (view 0) or camera (view 1) size
+    int radius;        // dilate / 2
+    int region_cap;    // cells of the shared-memory region (per buffer)
+    OutputSpec out;
+    void* dst;
+};
+
+__global__ void __launch_bounds__(256) epilogue_camera_kernel(const EpilogueParams p) {
+    const unsigned epoch = p.state->epoch_used;
+    const long long n = static_cast<long long>(p.out_w) * p.out_h;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        emit_pixel(p.out, p.dst, i, static_cast<float>(key_disparity(p.map[i], epoch)));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 (projector view): out[v,u] = max over the (2r+1)^2 window around remap(v,u) of the rectified
+// disparity map, 0 if remap(v,u) is outside it  ==  cv2.dilate + cv2.remap(NEAREST, BORDER_CONSTANT)
+// (disp_to_depth.py:76-97).  One CTA per 32x32 output tile: the tile's source bounding box (+ halo)
+// is decoded from the key map into shared memory once, dilated horizontally in shared memory, and
+// each output pixel then takes a (2r+1)-tap vertical max.  Tiles whose box does not fit the
+// shared-memory region fall back to direct window reads.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTile = 32;
+
+__global__ void __launch_bounds__(256) epilogue_projector_kernel(const EpilogueParams p) {
+    extern __shared__ __align__(128) unsigned char ev_smem[];
+    unsigned short* s_raw = reinterpret_cast<unsigned short*>(ev_smem);
+    unsigned short* s_h = s_raw + p.region_cap;
+    __shared__ int s_box[4][8];
+
+    const unsigned epoch = p.state->epoch_used;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int u0 = blockIdx.x * kTile, v0 = blockIdx.y * kTile;
+    const int r = p.radius;
+
+    short2 m[4];
+    bool inside[4];
+    int x0 = 0x7fffffff, x1 = -1, y0 = 0x7fffffff, y1 = -1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int u = u0 + lane, v = v0 + warp + k * 8;
+        inside[k] = false;
+        m[k] = make_short2(0, 0);
+        if (u < p.out_w && v < p.out_h) {
+            m[k] = __ldg(p.remap_xy + static_cast<long long>(v) * p.out_w + u);
+            inside[k] = m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h;
+            if (inside[k]) {
+                x0 = min(x0, static_cast<int>(m[k].x));
+                x1 = max(x1, static_cast<int>(m[k].x));
+                y0 = min(y0, static_cast<int>(m[k].y));
+                y1 = max(y1, static_cast<int>(m[k].y));
+            }
+        }
+    }
+    x0 = __reduce_min_sync(0xffffffffu, x0);
+    y0 = __reduce_min_sync(0xffffffffu, y0);
+    x1 = __reduce_max_sync(0xffffffffu, x1);
+    y1 = __reduce_max_sync(0xffffffffu, y1);
+    if (lane == 0) {
+        s_box[0][warp] = x0;
+        s_box[1][warp] = y0;
+        s_box[2][warp] = x1;
+        s_box[3][warp] = y1;
+    }
+    __syncthreads();
+    x0 = __reduce_min_sync(0xffffffffu, s_box[0][lane & 7]);
+    y0 = __reduce_min_sync(0xffffffffu, s_box[1][lane & 7]);
+    x1 = __reduce_max_sync(0xffffffffu, s_box[2][lane & 7]);
+    y1 = __reduce_max_sync(0xffffffffu, s_box[3][lane & 7]);
+
+    float val[4] = {0.f, 0.f, 0.f, 0.f};
+    if (x1 >= 0) {
+        // region = bounding box + halo; cells outside the image count as 0 (disparities are >= 0,
+        // so ignoring a tap, as cv2.dilate does at the border, equals reading 0)
+        const int rx0 = x0 - r, ry0 = y0 - r;
+        const int rw = x1 - x0 + 1 + 2 * r, rh = y1 - y0 + 1 + 2 * r;
+        if (rw * rh <= p.region_cap) {
+            for (int c = tid; c < rw * rh; c += 256) {
+                const int ry = c / rw, rx = c - ry * rw;
+                const int gx = rx0 + rx, gy = ry0 + ry;
+                unsigned short d = 0;
+                if (gx >= 0 && gx < p.rect_w && gy >= 0 && gy < p.rect_h)
+                    d = static_cast<unsigned short>(key_disparity(p.map[static_cast<long long>(gy) * p.rect_w + gx], epoch));
+                s_raw[c] = d;
+            }
+            __syncthreads();
+            // horizontal max, only for the columns the vertical pass can read: rx in [r, rw - r)
+            const int iw = rw - 2 * r;
+            for (int c = tid; c < iw * rh; c += 256) {
+                const int ry = c / iw, rx = c - ry * iw + r;
+                const unsigned short* row = s_raw + ry * rw + rx;
+                unsigned short best = 0;
+                for (int d = -r; d <= r; ++d) best = max(best, row[d]);
+                s_h[ry * rw + rx] = best;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!inside[k]) continue;
+                const int cx = m[k].x - rx0, cy = m[k].y - ry0;
+                unsigned short best = 0;
+                for (int d = -r; d <= r; ++d) best = max(best, s_h[(cy + d) * rw + cx]);
+                val[k] = static_cast<float>(best);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!inside[k]) continue;
+                int best = 0;
+                for (int dy = -r; dy <= r; ++dy) {
+                    const int gy = m[k].y + dy;
+                    if (gy < 0 || gy >= p.rect_h) continue;
+                    for (int dx = -r; dx <= r; ++dx) {
+                        const int gx = m[k].x + dx;
+                        if (gx < 0 || gx >= p.rect_w) continue;
+                        best = max(best, key_disparity(p.map[static_cast<long long>(gy) * p.rect_w + gx], epoch));
+                    }
+                }
+                val[k] = static_cast<float>(best);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int u = u0 + lane, v = v0 + warp + k * 8;
+        if (u < p.out_w && v < p.out_h) emit_pixel(p.out, p.dst, static_cast<long long>(v) * p.out_w + u, val[k]);
+    }
+}
+
+}  // namespace xm
