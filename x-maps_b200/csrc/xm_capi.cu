@@ -124,8 +124,13 @@ int configure_event_kernels(XmCtx* c) {
     if (cols > c->xmap_w) cols = c->xmap_w;
     c->cap_cols = cols;
     c->ev_smem = 256 + cols * c->col_stride * 2;
-    XM_CUDA(cudaFuncSetAttribute(xm::events_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->ev_smem));
-    XM_CUDA(cudaFuncSetAttribute(xm::events_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->ev_smem));
+    // the attribute is per function, not per context: always allow the device maximum so that
+    // contexts with different X-map geometries can coexist in one process
+    int optin = 0;
+    XM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    if (c->ev_smem > optin) return fail(XM_ERR_UNSUPPORTED, "event kernel needs %d B of shared memory, device allows %d", c->ev_smem, optin);
+    XM_CUDA(cudaFuncSetAttribute(xm::events_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    XM_CUDA(cudaFuncSetAttribute(xm::events_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ev_occ_i64, xm::events_kernel<false>, xm::kEvThreads, c->ev_smem));
     XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ev_occ_f64, xm::events_kernel<true>, xm::kEvThreads, c->ev_smem));
     if (c->ev_occ_i64 < 1 || c->ev_occ_f64 < 1) return fail(XM_ERR_UNSUPPORTED, "event kernel does not fit an SM (smem %d B)", c->ev_smem);
@@ -208,7 +213,7 @@ int check_frame_args(const XmCtx* c, const XmFrameArgs* a) {
 
 // profile support: drain recorded event triples into the accumulators (synchronises)
 int profile_drain(XmCtx* c) {
-    for (size_t i = 0; i + 2 < c->prof_used + 0 && i + 2 < c->prof_events.size() + 0; i += 3) {
+    for (size_t i = 0; i + 2 < c->prof_used; i += 3) {
         float a = 0.f, b = 0.f;
         XM_CUDA(cudaEventSynchronize(c->prof_events[i + 2]));
         XM_CUDA(cudaEventElapsedTime(&a, c->prof_events[i], c->prof_events[i + 1]));
@@ -809,7 +814,10 @@ int xm_build_xmap(int device, const float* d_time_map, int32_t h, int32_t w, int
     DeviceGuard guard(device);
     if (!guard.ok) return fail(XM_ERR_CUDA, "cannot select device %d", device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    XM_CUDA(cudaFuncSetAttribute(xm::build_xmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, w * 4));
+    int optin = 0;
+    XM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (w * 4 > optin) return fail(XM_ERR_UNSUPPORTED, "time-map row of %d floats exceeds shared memory", w);
+    XM_CUDA(cudaFuncSetAttribute(xm::build_xmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     xm::build_xmap_kernel<<<h, 256, static_cast<size_t>(w) * 4, s>>>(d_time_map, h, w, x_map_width, t_px_scale, x_offset, num_scanlines,
                                                                     d_x_map, d_t_diffs);
     XM_LAUNCHED();

@@ -55,12 +55,13 @@ class DisparityToDepth:
     def __post_init__(self):
         self.dilate_kernel = np.ones((7, 7), dtype=np.uint8)  # reference :74 (size fixed in the engine tables)
 
-    def remap_rectified_disp_map_to_proj(self, disp_map):
-        with _measure(self.stats, "dilate"), _measure(self.stats, "remap"):
-            if isinstance(disp_map, LazyDispMap) and disp_map._value is None and disp_map.stage == "rect":
-                return LazyDispMap(disp_map.ticket, "proj")
+    def remap_rectified_disp_map_to_proj(self, rectified_disp_map):
+        m = rectified_disp_map
+        with _measure(self.stats, "dilate"), _measure(self.stats, "remap disp"):
+            if isinstance(m, LazyDispMap) and m._value is None and m.stage == "rect":
+                return LazyDispMap(m.ticket, "proj")
             eng = self.calib_maps.engine()
-            return DeviceArray.of(eng.dilate_remap(to_tensor(disp_map, eng.device, torch.float32)))
+            return DeviceArray.of(eng.dilate_remap(to_tensor(m, eng.device, torch.float32)))
 
     def colorize_depth_from_disp(self, disp_map):
         from .engine import OUT_BGR
