@@ -1,0 +1,104 @@
+"""The reference's call surface (drop-in classes + lazy handles) driven the way the reference's
+own callers drive it: depth_reprojection_pipe.py:121-167 and eval/compute_depth_x_maps.py:97-122."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import xmaps_oracle as orc
+from xm_helpers import ROOT, golden_frame, load_golden_tables
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+CALIB = os.path.join(ROOT, "data", "esl_calib_hhi.json")
+
+
+@pytest.fixture(scope="module")
+def pipes():
+    from xmaps_b200.pipeline import DepthFramePipeline, RuntimeParams
+
+    def make(cam_view):
+        return DepthFramePipeline(RuntimeParams(640, 480, 720, 1280, 60, 0.1, 1.0, CALIB, None, False, cam_view))
+
+    return make(False), make(True)
+
+
+def test_setup_tables_match_reference(pipes, manifest):
+    """Calibration + time map on the host, X-map on the GPU: all identical to the reference's."""
+    proj, _ = pipes
+    tables, _ = load_golden_tables("default")
+    assert np.array_equal(proj.x_maps_disp.proj_x_map, tables.x_map)
+    assert np.array_equal(proj.calib_maps.disp_cam_mapx_i16, tables.lut_x)
+    assert np.array_equal(proj.calib_maps.disp_proj_mapxy_i16, tables.remap_xy)
+    assert proj.x_maps_disp.T_PX_SCALE == 719 and proj.x_maps_disp.X_OFFSET == 4242 and proj.x_maps_disp.X_MAP_WIDTH == 720
+
+
+def test_process_ev_frame_matches_reference(pipes):
+    proj, cam = pipes
+    evs = orc.polarity_mask(orc.synth_events(0, 100_000, 640, 480))  # the pipe polarity-filters upstream
+    got = []
+    proj.frame_callback = got.append
+    bgr = proj.process_ev_frame(evs)
+    assert isinstance(bgr, np.ndarray) and bgr.dtype == np.uint8 and got and got[0] is bgr
+    assert np.array_equal(bgr, golden_frame("default_100k_proj")["bgr"])
+    assert np.array_equal(cam.process_ev_frame(evs), golden_frame("default_100k_cam")["bgr"])
+    # device-resident events
+    dev = torch.from_numpy(evs.view(np.int32).reshape(-1, 4)).cuda()
+    assert np.array_equal(proj.process_ev_frame(dev), golden_frame("default_100k_proj")["bgr"])
+    # raw frame with the polarity mask fused
+    depth = proj.depth_frame(orc.synth_events(0, 100_000, 640, 480)).cpu().numpy()
+    assert np.array_equal(depth, golden_frame("default_100k_proj")["depth"])
+
+
+def test_lazy_handles_materialise(pipes):
+    proj, _ = pipes
+    g = golden_frame("default_100k_proj")
+    evs = orc.polarity_mask(orc.synth_events(0, 100_000, 640, 480))
+    maps, xd, d2d = proj.calib_maps, proj.x_maps_disp, proj.disp_to_depth
+    xr, yr = maps.rectify_cam_coords_i16(evs)
+    assert len(xr) == len(evs)
+    disp, mask = xd.compute_event_disparity(events=evs, ev_x_rect_i16=xr, ev_y_rect_i16=yr)
+    rect = maps.compute_disp_map_projector_view(ev_x_rect_i16=xr, ev_y_rect_i16=yr, inlier_mask=mask, ev_disparity_f32=disp)
+    remapped = d2d.remap_rectified_disp_map_to_proj(rect)
+    # nothing has been computed so far; now look at everything
+    assert np.array_equal(np.asarray(xr), g["xr"]) and np.array_equal(np.asarray(yr), g["yr"])
+    assert np.array_equal(np.asarray(disp), g["disp"])
+    assert np.array_equal(np.packbits(np.asarray(mask)), g["mask_bits"])
+    assert np.array_equal(np.asarray(rect), g["rect_map"])
+    assert np.array_equal(np.asarray(remapped), g["disp_map"])
+    # materialised maps take the stage kernels
+    assert np.array_equal(np.asarray(d2d.remap_rectified_disp_map_to_proj(np.asarray(rect))), g["disp_map"])
+    assert np.array_equal(d2d.colorize_depth_from_disp(np.asarray(remapped)), g["bgr"])
+    # plain NumPy intermediates supplied by the caller are honoured too
+    disp2, mask2 = xd.compute_event_disparity(events=evs, ev_x_rect_i16=g["xr"], ev_y_rect_i16=g["yr"])
+    assert np.array_equal(np.asarray(disp2), g["disp"])
+    rect2 = maps.compute_disp_map_projector_view(g["xr"], g["yr"], np.asarray(mask2), g["disp"])
+    assert np.array_equal(np.asarray(rect2), g["rect_map"])
+
+
+def test_evaluation_script_call_sequence(pipes):
+    """python/eval/compute_depth_x_maps.py:83-122: dict events with float t, camera view, depth via
+    the free function, point cloud from masked float coordinates."""
+    from xmaps_b200.depth import disparity_to_depth_rectified
+
+    _, cam = pipes
+    maps, xd = cam.calib_maps, cam.x_maps_disp
+    tables, _ = load_golden_tables("default")
+    rng = np.random.default_rng(12)
+    n = 200_000
+    events = {"x": rng.integers(0, 640, n), "y": rng.integers(0, 480, n), "t": rng.random(n)}
+    xcr_f32, ycr_f32 = maps.rectify_cam_coords_f32(events)
+    xcr_i16, ycr_i16 = maps.rectify_cam_coords_i16(events)
+    disparity, inlier_mask = xd.compute_event_disparity(events=events, ev_x_rect_i16=xcr_i16, ev_y_rect_i16=ycr_i16)
+    disp_map = maps.compute_disp_map_camera_view(events=events, inlier_mask=inlier_mask, ev_disparity_f32=disparity)
+    depth = disparity_to_depth_rectified(disp_map, maps.P2)
+
+    oxr, oyr = orc.rectify_i16(tables, events)
+    odisp, omask = orc.event_disparity(tables, oxr, oyr, events["t"])
+    want = orc.disparity_to_depth(orc.scatter_camera_view(tables, events, omask, odisp), tables.depth_scale)
+    assert np.array_equal(np.asarray(depth), want)
+    assert np.array_equal(np.asarray(inlier_mask), omask) and np.array_equal(np.asarray(disparity), odisp)
+    pc = maps.construct_point_cloud(xcr_f32[inlier_mask], ycr_f32[inlier_mask], disparity)
+    assert np.asarray(pc).shape == (int(omask.sum()), 3)
+    assert np.isfinite(np.asarray(pc)).all()

@@ -128,9 +128,14 @@ int configure_event_kernels(XmCtx* c) {
     // contexts with different X-map geometries can coexist in one process
     int optin = 0;
     XM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    if (c->ev_smem > optin) return fail(XM_ERR_UNSUPPORTED, "event kernel needs %d B of shared memory, device allows %d", c->ev_smem, optin);
-    XM_CUDA(cudaFuncSetAttribute(xm::events_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-    XM_CUDA(cudaFuncSetAttribute(xm::events_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    cudaFuncAttributes fa0, fa1;
+    XM_CUDA(cudaFuncGetAttributes(&fa0, xm::events_kernel<false>));
+    XM_CUDA(cudaFuncGetAttributes(&fa1, xm::events_kernel<true>));
+    const int dyn0 = optin - static_cast<int>(fa0.sharedSizeBytes), dyn1 = optin - static_cast<int>(fa1.sharedSizeBytes);
+    if (c->ev_smem > dyn0 || c->ev_smem > dyn1)
+        return fail(XM_ERR_UNSUPPORTED, "event kernel needs %d B of shared memory, device allows %d", c->ev_smem, dyn0 < dyn1 ? dyn0 : dyn1);
+    XM_CUDA(cudaFuncSetAttribute(xm::events_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn0));
+    XM_CUDA(cudaFuncSetAttribute(xm::events_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn1));
     XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ev_occ_i64, xm::events_kernel<false>, xm::kEvThreads, c->ev_smem));
     XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ev_occ_f64, xm::events_kernel<true>, xm::kEvThreads, c->ev_smem));
     if (c->ev_occ_i64 < 1 || c->ev_occ_f64 < 1) return fail(XM_ERR_UNSUPPORTED, "event kernel does not fit an SM (smem %d B)", c->ev_smem);
@@ -816,6 +821,9 @@ int xm_build_xmap(int device, const float* d_time_map, int32_t h, int32_t w, int
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int optin = 0;
     XM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    cudaFuncAttributes fa;
+    XM_CUDA(cudaFuncGetAttributes(&fa, xm::build_xmap_kernel));
+    optin -= static_cast<int>(fa.sharedSizeBytes);
     if (w * 4 > optin) return fail(XM_ERR_UNSUPPORTED, "time-map row of %d floats exceeds shared memory", w);
     XM_CUDA(cudaFuncSetAttribute(xm::build_xmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     xm::build_xmap_kernel<<<h, 256, static_cast<size_t>(w) * 4, s>>>(d_time_map, h, w, x_map_width, t_px_scale, x_offset, num_scanlines,
