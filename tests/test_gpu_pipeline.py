@@ -101,4 +101,13 @@ def test_evaluation_script_call_sequence(pipes):
     assert np.array_equal(np.asarray(inlier_mask), omask) and np.array_equal(np.asarray(disparity), odisp)
     pc = maps.construct_point_cloud(xcr_f32[inlier_mask], ycr_f32[inlier_mask], disparity)
     assert np.asarray(pc).shape == (int(omask.sum()), 3)
-    assert np.isfinite(np.asarray(pc)).all()
+    # reference formula (cam_proj_calibration.py:319-331) on the host; disparity 0 divides by zero there too
+    xf, yf, d = np.asarray(xcr_f32)[omask], np.asarray(ycr_f32)[omask], odisp.astype(np.float32)
+    pts = np.ones((len(d), 4), np.float32)
+    pts[:, 0], pts[:, 1], pts[:, 2] = xf + d, yf, -d
+    with np.errstate(all="ignore"):
+        ref = (maps.Q.astype(np.float32) @ pts.T).T
+        ref = (ref / ref[:, 3:])[:, :3]
+    ref[:, 1:] = -ref[:, 1:]
+    ok = np.isfinite(ref).all(axis=1) & (d > 0)
+    np.testing.assert_allclose(np.asarray(pc)[ok], ref[ok], rtol=2e-5, atol=1e-6)

@@ -73,6 +73,7 @@ struct XmCtx {
     short* d_xmap_t = nullptr;
     short2* d_remap_xy = nullptr;
     unsigned char* d_turbo = nullptr;
+    float* d_depth_lut = nullptr;  // [32768], exact depth of every integer disparity
     bool have_turbo = false;
     unsigned long long* d_map = nullptr;
     long long map_cells = 0;
@@ -91,7 +92,8 @@ struct XmCtx {
     int opt_auto_fixup = 1;
     int opt_lookahead = 1;
     int opt_ctas_per_sm = 0;  // 0 = occupancy query
-    int opt_smem_cols_bytes = 40 * 1024;
+    int opt_smem_cols_bytes = 16 * 1024;
+    int opt_stages = 3;  // depth of the shared-memory event ring of K1
     int opt_region_cells = 64 * 64;
     // per-kernel CUDA-event timing (option "profile"): pairs around K1 and K2 of every frame
     int opt_profile = 0;
@@ -123,7 +125,7 @@ int configure_event_kernels(XmCtx* c) {
     if (c->opt_stage_xmap && c->col_stride > 0) cols = c->opt_smem_cols_bytes / (c->col_stride * 2);
     if (cols > c->xmap_w) cols = c->xmap_w;
     c->cap_cols = cols;
-    c->ev_smem = 256 + cols * c->col_stride * 2;
+    c->ev_smem = xm::events_smem_bytes(c->opt_stages, cols * c->col_stride * 2);
     // the attribute is per function, not per context: always allow the device maximum so that
     // contexts with different X-map geometries can coexist in one process
     int optin = 0;
@@ -177,6 +179,7 @@ xm::OutputSpec make_output(const XmCtx* c, int kind, double depth_scale, float z
     o.z_near = z_near;
     o.z_far = z_far;
     o.turbo_bgr = c->d_turbo;
+    o.depth_lut = (depth_scale == c->depth_scale) ? c->d_depth_lut : nullptr;
     return o;
 }
 
@@ -281,6 +284,7 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     p.state = c->d_state;
     p.cap_cols = c->cap_cols;
     p.lookahead = c->opt_lookahead;
+    p.stages = c->opt_stages;
     p.conditional = 0;
     p.verify = assumed ? 1 : 0;
     p.arm_fixup = fixup ? 1 : 0;
@@ -340,7 +344,10 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
         q.out_w = c->proj_w;
         q.out_h = c->proj_h;
         dim3 grid((c->proj_w + xm::kTile - 1) / xm::kTile, (c->proj_h + xm::kTile - 1) / xm::kTile);
-        xm::epilogue_projector_kernel<<<grid, 256, static_cast<size_t>(c->opt_region_cells) * 4, s>>>(q);
+        if (c->dilate == 7)
+            xm::epilogue_projector_kernel<3><<<grid, 256, static_cast<size_t>(c->opt_region_cells) * 4, s>>>(q);
+        else
+            xm::epilogue_projector_kernel<0><<<grid, 256, static_cast<size_t>(c->opt_region_cells) * 4, s>>>(q);
     }
     XM_LAUNCHED();
     if (c->opt_profile) {
@@ -432,6 +439,12 @@ int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
         cudaMemset(c->d_state, 0, sizeof(xm::FrameState)) != cudaSuccess || cudaMalloc(&c->d_turbo, 768) != cudaSuccess ||
         cudaMemset(c->d_turbo, 0, 768) != cudaSuccess)
         return bail(fail(XM_ERR_CUDA, "allocating the scatter map failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (cudaMalloc(&c->d_depth_lut, 32768 * sizeof(float)) != cudaSuccess)
+        return bail(fail(XM_ERR_CUDA, "allocating the depth table failed: %s", cudaGetErrorString(cudaGetLastError())));
+    xm::depth_lut_kernel<<<32768 / 256, 256>>>(c->d_depth_lut, 32768, c->depth_scale);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (cudaDeviceSynchronize() != cudaSuccess)
+        return bail(fail(XM_ERR_CUDA, "building the depth table failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (t->x_map) {
         if (t->xmap_w <= 0) return bail(fail(XM_ERR_INVALID_ARG, "xmap_w must be positive"));
         rc = upload_xmap(c, t->x_map, t->rect_h, t->xmap_w, t->t_px_scale, t->x_offset);
@@ -450,6 +463,7 @@ int xm_ctx_destroy(XmCtx* c) {
     cudaFree(c->d_xmap_t);
     cudaFree(c->d_remap_xy);
     cudaFree(c->d_turbo);
+    cudaFree(c->d_depth_lut);
     cudaFree(c->d_map);
     cudaFree(c->d_state);
     cudaFree(c->d_counts);
@@ -486,6 +500,11 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
     if (!strcmp(key, "smem_cols_bytes")) {
         if (v < 0 || v > 200 * 1024) return fail(XM_ERR_INVALID_ARG, "smem_cols_bytes out of range");
         c->opt_smem_cols_bytes = v;
+        return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
+    }
+    if (!strcmp(key, "stages")) {
+        if (v < 1 || v > xm::kMaxStages) return fail(XM_ERR_INVALID_ARG, "stages must be 1..%d", xm::kMaxStages);
+        c->opt_stages = v;
         return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
     }
     if (!strcmp(key, "auto_fixup")) {
@@ -532,6 +551,7 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     if (!c || !key || !value) return fail(XM_ERR_INVALID_ARG, "null argument");
     if (!strcmp(key, "stage_xmap")) *value = c->opt_stage_xmap;
     else if (!strcmp(key, "smem_cols_bytes")) *value = c->opt_smem_cols_bytes;
+    else if (!strcmp(key, "stages")) *value = c->opt_stages;
     else if (!strcmp(key, "auto_fixup")) *value = c->opt_auto_fixup;
     else if (!strcmp(key, "lookahead")) *value = c->opt_lookahead;
     else if (!strcmp(key, "ctas_per_sm")) *value = c->opt_ctas_per_sm;

@@ -109,6 +109,63 @@ struct TimeNorm {
     }
 };
 
+// Same arithmetic with a cheap common case.  a = fl(num * fl(scale / den)) differs from the
+// reference's s = fl(fl(num / den) * scale) by < 4e-13 (both are within 2 ulp-ish of the exact
+// value, which is < 2^15), so rint(a) == rint(s) unless a lies within 1e-4 of a half-integer; only
+// then (exact ties in practice) is the division evaluated.  Integer timestamps whose range fits 31
+// bits also avoid the 64-bit int -> double conversion.
+template <bool F64>
+struct TimeCol {
+    unsigned long long lo_u, range;
+    double lo_f, hi_f, den, scale, inv;
+    bool fast;
+
+    __device__ __forceinline__ void init(long long lo_bits, long long hi_bits, int t_px_scale) {
+        scale = static_cast<double>(t_px_scale);
+        if (F64) {
+            lo_f = __longlong_as_double(lo_bits);
+            hi_f = __longlong_as_double(hi_bits);
+            den = __dsub_rn(hi_f, lo_f);
+            lo_u = range = 0;
+            fast = den > 0.0 && den < 1.7e308;
+        } else {
+            lo_u = static_cast<unsigned long long>(lo_bits);
+            range = hi_bits >= lo_bits ? static_cast<unsigned long long>(hi_bits) - lo_u : 0ULL;
+            den = static_cast<double>(hi_bits - lo_bits);
+            lo_f = hi_f = 0.0;
+            fast = range > 0 && range < 0x80000000ULL && hi_bits >= lo_bits;
+        }
+        inv = fast ? __ddiv_rn(scale, den) : 0.0;
+    }
+
+    __device__ __forceinline__ int exact(double num) const {
+        double r = rint(__dmul_rn(__ddiv_rn(num, den), scale));
+        if (!(r == r)) return 0;  // 0/0 (all timestamps equal) is NaN in NumPy and casts to 0
+        r = fmin(fmax(r, -32768.0), 32767.0);  // memory safety only (flagged events)
+        return static_cast<int>(r);
+    }
+
+    // int16(rint(((t - min) / (max - min)) * T_PX_SCALE)); `viol` = t outside the assumed [min, max]
+    __device__ __forceinline__ int column(long long t_bits, bool& viol) const {
+        double num;
+        if (F64) {
+            const double t = __longlong_as_double(t_bits);
+            viol = !(t >= lo_f && t <= hi_f);
+            num = __dsub_rn(t, lo_f);
+        } else {
+            const unsigned long long dt = static_cast<unsigned long long>(t_bits) - lo_u;
+            viol = dt > range;
+            num = fast ? static_cast<double>(static_cast<unsigned>(dt)) : static_cast<double>(static_cast<long long>(dt));
+        }
+        if (fast && !viol) {
+            const double a = __dmul_rn(num, inv);
+            const int k = __double2int_rn(a);
+            if (fabs(__dsub_rn(a, static_cast<double>(k))) < 0.4999) return k;
+        }
+        return exact(num);
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Scatter keys: the reference's `map[rows, cols] = vals` keeps the LAST duplicate.  Each event
 // contributes key = epoch:16 | event_index:32 | disparity:16 and the map keeps the maximum, i.e.
@@ -118,6 +175,13 @@ struct TimeNorm {
 __device__ __forceinline__ unsigned long long make_key(unsigned epoch, unsigned long long index, int disp) {
     return (static_cast<unsigned long long>(epoch) << 48) | ((index & 0xffffffffULL) << 16) |
            static_cast<unsigned long long>(static_cast<unsigned>(disp) & 0xffffu);
+}
+
+// same key from a 32-bit event index, built from two 32-bit halves
+__device__ __forceinline__ unsigned long long make_key32(unsigned epoch, unsigned index, int disp) {
+    const unsigned hi = (epoch << 16) | (index >> 16);
+    const unsigned lo = (index << 16) | (static_cast<unsigned>(disp) & 0xffffu);
+    return (static_cast<unsigned long long>(hi) << 32) | lo;
 }
 
 __device__ __forceinline__ int key_disparity(unsigned long long key, unsigned epoch) {
@@ -147,6 +211,7 @@ struct OutputSpec {
     double depth_scale;  // P2[0,3]
     float z_near, z_far;
     const unsigned char* turbo_bgr;  // [256][3]
+    const float* depth_lut;          // [32768] depth of every integer disparity (exact f64 divide), or NULL
 };
 
 // Writes one pixel of the frame from an integer-valued disparity.
@@ -165,6 +230,20 @@ __device__ __forceinline__ void emit_pixel(const OutputSpec& o, void* out, long 
             px[1] = o.turbo_bgr[u * 3 + 1];
             px[2] = o.turbo_bgr[u * 3 + 2];
         }
+    }
+}
+
+// Same for the fused epilogues, whose disparities are integers in [0, 32767]: the depth comes from a
+// per-context table filled once with disparity_to_depth() (bit-identical, no division per pixel).
+__device__ __forceinline__ void emit_pixel_int(const OutputSpec& o, void* out, long long idx, int disp) {
+    if (o.kind == 1) {
+        static_cast<float*>(out)[idx] = static_cast<float>(disp);
+    } else if (o.kind == 0) {
+        float z = 0.0f;
+        if (disp != 0) z = o.depth_lut ? __ldg(o.depth_lut + disp) : disparity_to_depth(static_cast<float>(disp), o.depth_scale);
+        static_cast<float*>(out)[idx] = z;
+    } else {
+        emit_pixel(o, out, idx, static_cast<float>(disp));
     }
 }
 
@@ -202,6 +281,15 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// same with an L2 cache-policy hint (evict-first for the one-pass event stream)
+__device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
 

@@ -60,6 +60,7 @@ struct EventParams {
     int conditional;  // 1: this launch is the fix-up pass, runs only if state->redo
     int verify;       // 1: bounds were assumed (sorted / given) -> check every event against them
     int arm_fixup;    // 1: the last CTA arms the fix-up pass when a violation was seen
+    int stages;       // depth of the shared-memory event ring (1..kMaxStages)
 };
 
 __device__ __forceinline__ bool event_valid(const EventFields& e, int polarity) {
@@ -175,21 +176,34 @@ __global__ void __launch_bounds__(256) bounds_reduce_kernel(const int4* __restri
 // ---------------------------------------------------------------------------------------------
 // K1: the fused per-event kernel.
 //
-// Each CTA owns one contiguous span of the event buffer and walks it in chunks of kEvChunk
-// events.  Per chunk every thread issues kEvPerThread independent 128-bit event loads followed by
-// the dependent LUT gathers; the block then agrees on the range of X-map time columns the chunk
-// needs.  For a time-sorted stream that range is 1-3 columns, which (in the transposed layout) is
-// one contiguous byte range: thread 0 stages it into shared memory with a single 1-D bulk async
-// copy (TMA) signalled on an mbarrier, and the lookups become shared-memory reads.  Chunks whose
-// range does not fit (unsorted input) read the transposed table through L2 instead.
+// Each CTA owns one contiguous span of the event buffer and walks it in chunks of kEvChunk events.
+// The chunks are streamed into a ring of shared-memory stages with 1-D bulk async copies (TMA,
+// L2 evict-first hint) signalled on per-stage mbarriers: thread 0 keeps `stages` chunks in flight,
+// so HBM latency is covered by the ring and not by registers.  Per chunk every thread takes
+// kEvPerThread events from the stage (conflict-free 128-bit shared loads), applies the polarity
+// mask, issues the dependent packed-LUT gathers (L2) and computes the X-map time column; the block
+// then agrees on the range of columns the chunk needs.  For a time-sorted stream that range is 1-3
+// columns, which in the transposed layout is ONE contiguous byte range: if it is not resident,
+// thread 0 stages it with a single bulk copy and the lookups become shared-memory reads.  Chunks
+// whose range does not fit (unsorted input) read the transposed table through L2 instead.
+// Inliers are scattered with a 64-bit atomicMax (RED) whose key orders by event index.
 // ---------------------------------------------------------------------------------------------
+constexpr int kMaxStages = 6;
+constexpr int kEvSmemHeader = 256;  // mbarriers + reduction scratch
+
+__host__ __device__ inline int events_smem_bytes(int stages, int win_bytes) {
+    return kEvSmemHeader + stages * kEvChunk * 16 + win_bytes;
+}
+
 template <bool F64>
-__global__ void __launch_bounds__(kEvThreads, 4) events_kernel(const EventParams p) {
+__global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams p) {
     extern __shared__ __align__(128) unsigned char ev_smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(ev_smem);
-    int* s_min = reinterpret_cast<int*>(ev_smem + 16);       // [2][8]
-    int* s_max = reinterpret_cast<int*>(ev_smem + 16 + 64);  // [2][8]
-    short* s_cols = reinterpret_cast<short*>(ev_smem + 256);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ev_smem);         // [kMaxStages]
+    uint64_t* colbar = reinterpret_cast<uint64_t*>(ev_smem + 64);  // X-map window copy
+    int* s_min = reinterpret_cast<int*>(ev_smem + 128);            // [2][8]
+    int* s_max = reinterpret_cast<int*>(ev_smem + 192);            // [2][8]
+    const int4* s_ev = reinterpret_cast<const int4*>(ev_smem + kEvSmemHeader);
+    short* s_cols = reinterpret_cast<short*>(ev_smem + kEvSmemHeader + p.stages * kEvChunk * 16);
 
     FrameState* st = p.state;
     if (p.conditional && !*reinterpret_cast<volatile unsigned*>(&st->redo)) return;
@@ -198,62 +212,73 @@ __global__ void __launch_bounds__(kEvThreads, 4) events_kernel(const EventParams
     const int lane = tid & 31;
     const int warp = tid >> 5;
 
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
-
-    TimeNorm<F64> tn;
-    tn.init(st->t_lo_bits, st->t_hi_bits, p.t_px_scale);
-
     // span of this CTA: equal shares, boundaries on multiples of 32 events (512 B)
     const long long per = ((p.n + gridDim.x - 1) / gridDim.x + 31) & ~31LL;
     const long long span_lo = per * blockIdx.x < p.n ? per * blockIdx.x : p.n;
     const long long span_hi = span_lo + per < p.n ? span_lo + per : p.n;
-
+    const int span_len = static_cast<int>(span_hi - span_lo);
+    const int n_chunks = (span_len + kEvChunk - 1) / kEvChunk;
+    const int4* span_ptr = p.events + span_lo;
     const uint64_t pol = make_evict_first_policy();
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) mbar_init(full + s, 1);
+        mbar_init(colbar, 1);
+        // prologue: fill the ring
+        const int pre = n_chunks < p.stages ? n_chunks : p.stages;
+        for (int c = 0; c < pre; ++c) {
+            const unsigned bytes = static_cast<unsigned>(min(kEvChunk, span_len - c * kEvChunk)) * 16u;
+            mbar_expect_tx(full + c, bytes);
+            tma_load_1d_hint(ev_smem + kEvSmemHeader + c * (kEvChunk * 16), span_ptr + c * kEvChunk, bytes, full + c, pol);
+        }
+    }
+    __syncthreads();
+
+    TimeCol<F64> tc;
+    tc.init(st->t_lo_bits, st->t_hi_bits, p.t_px_scale);
+
     unsigned n_valid = 0, n_inl = 0, flags = 0;
     int win_lo = 0, win_n = 0;
-    unsigned phase = 0;
-    int it = 0;
+    unsigned col_phase = 0;
+    int slot = 0;
+    unsigned ring_phase = 0;
 
-    for (long long base = span_lo; base < span_hi; base += kEvChunk, ++it) {
-        int4 raw[kEvPerThread];
-        bool ok[kEvPerThread];
-#pragma unroll
-        for (int k = 0; k < kEvPerThread; ++k) {
-            long long i = base + k * kEvThreads + tid;
-            ok[k] = i < span_hi;
-            if (ok[k]) raw[k] = ld_event_stream(p.events + i, pol);
-        }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int chunk_base = c * kEvChunk;
+        mbar_wait(full + slot, ring_phase);
+
         int col[kEvPerThread];
         int lut[kEvPerThread];
         int pix[kEvPerThread];
+        bool ok[kEvPerThread];
         int cmin = 0x7fffffff, cmax = -1;
 #pragma unroll
         for (int k = 0; k < kEvPerThread; ++k) {
+            const int i = chunk_base + k * kEvThreads + tid;
             col[k] = 0;
             lut[k] = 0;
             pix[k] = 0;
-            if (ok[k]) {
-                EventFields e = unpack_event(raw[k]);
-                ok[k] = event_valid(e, p.polarity);
-                if (ok[k]) {
+            ok[k] = false;
+            if (i < span_len) {
+                const EventFields e = unpack_event(s_ev[slot * kEvChunk + k * kEvThreads + tid]);
+                if (event_valid(e, p.polarity)) {
                     ++n_valid;
-                    if (e.x >= static_cast<unsigned>(p.cam_w) || e.y >= static_cast<unsigned>(p.cam_h)) {
-                        flags |= kStatusPixelOob;  // the reference raises IndexError here
-                        ok[k] = false;
-                    } else {
+                    if (e.x < static_cast<unsigned>(p.cam_w) && e.y < static_cast<unsigned>(p.cam_h)) {
+                        ok[k] = true;
                         pix[k] = static_cast<int>(e.y) * p.cam_w + static_cast<int>(e.x);
                         lut[k] = __ldg(p.lut_xy + pix[k]);
-                        if (p.verify && tn.outside(e.t_bits)) flags |= kStatusTBounds;
-                        int c = tn.column(e.t_bits);
-                        if (c < 0) c += p.xmap_w;  // NumPy negative index (only reachable with wrong bounds)
-                        if (c < 0 || c >= p.xmap_w) {
+                        bool viol;
+                        int cc = tc.column(e.t_bits, viol);
+                        if (cc < 0) cc += p.xmap_w;  // NumPy negative index (only reachable with wrong bounds)
+                        if (viol || cc < 0 || cc >= p.xmap_w) {
                             flags |= kStatusTBounds;
-                            c = 0;
+                            cc = 0;
                         }
-                        col[k] = c;
-                        cmin = min(cmin, c);
-                        cmax = max(cmax, c);
+                        col[k] = cc;
+                        cmin = min(cmin, cc);
+                        cmax = max(cmax, cc);
+                    } else {
+                        flags |= kStatusPixelOob;  // the reference raises IndexError here
                     }
                 }
             }
@@ -261,18 +286,25 @@ __global__ void __launch_bounds__(kEvThreads, 4) events_kernel(const EventParams
         // block-wide column range of this chunk
         cmin = __reduce_min_sync(0xffffffffu, cmin);
         cmax = __reduce_max_sync(0xffffffffu, cmax);
-        const int buf = (it & 1) * 8;
+        const int buf = (c & 1) * 8;
         if (lane == 0) {
             s_min[buf + warp] = cmin;
             s_max[buf + warp] = cmax;
         }
-        __syncthreads();  // also: every thread is done reading the window of the previous chunk
-        {
-            int v0 = s_min[buf + (lane & 7)];
-            int v1 = s_max[buf + (lane & 7)];
-            cmin = __reduce_min_sync(0xffffffffu, v0);
-            cmax = __reduce_max_sync(0xffffffffu, v1);
+        __syncthreads();  // every thread has taken its events out of `slot` and is done with the
+                          // X-map window of the previous chunk
+        if (tid == 0 && c + p.stages < n_chunks) {  // refill the stage just drained
+            const int cn = c + p.stages;
+            const unsigned bytes = static_cast<unsigned>(min(kEvChunk, span_len - cn * kEvChunk)) * 16u;
+            mbar_expect_tx(full + slot, bytes);
+            tma_load_1d_hint(ev_smem + kEvSmemHeader + slot * (kEvChunk * 16), span_ptr + cn * kEvChunk, bytes, full + slot, pol);
         }
+        if (++slot == p.stages) {
+            slot = 0;
+            ring_phase ^= 1u;
+        }
+        cmin = __reduce_min_sync(0xffffffffu, s_min[buf + (lane & 7)]);
+        cmax = __reduce_max_sync(0xffffffffu, s_max[buf + (lane & 7)]);
         if (cmax < 0) continue;  // no valid event in this chunk (uniform across the CTA)
 
         bool from_smem = false;
@@ -284,43 +316,45 @@ __global__ void __launch_bounds__(kEvThreads, 4) events_kernel(const EventParams
                 win_n = min(min(need + p.lookahead, p.cap_cols), p.xmap_w - cmin);
                 if (tid == 0) {
                     const unsigned bytes = static_cast<unsigned>(win_n) * p.col_stride * 2u;
-                    mbar_expect_tx(bar, bytes);
-                    tma_load_1d(s_cols, p.xmap_t + static_cast<long long>(win_lo) * p.col_stride, bytes, bar);
+                    mbar_expect_tx(colbar, bytes);
+                    tma_load_1d(s_cols, p.xmap_t + static_cast<long long>(win_lo) * p.col_stride, bytes, colbar);
                 }
-                mbar_wait(bar, phase);
-                phase ^= 1u;
+                mbar_wait(colbar, col_phase);
+                col_phase ^= 1u;
             }
         }
 
+        const unsigned idx_base = static_cast<unsigned>(span_lo) + static_cast<unsigned>(chunk_base + tid);
 #pragma unroll
         for (int k = 0; k < kEvPerThread; ++k) {
-            if (!ok[k]) continue;
             const int xcr = static_cast<short>(lut[k] & 0xffff);
             const int ycr = lut[k] >> 16;
-            if (ycr < 0 || ycr >= p.xmap_h - 1) continue;  // x_maps_disparity.py:23 (last row excluded)
-            int xp;
-            if (from_smem)
-                xp = s_cols[(col[k] - win_lo) * p.col_stride + ycr];
-            else
-                xp = __ldg(p.xmap_t + static_cast<long long>(col[k]) * p.col_stride + ycr);
-            const int disp = static_cast<short>(xp - xcr - p.x_offset);  // int16 arithmetic wraps
-            if (disp < 0) continue;
-            ++n_inl;
-            long long cell;
-            if (p.view == 1) {
-                cell = pix[k];
-            } else {
-                int xpr = static_cast<short>(xcr + disp);
-                int ypr = ycr;
-                if (xpr < 0) xpr += p.rect_w;  // NumPy negative index wraps once
-                if (xpr < 0 || xpr >= p.rect_w || ypr >= p.rect_h) {
-                    flags |= kStatusScatterOob;  // the reference raises IndexError here
-                    continue;
-                }
-                cell = static_cast<long long>(ypr) * p.rect_w + xpr;
+            const bool y_ok = ok[k] && ycr >= 0 && ycr < p.xmap_h - 1;  // x_maps_disparity.py:23 (last row excluded)
+            int xp = 0;
+            if (y_ok) {
+                if (from_smem)
+                    xp = s_cols[(col[k] - win_lo) * p.col_stride + ycr];
+                else
+                    xp = __ldg(p.xmap_t + static_cast<long long>(col[k]) * p.col_stride + ycr);
             }
-            const unsigned long long idx = static_cast<unsigned long long>(base + k * kEvThreads + tid);
-            atomicMax(p.map + cell, make_key(p.epoch, idx, disp));
+            const int disp = static_cast<short>(xp - xcr - p.x_offset);  // int16 arithmetic wraps
+            if (y_ok && disp >= 0) {
+                ++n_inl;
+                int cell;
+                bool in_map = true;
+                if (p.view == 1) {
+                    cell = pix[k];
+                } else {
+                    int xpr = static_cast<short>(xcr + disp);
+                    if (xpr < 0) xpr += p.rect_w;  // NumPy negative index wraps once
+                    in_map = xpr >= 0 && xpr < p.rect_w && ycr < p.rect_h;
+                    cell = ycr * p.rect_w + xpr;
+                }
+                if (in_map)
+                    atomicMax(p.map + cell, make_key32(p.epoch, idx_base + static_cast<unsigned>(k * kEvThreads), disp));
+                else
+                    flags |= kStatusScatterOob;  // the reference raises IndexError here
+            }
         }
     }
 
@@ -373,7 +407,7 @@ __global__ void __launch_bounds__(256) epilogue_camera_kernel(const EpiloguePara
     const long long n = static_cast<long long>(p.out_w) * p.out_h;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        emit_pixel(p.out, p.dst, i, static_cast<float>(key_disparity(p.map[i], epoch)));
+        emit_pixel_int(p.out, p.dst, i, key_disparity(p.map[i], epoch));
     }
 }
 
@@ -387,7 +421,9 @@ __global__ void __launch_bounds__(256) epilogue_camera_kernel(const EpiloguePara
 // ---------------------------------------------------------------------------------------------
 constexpr int kTile = 32;
 
-__global__ void __launch_bounds__(256) epilogue_projector_kernel(const EpilogueParams p) {
+// R > 0: compile-time dilate radius (unrolled taps); R == 0: runtime radius p.radius.
+template <int R>
+__global__ void __launch_bounds__(256, 8) epilogue_projector_kernel(const EpilogueParams p) {
     extern __shared__ __align__(128) unsigned char ev_smem[];
     unsigned short* s_raw = reinterpret_cast<unsigned short*>(ev_smem);
     unsigned short* s_h = s_raw + p.region_cap;
@@ -397,20 +433,19 @@ __global__ void __launch_bounds__(256) epilogue_projector_kernel(const EpilogueP
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int u0 = blockIdx.x * kTile, v0 = blockIdx.y * kTile;
-    const int r = p.radius;
+    const int r = R > 0 ? R : p.radius;
 
     short2 m[4];
-    bool inside[4];
+    unsigned inside = 0;
     int x0 = 0x7fffffff, x1 = -1, y0 = 0x7fffffff, y1 = -1;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int u = u0 + lane, v = v0 + warp + k * 8;
-        inside[k] = false;
         m[k] = make_short2(0, 0);
         if (u < p.out_w && v < p.out_h) {
-            m[k] = __ldg(p.remap_xy + static_cast<long long>(v) * p.out_w + u);
-            inside[k] = m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h;
-            if (inside[k]) {
+            m[k] = __ldg(p.remap_xy + v * p.out_w + u);
+            if (m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h) {
+                inside |= 1u << k;
                 x0 = min(x0, static_cast<int>(m[k].x));
                 x1 = max(x1, static_cast<int>(m[k].x));
                 y0 = min(y0, static_cast<int>(m[k].y));
@@ -434,44 +469,59 @@ __global__ void __launch_bounds__(256) epilogue_projector_kernel(const EpilogueP
     x1 = __reduce_max_sync(0xffffffffu, s_box[2][lane & 7]);
     y1 = __reduce_max_sync(0xffffffffu, s_box[3][lane & 7]);
 
-    float val[4] = {0.f, 0.f, 0.f, 0.f};
+    int val[4] = {0, 0, 0, 0};
     if (x1 >= 0) {
         // region = bounding box + halo; cells outside the image count as 0 (disparities are >= 0,
         // so ignoring a tap, as cv2.dilate does at the border, equals reading 0)
         const int rx0 = x0 - r, ry0 = y0 - r;
         const int rw = x1 - x0 + 1 + 2 * r, rh = y1 - y0 + 1 + 2 * r;
         if (rw * rh <= p.region_cap) {
+            // flat index -> (row, col) with a multiply-high instead of a division (exact: c * rw < 2^32)
+            const unsigned magic_w = 0xffffffffu / static_cast<unsigned>(rw) + 1u;
             for (int c = tid; c < rw * rh; c += 256) {
-                const int ry = c / rw, rx = c - ry * rw;
+                const int ry = static_cast<int>(__umulhi(static_cast<unsigned>(c), magic_w));
+                const int rx = c - ry * rw;
                 const int gx = rx0 + rx, gy = ry0 + ry;
                 unsigned short d = 0;
                 if (gx >= 0 && gx < p.rect_w && gy >= 0 && gy < p.rect_h)
-                    d = static_cast<unsigned short>(key_disparity(p.map[static_cast<long long>(gy) * p.rect_w + gx], epoch));
+                    d = static_cast<unsigned short>(key_disparity(p.map[gy * p.rect_w + gx], epoch));
                 s_raw[c] = d;
             }
             __syncthreads();
             // horizontal max, only for the columns the vertical pass can read: rx in [r, rw - r)
             const int iw = rw - 2 * r;
+            const unsigned magic_i = 0xffffffffu / static_cast<unsigned>(iw) + 1u;
             for (int c = tid; c < iw * rh; c += 256) {
-                const int ry = c / iw, rx = c - ry * iw + r;
+                const int ry = static_cast<int>(__umulhi(static_cast<unsigned>(c), magic_i));
+                const int rx = c - ry * iw + r;
                 const unsigned short* row = s_raw + ry * rw + rx;
-                unsigned short best = 0;
-                for (int d = -r; d <= r; ++d) best = max(best, row[d]);
-                s_h[ry * rw + rx] = best;
+                unsigned best = 0;
+                if (R > 0) {
+#pragma unroll
+                    for (int d = -R; d <= R; ++d) best = max(best, static_cast<unsigned>(row[d]));
+                } else {
+                    for (int d = -r; d <= r; ++d) best = max(best, static_cast<unsigned>(row[d]));
+                }
+                s_h[ry * rw + rx] = static_cast<unsigned short>(best);
             }
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (!inside[k]) continue;
-                const int cx = m[k].x - rx0, cy = m[k].y - ry0;
-                unsigned short best = 0;
-                for (int d = -r; d <= r; ++d) best = max(best, s_h[(cy + d) * rw + cx]);
-                val[k] = static_cast<float>(best);
+                if (!(inside & (1u << k))) continue;
+                const unsigned short* colp = s_h + (m[k].y - ry0) * rw + (m[k].x - rx0);
+                unsigned best = 0;
+                if (R > 0) {
+#pragma unroll
+                    for (int d = -R; d <= R; ++d) best = max(best, static_cast<unsigned>(colp[d * rw]));
+                } else {
+                    for (int d = -r; d <= r; ++d) best = max(best, static_cast<unsigned>(colp[d * rw]));
+                }
+                val[k] = static_cast<int>(best);
             }
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (!inside[k]) continue;
+                if (!(inside & (1u << k))) continue;
                 int best = 0;
                 for (int dy = -r; dy <= r; ++dy) {
                     const int gy = m[k].y + dy;
@@ -479,17 +529,17 @@ __global__ void __launch_bounds__(256) epilogue_projector_kernel(const EpilogueP
                     for (int dx = -r; dx <= r; ++dx) {
                         const int gx = m[k].x + dx;
                         if (gx < 0 || gx >= p.rect_w) continue;
-                        best = max(best, key_disparity(p.map[static_cast<long long>(gy) * p.rect_w + gx], epoch));
+                        best = max(best, key_disparity(p.map[gy * p.rect_w + gx], epoch));
                     }
                 }
-                val[k] = static_cast<float>(best);
+                val[k] = best;
             }
         }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int u = u0 + lane, v = v0 + warp + k * 8;
-        if (u < p.out_w && v < p.out_h) emit_pixel(p.out, p.dst, static_cast<long long>(v) * p.out_w + u, val[k]);
+        if (u < p.out_w && v < p.out_h) emit_pixel_int(p.out, p.dst, v * p.out_w + u, val[k]);
     }
 }
 

@@ -277,6 +277,12 @@ __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ 
         emit_pixel(out, dst, i, disp[i]);
 }
 
+// depth of every integer disparity 0..n-1 (context set-up; feeds emit_pixel_int)
+__global__ void __launch_bounds__(256) depth_lut_kernel(float* __restrict__ lut, int n, double depth_scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lut[i] = disparity_to_depth(static_cast<float>(i), depth_scale);
+}
+
 // CamProjMaps.construct_point_cloud (cam_proj_calibration.py:319-331), float32 arithmetic.
 struct Mat4f {
     float m[16];
