@@ -369,6 +369,11 @@ def run_ours(args):
         except Exception:
             pass
 
+    if args.quick:  # parameter sweeps: kernel numbers only
+        print(json.dumps({"quick": True, "options": args.opt, "value": value, "frame_us": roofline["frame_us"],
+                          "k1_us": k1_us, "k2_us": k2_us, "k1_frac": roofline["frac"], "events": n, "frames": F}), flush=True)
+        return
+
     # ---- parity spot check + CPU baseline on one frame of the same workload -------------------
     ev_host = host_frame(frames[0])
     want, cpu = cpu_baseline_sample(ev_host, tables, runs=args.cpu_runs)
@@ -450,6 +455,7 @@ def main():
     ap.add_argument("--e2e-reps", type=int, default=3)
     ap.add_argument("--ref-workers", type=int, default=32)
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
+    ap.add_argument("--quick", action="store_true", help="print kernel timings only (no CPU baseline / e2e); single GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

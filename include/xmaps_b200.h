@@ -136,6 +136,8 @@ int xm_ctx_set_colormap(XmCtx* ctx, const uint8_t* h_bgr256);
  *   "stage_xmap"      0/1  stage X-map time columns into shared memory with 1-D bulk (TMA) copies [1]
  *   "smem_cols_bytes" shared-memory budget per CTA for that window                              [16384]
  *   "stages"          depth of K1's shared-memory event ring (16 KB per stage, TMA-filled)      [3]
+  *   "safe_tables"     0/1  allow the check-free scatter of K1 when the tables were verified at upload
+ *                     (every defined X-map cell in [x_offset, x_offset + rect_w), LUT x > -x_offset) [1]
  *   "lookahead"       extra columns fetched ahead of a time-sorted stream                       [1]
  *   "auto_fixup"      0/1  with XM_TBOUNDS_SORTED / _GIVEN: when an event lies outside the assumed
  *                     bounds, redo the frame on the device with exact (reduced) bounds         [1]

@@ -114,6 +114,30 @@ def test_default_100k_matches_reference(default, manifest, view, tag):
     assert st["n_inliers"] == manifest["configs"]["default"]["n_inliers"]
 
 
+def test_checked_scatter_variant(default):
+    """The tables of a valid calibration select the check-free scatter; the checked variant must
+    give the same frames, and corrupt X-map cells must be reported, not written out of bounds."""
+    tables, _, eng = default
+    ev = orc.synth_events(0, 100_000, 640, 480)
+    assert eng.get_option("safe_tables") == 1
+    want = golden_frame("default_100k_proj")["depth"]
+    eng.set_option("safe_tables", 0)
+    try:
+        assert eng.get_option("safe_tables") == 0
+        assert np.array_equal(eng.frame(ev, view=0).cpu().numpy(), want)
+    finally:
+        eng.set_option("safe_tables", 1)
+    bad = tables.x_map.copy()
+    bad[200:900:7, 100:600:5] = tables.x_offset + tables.rect_w + 50  # outside the rectified image
+    eng2 = make_engine(type(tables)(**{**tables.__dict__, "x_map": bad}))
+    try:
+        assert eng2.get_option("safe_tables") == 0
+        eng2.frame(ev, view=0)
+        assert eng2.status()["scatter_oob"]
+    finally:
+        eng2.close()
+
+
 def test_default_1m_hashes(default, manifest):
     _, _, eng = default
     h = manifest["configs"]["default"]["hash"]

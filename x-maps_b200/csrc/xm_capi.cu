@@ -93,6 +93,7 @@ struct XmCtx {
     int opt_lookahead = 1;
     int opt_ctas_per_sm = 0;  // 0 = occupancy query
     int opt_smem_cols_bytes = 16 * 1024;
+    int opt_safe_tables = 1;  // use the check-free scatter when the tables were verified
     int opt_stages = 3;  // depth of the shared-memory event ring of K1
     int opt_region_cells = 64 * 64;
     // per-kernel CUDA-event timing (option "profile"): pairs around K1 and K2 of every frame
@@ -104,6 +105,7 @@ struct XmCtx {
     // derived
     int ev_occ_i64 = 0, ev_occ_f64 = 0;
     int ev_smem = 0, cap_cols = 0;
+    bool lut_safe = false, xmap_safe = false;  // table ranges verified: scatter targets always inside the map
 };
 
 namespace {
@@ -120,6 +122,12 @@ unsigned next_epoch(XmCtx* c, unsigned count, cudaStream_t s, cudaError_t* err) 
     return e;
 }
 
+using EvKernel = void (*)(xm::EventParams);
+EvKernel ev_kernel(bool f64, bool safe) {
+    if (f64) return safe ? xm::events_kernel<true, true> : xm::events_kernel<true, false>;
+    return safe ? xm::events_kernel<false, true> : xm::events_kernel<false, false>;
+}
+
 int configure_event_kernels(XmCtx* c) {
     int cols = 0;
     if (c->opt_stage_xmap && c->col_stride > 0) cols = c->opt_smem_cols_bytes / (c->col_stride * 2);
@@ -130,16 +138,20 @@ int configure_event_kernels(XmCtx* c) {
     // contexts with different X-map geometries can coexist in one process
     int optin = 0;
     XM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    cudaFuncAttributes fa0, fa1;
-    XM_CUDA(cudaFuncGetAttributes(&fa0, xm::events_kernel<false>));
-    XM_CUDA(cudaFuncGetAttributes(&fa1, xm::events_kernel<true>));
-    const int dyn0 = optin - static_cast<int>(fa0.sharedSizeBytes), dyn1 = optin - static_cast<int>(fa1.sharedSizeBytes);
-    if (c->ev_smem > dyn0 || c->ev_smem > dyn1)
-        return fail(XM_ERR_UNSUPPORTED, "event kernel needs %d B of shared memory, device allows %d", c->ev_smem, dyn0 < dyn1 ? dyn0 : dyn1);
-    XM_CUDA(cudaFuncSetAttribute(xm::events_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn0));
-    XM_CUDA(cudaFuncSetAttribute(xm::events_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn1));
-    XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ev_occ_i64, xm::events_kernel<false>, xm::kEvThreads, c->ev_smem));
-    XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ev_occ_f64, xm::events_kernel<true>, xm::kEvThreads, c->ev_smem));
+    c->ev_occ_i64 = c->ev_occ_f64 = 1 << 30;
+    for (int f64 = 0; f64 < 2; ++f64)
+        for (int safe = 0; safe < 2; ++safe) {
+            EvKernel k = ev_kernel(f64 != 0, safe != 0);
+            cudaFuncAttributes fa;
+            XM_CUDA(cudaFuncGetAttributes(&fa, k));
+            const int dyn = optin - static_cast<int>(fa.sharedSizeBytes);
+            if (c->ev_smem > dyn) return fail(XM_ERR_UNSUPPORTED, "event kernel needs %d B of shared memory, device allows %d", c->ev_smem, dyn);
+            XM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+            int occ = 0;
+            XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, xm::kEvThreads, c->ev_smem));
+            int& dst = f64 ? c->ev_occ_f64 : c->ev_occ_i64;
+            dst = occ < dst ? occ : dst;
+        }
     if (c->ev_occ_i64 < 1 || c->ev_occ_f64 < 1) return fail(XM_ERR_UNSUPPORTED, "event kernel does not fit an SM (smem %d B)", c->ev_smem);
     return XM_OK;
 }
@@ -149,6 +161,15 @@ int upload_xmap(XmCtx* c, const int16_t* h_x_map, int rows, int cols, int t_px_s
     // asserts of the reference (x_maps_disparity.py:52-53)
     if (rows > 32767) return fail(XM_ERR_TABLE_RANGE, "x_map has %d rows, int16 indices allow 32767", rows);
     if (cols > 32767) return fail(XM_ERR_TABLE_RANGE, "x_map has %d time columns, int16 indices allow 32767", cols);
+    // With every defined X-map cell in [x_offset, x_offset + rect_w) (and LUT x > -x_offset, checked at
+    // creation, so that undefined cells can never produce disp >= 0) an inlier's scatter target
+    // x_rect + disp = x_map - x_offset is always inside the map: K1 may skip the checks.
+    bool safe = rows <= c->rect_h;
+    for (size_t i = 0, e = static_cast<size_t>(rows) * cols; i < e && safe; ++i) {
+        const int v = h_x_map[i];
+        safe = v == 0 || (v >= x_offset && v < x_offset + c->rect_w);
+    }
+    c->xmap_safe = safe;
     const int stride = (rows + 7) & ~7;  // 16-byte multiple: one column range = one bulk copy
     std::vector<short> t(static_cast<size_t>(cols) * stride, 0);
     for (int y = 0; y < rows; ++y)
@@ -296,10 +317,8 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     if (a->n_events > 0) {
         const int occ = c->opt_ctas_per_sm > 0 ? c->opt_ctas_per_sm : (f64 ? c->ev_occ_f64 : c->ev_occ_i64);
         const int grid = grid_for(a->n_events, xm::kEvThreads, xm::kEvPerThread, c->sm_count * occ);
-        if (f64)
-            xm::events_kernel<true><<<grid, xm::kEvThreads, c->ev_smem, s>>>(p);
-        else
-            xm::events_kernel<false><<<grid, xm::kEvThreads, c->ev_smem, s>>>(p);
+        const EvKernel k1 = ev_kernel(f64, c->lut_safe && c->xmap_safe && c->opt_safe_tables);
+        k1<<<grid, xm::kEvThreads, c->ev_smem, s>>>(p);
         XM_LAUNCHED();
         if (fixup) {
             // runs only if K1 found an event outside the assumed bounds (state->redo)
@@ -313,10 +332,7 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
             p.verify = 0;
             p.arm_fixup = 0;
             p.epoch = epoch + 1;
-            if (f64)
-                xm::events_kernel<true><<<grid, xm::kEvThreads, c->ev_smem, s>>>(p);
-            else
-                xm::events_kernel<false><<<grid, xm::kEvThreads, c->ev_smem, s>>>(p);
+            k1<<<grid, xm::kEvThreads, c->ev_smem, s>>>(p);
             XM_LAUNCHED();
         }
     }
@@ -412,6 +428,9 @@ int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
     const size_t cam_px = static_cast<size_t>(t->cam_w) * t->cam_h;
     {
         std::vector<int> packed(cam_px);
+        int min_x = 32767;
+        for (size_t i = 0; i < cam_px; ++i) min_x = t->lut_x[i] < min_x ? t->lut_x[i] : min_x;
+        c->lut_safe = min_x > -t->x_offset && t->x_offset > 0;
         for (size_t i = 0; i < cam_px; ++i)
             packed[i] = static_cast<int>((static_cast<unsigned>(static_cast<unsigned short>(t->lut_y[i])) << 16) |
                                          static_cast<unsigned short>(t->lut_x[i]));
@@ -507,6 +526,10 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         c->opt_stages = v;
         return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
     }
+    if (!strcmp(key, "safe_tables")) {
+        c->opt_safe_tables = v != 0;
+        return XM_OK;
+    }
     if (!strcmp(key, "auto_fixup")) {
         c->opt_auto_fixup = v != 0;
         return XM_OK;
@@ -552,6 +575,7 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     if (!strcmp(key, "stage_xmap")) *value = c->opt_stage_xmap;
     else if (!strcmp(key, "smem_cols_bytes")) *value = c->opt_smem_cols_bytes;
     else if (!strcmp(key, "stages")) *value = c->opt_stages;
+    else if (!strcmp(key, "safe_tables")) *value = c->opt_safe_tables && c->lut_safe && c->xmap_safe;
     else if (!strcmp(key, "auto_fixup")) *value = c->opt_auto_fixup;
     else if (!strcmp(key, "lookahead")) *value = c->opt_lookahead;
     else if (!strcmp(key, "ctas_per_sm")) *value = c->opt_ctas_per_sm;

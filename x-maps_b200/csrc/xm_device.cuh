@@ -164,6 +164,25 @@ struct TimeCol {
         }
         return exact(num);
     }
+
+    // Hot-loop variant, valid only when `fast`: returns a column in [0, T_PX_SCALE] (0 if `viol`).
+    __device__ __forceinline__ int column_fast(long long t_bits, bool& viol) const {
+        double num;
+        if (F64) {
+            const double t = __longlong_as_double(t_bits);
+            viol = !(t >= lo_f && t <= hi_f);
+            num = __dsub_rn(t, lo_f);
+        } else {
+            const unsigned long long dt = static_cast<unsigned long long>(t_bits) - lo_u;
+            viol = dt > range;
+            num = static_cast<double>(static_cast<unsigned>(dt));
+        }
+        const double a = __dmul_rn(num, inv);
+        const int k = __double2int_rn(a);
+        if (viol) return 0;
+        if (fabs(__dsub_rn(a, static_cast<double>(k))) < 0.4999) return k;
+        return exact(num);
+    }
 };
 
 // ---------------------------------------------------------------------------------------------

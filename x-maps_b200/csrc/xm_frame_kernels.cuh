@@ -177,16 +177,20 @@ __global__ void __launch_bounds__(256) bounds_reduce_kernel(const int4* __restri
 // K1: the fused per-event kernel.
 //
 // Each CTA owns one contiguous span of the event buffer and walks it in chunks of kEvChunk events.
-// The chunks are streamed into a ring of shared-memory stages with 1-D bulk async copies (TMA,
-// L2 evict-first hint) signalled on per-stage mbarriers: thread 0 keeps `stages` chunks in flight,
-// so HBM latency is covered by the ring and not by registers.  Per chunk every thread takes
-// kEvPerThread events from the stage (conflict-free 128-bit shared loads), applies the polarity
-// mask, issues the dependent packed-LUT gathers (L2) and computes the X-map time column; the block
-// then agrees on the range of columns the chunk needs.  For a time-sorted stream that range is 1-3
-// columns, which in the transposed layout is ONE contiguous byte range: if it is not resident,
-// thread 0 stages it with a single bulk copy and the lookups become shared-memory reads.  Chunks
-// whose range does not fit (unsorted input) read the transposed table through L2 instead.
-// Inliers are scattered with a 64-bit atomicMax (RED) whose key orders by event index.
+//
+//  * Event stream: the chunks are streamed into a ring of shared-memory stages with 1-D bulk async
+//    copies (TMA, L2 evict-first hint) signalled on per-stage mbarriers; thread 0 keeps `stages`
+//    chunks in flight, so HBM latency is covered by the ring and not by registers.
+//  * Software pipeline: iteration c runs the FRONT half of chunk c+1 (take kEvPerThread events per
+//    thread from the stage with conflict-free 128-bit shared loads, polarity mask, issue the
+//    dependent packed-LUT gathers, compute the X-map time column, reduce the chunk's column range)
+//    and then the BACK half of chunk c (X-map lookup, disparity, scatter), so the L2 latency of the
+//    LUT gathers is hidden behind a whole chunk of work.
+//  * X-map: for a time-sorted stream a chunk needs 1-3 adjacent time columns, which in the
+//    transposed layout is ONE contiguous byte range; when it is not resident thread 0 stages it
+//    with a single bulk copy one chunk ahead of its use, and lookups are shared-memory reads.
+//    Chunks whose range does not fit (unsorted input) read the transposed table through L2.
+//  * Scatter: 64-bit atomicMax whose key orders by event index (last write wins, deterministic).
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxStages = 6;
 constexpr int kEvSmemHeader = 256;  // mbarriers + reduction scratch
@@ -195,15 +199,100 @@ __host__ __device__ inline int events_smem_bytes(int stages, int win_bytes) {
     return kEvSmemHeader + stages * kEvChunk * 16 + win_bytes;
 }
 
-template <bool F64>
+struct ChunkRegs {
+    int lut[kEvPerThread];  // packed (x_rect, y_rect) of the event's pixel
+    int col[kEvPerThread];  // X-map time column, -1 = event dropped
+    int pix[kEvPerThread];  // camera pixel index
+};
+
+// FRONT half.  FULL: the chunk has kEvChunk events (no per-event bound check).  FAST: TimeCol::fast.
+template <bool F64, bool FULL, bool FAST>
+__device__ __forceinline__ void front_half(const EventParams& p, const TimeCol<F64>& tc, const int4* stage, int tid, int limit,
+                                           ChunkRegs& r, unsigned& cmin, int& cmax, unsigned& n_valid, unsigned& flags) {
+#pragma unroll
+    for (int k = 0; k < kEvPerThread; ++k) {
+        r.col[k] = -1;
+        r.lut[k] = 0;
+        r.pix[k] = 0;
+        if (FULL || k * kEvThreads + tid < limit) {
+            const EventFields e = unpack_event(stage[k * kEvThreads + tid]);
+            if (event_valid(e, p.polarity)) {
+                ++n_valid;
+                if (e.x < static_cast<unsigned>(p.cam_w) && e.y < static_cast<unsigned>(p.cam_h)) {
+                    r.pix[k] = static_cast<int>(e.y) * p.cam_w + static_cast<int>(e.x);
+                    r.lut[k] = __ldg(p.lut_xy + r.pix[k]);
+                    bool viol;
+                    int cc;
+                    if (FAST) {
+                        cc = tc.column_fast(e.t_bits, viol);
+                    } else {
+                        cc = tc.column(e.t_bits, viol);
+                        if (cc < 0) cc += p.xmap_w;  // NumPy negative index (only reachable with wrong bounds)
+                        viol = viol || cc < 0 || cc >= p.xmap_w;
+                        if (viol) cc = 0;
+                    }
+                    if (viol) flags |= kStatusTBounds;
+                    r.col[k] = cc;
+                } else {
+                    flags |= kStatusPixelOob;  // the reference raises IndexError here
+                }
+            }
+        }
+        cmin = min(cmin, static_cast<unsigned>(r.col[k]));  // -1 -> UINT_MAX: ignored
+        cmax = max(cmax, r.col[k]);
+    }
+}
+
+// BACK half.  SAFE: the tables were verified at upload so that every inlier's scatter target lies
+// inside the map (no wrap / bound checks needed).
+template <bool SAFE>
+__device__ __forceinline__ void back_half(const EventParams& p, const ChunkRegs& r, const short* s_cols, bool from_smem, int win_lo,
+                                          unsigned idx_base, unsigned& n_inl, unsigned& flags) {
+#pragma unroll
+    for (int k = 0; k < kEvPerThread; ++k) {
+        const int xcr = static_cast<short>(r.lut[k] & 0xffff);
+        const int ycr = r.lut[k] >> 16;
+        // x_maps_disparity.py:23: 0 <= y_rect < H - 1 (last row excluded)
+        const bool y_ok = r.col[k] >= 0 && static_cast<unsigned>(ycr) < static_cast<unsigned>(p.xmap_h - 1);
+        int xp = 0;
+        if (y_ok) {
+            if (from_smem)
+                xp = s_cols[(r.col[k] - win_lo) * p.col_stride + ycr];
+            else
+                xp = __ldg(p.xmap_t + static_cast<long long>(r.col[k]) * p.col_stride + ycr);
+        }
+        const int disp = static_cast<short>(xp - xcr - p.x_offset);  // int16 arithmetic wraps
+        if (y_ok && disp >= 0) {
+            ++n_inl;
+            int cell;
+            bool in_map = true;
+            if (p.view == 1) {
+                cell = r.pix[k];
+            } else if (SAFE) {
+                cell = ycr * p.rect_w + (xp - p.x_offset);  // = x_rect + disp, in [0, rect_w)
+            } else {
+                int xpr = static_cast<short>(xcr + disp);
+                if (xpr < 0) xpr += p.rect_w;  // NumPy negative index wraps once
+                in_map = xpr >= 0 && xpr < p.rect_w && ycr < p.rect_h;
+                cell = ycr * p.rect_w + xpr;
+            }
+            if (in_map)
+                atomicMax(p.map + cell, make_key32(p.epoch, idx_base + static_cast<unsigned>(k * kEvThreads), disp));
+            else
+                flags |= kStatusScatterOob;  // the reference raises IndexError here
+        }
+    }
+}
+
+template <bool F64, bool SAFE>
 __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams p) {
     extern __shared__ __align__(128) unsigned char ev_smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(ev_smem);         // [kMaxStages]
-    uint64_t* colbar = reinterpret_cast<uint64_t*>(ev_smem + 64);  // X-map window copy
-    int* s_min = reinterpret_cast<int*>(ev_smem + 128);            // [2][8]
+    uint64_t* winbar = reinterpret_cast<uint64_t*>(ev_smem + 64);  // X-map window copy
+    unsigned* s_min = reinterpret_cast<unsigned*>(ev_smem + 128);  // [2][8]
     int* s_max = reinterpret_cast<int*>(ev_smem + 192);            // [2][8]
-    const int4* s_ev = reinterpret_cast<const int4*>(ev_smem + kEvSmemHeader);
-    short* s_cols = reinterpret_cast<short*>(ev_smem + kEvSmemHeader + p.stages * kEvChunk * 16);
+    unsigned char* ring = ev_smem + kEvSmemHeader;
+    short* s_cols = reinterpret_cast<short*>(ring + p.stages * (kEvChunk * 16));
 
     FrameState* st = p.state;
     if (p.conditional && !*reinterpret_cast<volatile unsigned*>(&st->redo)) return;
@@ -221,16 +310,17 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
     const int4* span_ptr = p.events + span_lo;
     const uint64_t pol = make_evict_first_policy();
 
+    auto issue_chunk = [&](int c, int slot) {  // thread 0 only
+        const unsigned bytes = static_cast<unsigned>(min(kEvChunk, span_len - c * kEvChunk)) * 16u;
+        mbar_expect_tx(full + slot, bytes);
+        tma_load_1d_hint(ring + slot * (kEvChunk * 16), span_ptr + c * kEvChunk, bytes, full + slot, pol);
+    };
+
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) mbar_init(full + s, 1);
-        mbar_init(colbar, 1);
-        // prologue: fill the ring
+        mbar_init(winbar, 1);
         const int pre = n_chunks < p.stages ? n_chunks : p.stages;
-        for (int c = 0; c < pre; ++c) {
-            const unsigned bytes = static_cast<unsigned>(min(kEvChunk, span_len - c * kEvChunk)) * 16u;
-            mbar_expect_tx(full + c, bytes);
-            tma_load_1d_hint(ev_smem + kEvSmemHeader + c * (kEvChunk * 16), span_ptr + c * kEvChunk, bytes, full + c, pol);
-        }
+        for (int c = 0; c < pre; ++c) issue_chunk(c, c);  // prologue: fill the ring
     }
     __syncthreads();
 
@@ -239,122 +329,88 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
 
     unsigned n_valid = 0, n_inl = 0, flags = 0;
     int win_lo = 0, win_n = 0;
-    unsigned col_phase = 0;
-    int slot = 0;
-    unsigned ring_phase = 0;
+    unsigned win_phase = 0;
+    bool win_pending = false;
 
-    for (int c = 0; c < n_chunks; ++c) {
-        const int chunk_base = c * kEvChunk;
-        mbar_wait(full + slot, ring_phase);
-
-        int col[kEvPerThread];
-        int lut[kEvPerThread];
-        int pix[kEvPerThread];
-        bool ok[kEvPerThread];
-        int cmin = 0x7fffffff, cmax = -1;
-#pragma unroll
-        for (int k = 0; k < kEvPerThread; ++k) {
-            const int i = chunk_base + k * kEvThreads + tid;
-            col[k] = 0;
-            lut[k] = 0;
-            pix[k] = 0;
-            ok[k] = false;
-            if (i < span_len) {
-                const EventFields e = unpack_event(s_ev[slot * kEvChunk + k * kEvThreads + tid]);
-                if (event_valid(e, p.polarity)) {
-                    ++n_valid;
-                    if (e.x < static_cast<unsigned>(p.cam_w) && e.y < static_cast<unsigned>(p.cam_h)) {
-                        ok[k] = true;
-                        pix[k] = static_cast<int>(e.y) * p.cam_w + static_cast<int>(e.x);
-                        lut[k] = __ldg(p.lut_xy + pix[k]);
-                        bool viol;
-                        int cc = tc.column(e.t_bits, viol);
-                        if (cc < 0) cc += p.xmap_w;  // NumPy negative index (only reachable with wrong bounds)
-                        if (viol || cc < 0 || cc >= p.xmap_w) {
-                            flags |= kStatusTBounds;
-                            cc = 0;
-                        }
-                        col[k] = cc;
-                        cmin = min(cmin, cc);
-                        cmax = max(cmax, cc);
-                    } else {
-                        flags |= kStatusPixelOob;  // the reference raises IndexError here
-                    }
-                }
-            }
+    // FRONT half of chunk c (c < n_chunks): fills `r`, publishes the warp's column range
+    auto front = [&](int c, ChunkRegs& r) {
+        const int slot = c % p.stages;
+        mbar_wait(full + slot, static_cast<unsigned>(c / p.stages) & 1u);
+        const int4* stage = reinterpret_cast<const int4*>(ring + slot * (kEvChunk * 16));
+        const int limit = span_len - c * kEvChunk;
+        unsigned cmin = 0xffffffffu;
+        int cmax = -1;
+        if (limit >= kEvChunk) {
+            if (tc.fast)
+                front_half<F64, true, true>(p, tc, stage, tid, limit, r, cmin, cmax, n_valid, flags);
+            else
+                front_half<F64, true, false>(p, tc, stage, tid, limit, r, cmin, cmax, n_valid, flags);
+        } else {
+            if (tc.fast)
+                front_half<F64, false, true>(p, tc, stage, tid, limit, r, cmin, cmax, n_valid, flags);
+            else
+                front_half<F64, false, false>(p, tc, stage, tid, limit, r, cmin, cmax, n_valid, flags);
         }
-        // block-wide column range of this chunk
         cmin = __reduce_min_sync(0xffffffffu, cmin);
         cmax = __reduce_max_sync(0xffffffffu, cmax);
-        const int buf = (c & 1) * 8;
         if (lane == 0) {
-            s_min[buf + warp] = cmin;
-            s_max[buf + warp] = cmax;
+            s_min[(c & 1) * 8 + warp] = cmin;
+            s_max[(c & 1) * 8 + warp] = cmax;
         }
-        __syncthreads();  // every thread has taken its events out of `slot` and is done with the
-                          // X-map window of the previous chunk
-        if (tid == 0 && c + p.stages < n_chunks) {  // refill the stage just drained
-            const int cn = c + p.stages;
-            const unsigned bytes = static_cast<unsigned>(min(kEvChunk, span_len - cn * kEvChunk)) * 16u;
-            mbar_expect_tx(full + slot, bytes);
-            tma_load_1d_hint(ev_smem + kEvSmemHeader + slot * (kEvChunk * 16), span_ptr + cn * kEvChunk, bytes, full + slot, pol);
-        }
-        if (++slot == p.stages) {
-            slot = 0;
-            ring_phase ^= 1u;
-        }
-        cmin = __reduce_min_sync(0xffffffffu, s_min[buf + (lane & 7)]);
-        cmax = __reduce_max_sync(0xffffffffu, s_max[buf + (lane & 7)]);
-        if (cmax < 0) continue;  // no valid event in this chunk (uniform across the CTA)
+    };
 
-        bool from_smem = false;
+    // after the block barrier that follows front(c): recycle the stage, decide how chunk c reads the X-map
+    // returns: 0 = chunk has no valid event, 1 = shared-memory window, 2 = through L2
+    auto after_barrier = [&](int c) -> int {
+        if (tid == 0 && c + p.stages < n_chunks) issue_chunk(c + p.stages, c % p.stages);
+        const int cmin = static_cast<int>(__reduce_min_sync(0xffffffffu, s_min[(c & 1) * 8 + (lane & 7)]));
+        const int cmax = __reduce_max_sync(0xffffffffu, s_max[(c & 1) * 8 + (lane & 7)]);
+        if (cmax < 0) return 0;
         const int need = cmax - cmin + 1;
-        if (need <= p.cap_cols) {
-            from_smem = true;
-            if (cmin < win_lo || cmax >= win_lo + win_n) {
-                win_lo = cmin;
-                win_n = min(min(need + p.lookahead, p.cap_cols), p.xmap_w - cmin);
-                if (tid == 0) {
-                    const unsigned bytes = static_cast<unsigned>(win_n) * p.col_stride * 2u;
-                    mbar_expect_tx(colbar, bytes);
-                    tma_load_1d(s_cols, p.xmap_t + static_cast<long long>(win_lo) * p.col_stride, bytes, colbar);
-                }
-                mbar_wait(colbar, col_phase);
-                col_phase ^= 1u;
+        if (need > p.cap_cols) return 2;
+        if (cmin < win_lo || cmax >= win_lo + win_n) {
+            win_lo = cmin;
+            win_n = min(min(need + p.lookahead, p.cap_cols), p.xmap_w - cmin);
+            if (tid == 0) {
+                const unsigned bytes = static_cast<unsigned>(win_n) * p.col_stride * 2u;
+                mbar_expect_tx(winbar, bytes);
+                tma_load_1d(s_cols, p.xmap_t + static_cast<long long>(win_lo) * p.col_stride, bytes, winbar);
             }
+            win_pending = true;
         }
+        return 1;
+    };
 
-        const unsigned idx_base = static_cast<unsigned>(span_lo) + static_cast<unsigned>(chunk_base + tid);
+    ChunkRegs cur;
+    int mode = 0;
+    if (n_chunks > 0) {  // (uniform) a trailing CTA may own an empty span
+        front(0, cur);
+        __syncthreads();
+        mode = after_barrier(0);
+    }
+
+    for (int c = 0; c < n_chunks; ++c) {
+        ChunkRegs nxt;
+        const bool has_next = c + 1 < n_chunks;
+        if (has_next) front(c + 1, nxt);
+        if (mode != 0) {
+            if (win_pending) {  // the window copy was issued one chunk ago
+                mbar_wait(winbar, win_phase);
+                win_phase ^= 1u;
+                win_pending = false;
+            }
+            const unsigned idx_base = static_cast<unsigned>(span_lo) + static_cast<unsigned>(c * kEvChunk + tid);
+            back_half<SAFE>(p, cur, s_cols, mode == 1, win_lo, idx_base, n_inl, flags);
+        }
+        if (!has_next) break;
+        __syncthreads();  // every thread has taken its events of chunk c+1 out of the ring and is done
+                          // with the X-map window of chunk c
+        mode = after_barrier(c + 1);
 #pragma unroll
         for (int k = 0; k < kEvPerThread; ++k) {
-            const int xcr = static_cast<short>(lut[k] & 0xffff);
-            const int ycr = lut[k] >> 16;
-            const bool y_ok = ok[k] && ycr >= 0 && ycr < p.xmap_h - 1;  // x_maps_disparity.py:23 (last row excluded)
-            int xp = 0;
-            if (y_ok) {
-                if (from_smem)
-                    xp = s_cols[(col[k] - win_lo) * p.col_stride + ycr];
-                else
-                    xp = __ldg(p.xmap_t + static_cast<long long>(col[k]) * p.col_stride + ycr);
-            }
-            const int disp = static_cast<short>(xp - xcr - p.x_offset);  // int16 arithmetic wraps
-            if (y_ok && disp >= 0) {
-                ++n_inl;
-                int cell;
-                bool in_map = true;
-                if (p.view == 1) {
-                    cell = pix[k];
-                } else {
-                    int xpr = static_cast<short>(xcr + disp);
-                    if (xpr < 0) xpr += p.rect_w;  // NumPy negative index wraps once
-                    in_map = xpr >= 0 && xpr < p.rect_w && ycr < p.rect_h;
-                    cell = ycr * p.rect_w + xpr;
-                }
-                if (in_map)
-                    atomicMax(p.map + cell, make_key32(p.epoch, idx_base + static_cast<unsigned>(k * kEvThreads), disp));
-                else
-                    flags |= kStatusScatterOob;  // the reference raises IndexError here
-            }
+            cur.lut[k] = nxt.lut[k];
+            cur.col[k] = nxt.col[k];
+            cur.pix[k] = nxt.pix[k];
         }
     }
 
@@ -370,9 +426,11 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
     if (p.arm_fixup) {
         // last CTA: if any event violated the assumed bounds, arm the fix-up pass
         __shared__ unsigned s_last;
-        __threadfence();
         __syncthreads();
-        if (tid == 0) s_last = (atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1);
+        if (tid == 0) {
+            __threadfence();
+            s_last = (atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1);
+        }
         __syncthreads();
         if (s_last && tid == 0) {
             __threadfence();
