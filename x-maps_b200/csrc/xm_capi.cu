@@ -72,6 +72,7 @@ struct XmCtx {
     float* d_lut_y_f32 = nullptr;
     short* d_xmap_t = nullptr;
     short2* d_remap_xy = nullptr;
+    short4* d_tile_box = nullptr;  // bounding box of the remap targets of every 32x32 output tile
     unsigned char* d_turbo = nullptr;
     float* d_depth_lut = nullptr;  // [32768], exact depth of every integer disparity
     bool have_turbo = false;
@@ -92,7 +93,7 @@ struct XmCtx {
     int opt_auto_fixup = 1;
     int opt_lookahead = 1;
     int opt_ctas_per_sm = 0;  // 0 = occupancy query
-    int opt_smem_cols_bytes = 16 * 1024;
+    int opt_smem_cols_bytes = 12 * 1024;
     int opt_safe_tables = 1;  // use the check-free scatter when the tables were verified
     int opt_stages = 3;  // depth of the shared-memory event ring of K1
     int opt_region_cells = 64 * 64;
@@ -345,6 +346,7 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     q.map = c->d_map;
     q.state = c->d_state;
     q.remap_xy = c->d_remap_xy;
+    q.tile_box = c->d_tile_box;
     q.rect_w = c->rect_w;
     q.rect_h = c->rect_h;
     q.radius = c->dilate / 2;
@@ -449,6 +451,26 @@ int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
         if (cudaMalloc(&c->d_remap_xy, bytes) != cudaSuccess ||
             cudaMemcpy(c->d_remap_xy, t->remap_xy, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(XM_ERR_CUDA, "uploading the remap table failed: %s", cudaGetErrorString(cudaGetLastError())));
+        const int tx = (t->proj_w + xm::kTile - 1) / xm::kTile, ty = (t->proj_h + xm::kTile - 1) / xm::kTile;
+        std::vector<short4> boxes(static_cast<size_t>(tx) * ty);
+        for (int by = 0; by < ty; ++by)
+            for (int bx = 0; bx < tx; ++bx) {
+                int x0 = 32767, y0 = 32767, x1 = -1, y1 = -1;
+                for (int v = by * xm::kTile; v < (by + 1) * xm::kTile && v < t->proj_h; ++v)
+                    for (int u = bx * xm::kTile; u < (bx + 1) * xm::kTile && u < t->proj_w; ++u) {
+                        const int mx = t->remap_xy[(static_cast<size_t>(v) * t->proj_w + u) * 2];
+                        const int my = t->remap_xy[(static_cast<size_t>(v) * t->proj_w + u) * 2 + 1];
+                        if (mx < 0 || mx >= t->rect_w || my < 0 || my >= t->rect_h) continue;
+                        x0 = mx < x0 ? mx : x0;
+                        x1 = mx > x1 ? mx : x1;
+                        y0 = my < y0 ? my : y0;
+                        y1 = my > y1 ? my : y1;
+                    }
+                boxes[static_cast<size_t>(by) * tx + bx] = make_short4(static_cast<short>(x0), static_cast<short>(y0), static_cast<short>(x1), static_cast<short>(y1));
+            }
+        if (cudaMalloc(&c->d_tile_box, boxes.size() * sizeof(short4)) != cudaSuccess ||
+            cudaMemcpy(c->d_tile_box, boxes.data(), boxes.size() * sizeof(short4), cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(XM_ERR_CUDA, "uploading the tile boxes failed: %s", cudaGetErrorString(cudaGetLastError())));
     }
     c->map_cells = static_cast<long long>(t->rect_w) * t->rect_h;
     if (static_cast<long long>(cam_px) > c->map_cells) c->map_cells = static_cast<long long>(cam_px);
@@ -481,6 +503,7 @@ int xm_ctx_destroy(XmCtx* c) {
     cudaFree(c->d_lut_y_f32);
     cudaFree(c->d_xmap_t);
     cudaFree(c->d_remap_xy);
+    cudaFree(c->d_tile_box);
     cudaFree(c->d_turbo);
     cudaFree(c->d_depth_lut);
     cudaFree(c->d_map);

@@ -303,6 +303,19 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
         : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// 4-byte asynchronous gather global -> shared (LDGSTS): completion is tracked per thread by
+// cp.async groups, not by a register scoreboard, so a later chunk's gathers never stall this one
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // same with an L2 cache-policy hint (evict-first for the one-pass event stream)
 __device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar, uint64_t policy) {
     asm volatile(

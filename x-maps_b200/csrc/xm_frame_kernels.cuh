@@ -193,94 +193,98 @@ __global__ void __launch_bounds__(256) bounds_reduce_kernel(const int4* __restri
 //  * Scatter: 64-bit atomicMax whose key orders by event index (last write wins, deterministic).
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxStages = 6;
-constexpr int kEvSmemHeader = 256;  // mbarriers + reduction scratch
+constexpr int kEvSmemHeader = 256;             // mbarriers + reduction scratch
+constexpr int kEvLutBytes = 2 * kEvChunk * 4;  // double-buffered gathered LUT words
 
 __host__ __device__ inline int events_smem_bytes(int stages, int win_bytes) {
-    return kEvSmemHeader + stages * kEvChunk * 16 + win_bytes;
+    return kEvSmemHeader + kEvLutBytes + stages * kEvChunk * 16 + win_bytes;
 }
 
 struct ChunkRegs {
-    int lut[kEvPerThread];  // packed (x_rect, y_rect) of the event's pixel
     int col[kEvPerThread];  // X-map time column, -1 = event dropped
     int pix[kEvPerThread];  // camera pixel index
 };
 
 // FRONT half.  FULL: the chunk has kEvChunk events (no per-event bound check).  FAST: TimeCol::fast.
+// The packed-LUT words are gathered asynchronously into `s_lut` (one cp.async group per chunk).
 template <bool F64, bool FULL, bool FAST>
-__device__ __forceinline__ void front_half(const EventParams& p, const TimeCol<F64>& tc, const int4* stage, int tid, int limit,
-                                           ChunkRegs& r, unsigned& cmin, int& cmax, unsigned& n_valid, unsigned& flags) {
+__device__ __forceinline__ void front_half(const EventParams& p, const TimeCol<F64>& tc, const int4* stage, int* s_lut, int tid,
+                                           int limit, unsigned pol_mask, ChunkRegs& r, unsigned& cmin, int& cmax,
+                                           unsigned& n_valid, unsigned& flags) {
 #pragma unroll
     for (int k = 0; k < kEvPerThread; ++k) {
-        r.col[k] = -1;
-        r.lut[k] = 0;
-        r.pix[k] = 0;
+        int cc = -1;
+        int pix = 0;
         if (FULL || k * kEvThreads + tid < limit) {
-            const EventFields e = unpack_event(stage[k * kEvThreads + tid]);
-            if (event_valid(e, p.polarity)) {
+            const int4 raw = stage[k * kEvThreads + tid];
+            // polarity: keep p == 1 (pol_mask = 0xffff) or everything (pol_mask = 0)
+            if ((((static_cast<unsigned>(raw.y) & 0xffffu) ^ 1u) & pol_mask) == 0u) {
                 ++n_valid;
-                if (e.x < static_cast<unsigned>(p.cam_w) && e.y < static_cast<unsigned>(p.cam_h)) {
-                    r.pix[k] = static_cast<int>(e.y) * p.cam_w + static_cast<int>(e.x);
-                    r.lut[k] = __ldg(p.lut_xy + r.pix[k]);
+                const unsigned ex = static_cast<unsigned>(raw.x) & 0xffffu, ey = static_cast<unsigned>(raw.x) >> 16;
+                if (ex < static_cast<unsigned>(p.cam_w) && ey < static_cast<unsigned>(p.cam_h)) {
+                    pix = static_cast<int>(ey) * p.cam_w + static_cast<int>(ex);
+                    cp_async_4(s_lut + k * kEvThreads + tid, p.lut_xy + pix);
+                    const long long t_bits = (static_cast<long long>(raw.w) << 32) | static_cast<unsigned>(raw.z);
                     bool viol;
-                    int cc;
                     if (FAST) {
-                        cc = tc.column_fast(e.t_bits, viol);
+                        cc = tc.column_fast(t_bits, viol);
                     } else {
-                        cc = tc.column(e.t_bits, viol);
+                        cc = tc.column(t_bits, viol);
                         if (cc < 0) cc += p.xmap_w;  // NumPy negative index (only reachable with wrong bounds)
                         viol = viol || cc < 0 || cc >= p.xmap_w;
                         if (viol) cc = 0;
                     }
-                    if (viol) flags |= kStatusTBounds;
-                    r.col[k] = cc;
+                    flags |= viol ? kStatusTBounds : 0u;
                 } else {
                     flags |= kStatusPixelOob;  // the reference raises IndexError here
                 }
             }
         }
-        cmin = min(cmin, static_cast<unsigned>(r.col[k]));  // -1 -> UINT_MAX: ignored
-        cmax = max(cmax, r.col[k]);
+        r.col[k] = cc;
+        r.pix[k] = pix;
+        cmin = min(cmin, static_cast<unsigned>(cc));  // -1 -> UINT_MAX: ignored
+        cmax = max(cmax, cc);
     }
+    cp_async_commit();
 }
 
 // BACK half.  SAFE: the tables were verified at upload so that every inlier's scatter target lies
-// inside the map (no wrap / bound checks needed).
-template <bool SAFE>
-__device__ __forceinline__ void back_half(const EventParams& p, const ChunkRegs& r, const short* s_cols, bool from_smem, int win_lo,
-                                          unsigned idx_base, unsigned& n_inl, unsigned& flags) {
+// inside the map (no wrap / bound checks).  FROM_SMEM: X-map columns come from the shared window
+// (kept a separate instantiation so that the hot path only ever waits on shared-memory loads).
+template <bool SAFE, bool FROM_SMEM>
+__device__ __forceinline__ void back_half(const EventParams& p, const ChunkRegs& r, const int* s_lut, const short* s_cols, int win_lo,
+                                          int tid, unsigned idx_base, unsigned& n_inl, unsigned& flags) {
+    const unsigned y_lim = static_cast<unsigned>(p.xmap_h - 1);
 #pragma unroll
     for (int k = 0; k < kEvPerThread; ++k) {
-        const int xcr = static_cast<short>(r.lut[k] & 0xffff);
-        const int ycr = r.lut[k] >> 16;
-        // x_maps_disparity.py:23: 0 <= y_rect < H - 1 (last row excluded)
-        const bool y_ok = r.col[k] >= 0 && static_cast<unsigned>(ycr) < static_cast<unsigned>(p.xmap_h - 1);
-        int xp = 0;
-        if (y_ok) {
-            if (from_smem)
-                xp = s_cols[(r.col[k] - win_lo) * p.col_stride + ycr];
-            else
-                xp = __ldg(p.xmap_t + static_cast<long long>(r.col[k]) * p.col_stride + ycr);
-        }
+        if (r.col[k] < 0) continue;
+        const int lut = s_lut[k * kEvThreads + tid];
+        const int xcr = static_cast<short>(lut & 0xffff);
+        const int ycr = lut >> 16;
+        if (static_cast<unsigned>(ycr) >= y_lim) continue;  // x_maps_disparity.py:23: 0 <= y_rect < H - 1
+        int xp;
+        if (FROM_SMEM)
+            xp = s_cols[(r.col[k] - win_lo) * p.col_stride + ycr];
+        else
+            xp = __ldg(p.xmap_t + static_cast<long long>(r.col[k]) * p.col_stride + ycr);
         const int disp = static_cast<short>(xp - xcr - p.x_offset);  // int16 arithmetic wraps
-        if (y_ok && disp >= 0) {
-            ++n_inl;
-            int cell;
-            bool in_map = true;
-            if (p.view == 1) {
-                cell = r.pix[k];
-            } else if (SAFE) {
-                cell = ycr * p.rect_w + (xp - p.x_offset);  // = x_rect + disp, in [0, rect_w)
-            } else {
-                int xpr = static_cast<short>(xcr + disp);
-                if (xpr < 0) xpr += p.rect_w;  // NumPy negative index wraps once
-                in_map = xpr >= 0 && xpr < p.rect_w && ycr < p.rect_h;
-                cell = ycr * p.rect_w + xpr;
-            }
-            if (in_map)
-                atomicMax(p.map + cell, make_key32(p.epoch, idx_base + static_cast<unsigned>(k * kEvThreads), disp));
-            else
+        if (disp < 0) continue;
+        ++n_inl;
+        int cell;
+        if (p.view == 1) {
+            cell = r.pix[k];
+        } else if (SAFE) {
+            cell = ycr * p.rect_w + (xp - p.x_offset);  // = x_rect + disp, in [0, rect_w)
+        } else {
+            int xpr = static_cast<short>(xcr + disp);
+            if (xpr < 0) xpr += p.rect_w;  // NumPy negative index wraps once
+            if (xpr < 0 || xpr >= p.rect_w || ycr >= p.rect_h) {
                 flags |= kStatusScatterOob;  // the reference raises IndexError here
+                continue;
+            }
+            cell = ycr * p.rect_w + xpr;
         }
+        atomicMax(p.map + cell, make_key32(p.epoch, idx_base + static_cast<unsigned>(k * kEvThreads), disp));
     }
 }
 
@@ -291,7 +295,8 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
     uint64_t* winbar = reinterpret_cast<uint64_t*>(ev_smem + 64);  // X-map window copy
     unsigned* s_min = reinterpret_cast<unsigned*>(ev_smem + 128);  // [2][8]
     int* s_max = reinterpret_cast<int*>(ev_smem + 192);            // [2][8]
-    unsigned char* ring = ev_smem + kEvSmemHeader;
+    int* s_lut = reinterpret_cast<int*>(ev_smem + kEvSmemHeader);  // [2][kEvChunk]
+    unsigned char* ring = ev_smem + kEvSmemHeader + kEvLutBytes;
     short* s_cols = reinterpret_cast<short*>(ring + p.stages * (kEvChunk * 16));
 
     FrameState* st = p.state;
@@ -309,6 +314,7 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
     const int n_chunks = (span_len + kEvChunk - 1) / kEvChunk;
     const int4* span_ptr = p.events + span_lo;
     const uint64_t pol = make_evict_first_policy();
+    const unsigned pol_mask = p.polarity ? 0xffffu : 0u;
 
     auto issue_chunk = [&](int c, int slot) {  // thread 0 only
         const unsigned bytes = static_cast<unsigned>(min(kEvChunk, span_len - c * kEvChunk)) * 16u;
@@ -331,25 +337,27 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
     int win_lo = 0, win_n = 0;
     unsigned win_phase = 0;
     bool win_pending = false;
+    int f_slot = 0;            // ring slot / parity of the next chunk the FRONT half will take
+    unsigned f_phase = 0;
 
-    // FRONT half of chunk c (c < n_chunks): fills `r`, publishes the warp's column range
+    // FRONT half of chunk c: fills `r`, starts the LUT gathers, publishes the warp's column range
     auto front = [&](int c, ChunkRegs& r) {
-        const int slot = c % p.stages;
-        mbar_wait(full + slot, static_cast<unsigned>(c / p.stages) & 1u);
-        const int4* stage = reinterpret_cast<const int4*>(ring + slot * (kEvChunk * 16));
+        mbar_wait(full + f_slot, f_phase);
+        const int4* stage = reinterpret_cast<const int4*>(ring + f_slot * (kEvChunk * 16));
+        int* lut_dst = s_lut + (c & 1) * kEvChunk;
         const int limit = span_len - c * kEvChunk;
         unsigned cmin = 0xffffffffu;
         int cmax = -1;
         if (limit >= kEvChunk) {
             if (tc.fast)
-                front_half<F64, true, true>(p, tc, stage, tid, limit, r, cmin, cmax, n_valid, flags);
+                front_half<F64, true, true>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, cmin, cmax, n_valid, flags);
             else
-                front_half<F64, true, false>(p, tc, stage, tid, limit, r, cmin, cmax, n_valid, flags);
+                front_half<F64, true, false>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, cmin, cmax, n_valid, flags);
         } else {
             if (tc.fast)
-                front_half<F64, false, true>(p, tc, stage, tid, limit, r, cmin, cmax, n_valid, flags);
+                front_half<F64, false, true>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, cmin, cmax, n_valid, flags);
             else
-                front_half<F64, false, false>(p, tc, stage, tid, limit, r, cmin, cmax, n_valid, flags);
+                front_half<F64, false, false>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, cmin, cmax, n_valid, flags);
         }
         cmin = __reduce_min_sync(0xffffffffu, cmin);
         cmax = __reduce_max_sync(0xffffffffu, cmax);
@@ -362,7 +370,11 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
     // after the block barrier that follows front(c): recycle the stage, decide how chunk c reads the X-map
     // returns: 0 = chunk has no valid event, 1 = shared-memory window, 2 = through L2
     auto after_barrier = [&](int c) -> int {
-        if (tid == 0 && c + p.stages < n_chunks) issue_chunk(c + p.stages, c % p.stages);
+        if (tid == 0 && c + p.stages < n_chunks) issue_chunk(c + p.stages, f_slot);
+        if (++f_slot == p.stages) {
+            f_slot = 0;
+            f_phase ^= 1u;
+        }
         const int cmin = static_cast<int>(__reduce_min_sync(0xffffffffu, s_min[(c & 1) * 8 + (lane & 7)]));
         const int cmax = __reduce_max_sync(0xffffffffu, s_max[(c & 1) * 8 + (lane & 7)]);
         if (cmax < 0) return 0;
@@ -392,15 +404,25 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
     for (int c = 0; c < n_chunks; ++c) {
         ChunkRegs nxt;
         const bool has_next = c + 1 < n_chunks;
-        if (has_next) front(c + 1, nxt);
+        if (has_next) {
+            front(c + 1, nxt);
+            cp_async_wait<1>();  // the gathers of chunk c have landed; those of chunk c+1 stay in flight
+        } else {
+            cp_async_wait<0>();
+        }
         if (mode != 0) {
-            if (win_pending) {  // the window copy was issued one chunk ago
-                mbar_wait(winbar, win_phase);
-                win_phase ^= 1u;
-                win_pending = false;
-            }
             const unsigned idx_base = static_cast<unsigned>(span_lo) + static_cast<unsigned>(c * kEvChunk + tid);
-            back_half<SAFE>(p, cur, s_cols, mode == 1, win_lo, idx_base, n_inl, flags);
+            const int* lut_src = s_lut + (c & 1) * kEvChunk;
+            if (mode == 1) {
+                if (win_pending) {  // the window copy was issued one chunk ago
+                    mbar_wait(winbar, win_phase);
+                    win_phase ^= 1u;
+                    win_pending = false;
+                }
+                back_half<SAFE, true>(p, cur, lut_src, s_cols, win_lo, tid, idx_base, n_inl, flags);
+            } else {
+                back_half<SAFE, false>(p, cur, lut_src, s_cols, win_lo, tid, idx_base, n_inl, flags);
+            }
         }
         if (!has_next) break;
         __syncthreads();  // every thread has taken its events of chunk c+1 out of the ring and is done
@@ -408,7 +430,6 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
         mode = after_barrier(c + 1);
 #pragma unroll
         for (int k = 0; k < kEvPerThread; ++k) {
-            cur.lut[k] = nxt.lut[k];
             cur.col[k] = nxt.col[k];
             cur.pix[k] = nxt.pix[k];
         }
@@ -452,6 +473,7 @@ struct EpilogueParams {
     const unsigned long long* map;
     const FrameState* state;
     const short2* remap_xy;
+    const short4* tile_box;  // per 32x32 output tile: bounding box (x0, y0, x1, y1) of its remap targets; x1 < 0: none
     int rect_w, rect_h;
     int out_w, out_h;  // projector (view 0) or camera (view 1) size
     int radius;        // dilate / 2
@@ -481,11 +503,10 @@ constexpr int kTile = 32;
 
 // R > 0: compile-time dilate radius (unrolled taps); R == 0: runtime radius p.radius.
 template <int R>
-__global__ void __launch_bounds__(256, 8) epilogue_projector_kernel(const EpilogueParams p) {
+__global__ void __launch_bounds__(256, 7) epilogue_projector_kernel(const EpilogueParams p) {
     extern __shared__ __align__(128) unsigned char ev_smem[];
     unsigned short* s_raw = reinterpret_cast<unsigned short*>(ev_smem);
     unsigned short* s_h = s_raw + p.region_cap;
-    __shared__ int s_box[4][8];
 
     const unsigned epoch = p.state->epoch_used;
     const int tid = threadIdx.x;
@@ -493,39 +514,20 @@ __global__ void __launch_bounds__(256, 8) epilogue_projector_kernel(const Epilog
     const int u0 = blockIdx.x * kTile, v0 = blockIdx.y * kTile;
     const int r = R > 0 ? R : p.radius;
 
+    // the tile's source bounding box was computed when the remap table was uploaded, so the region
+    // loads below do not have to wait for the remap loads (one dependent memory round trip less)
+    const short4 box = __ldg(p.tile_box + blockIdx.y * gridDim.x + blockIdx.x);
+    const int x0 = box.x, y0 = box.y, x1 = box.z, y1 = box.w;
+    if (p.out.kind == 0 && p.out.depth_lut && tid < 128) prefetch_l1(p.out.depth_lut + tid * 32);  // first 16 KB of the depth table
+
     short2 m[4];
     unsigned inside = 0;
-    int x0 = 0x7fffffff, x1 = -1, y0 = 0x7fffffff, y1 = -1;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int u = u0 + lane, v = v0 + warp + k * 8;
-        m[k] = make_short2(0, 0);
-        if (u < p.out_w && v < p.out_h) {
-            m[k] = __ldg(p.remap_xy + v * p.out_w + u);
-            if (m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h) {
-                inside |= 1u << k;
-                x0 = min(x0, static_cast<int>(m[k].x));
-                x1 = max(x1, static_cast<int>(m[k].x));
-                y0 = min(y0, static_cast<int>(m[k].y));
-                y1 = max(y1, static_cast<int>(m[k].y));
-            }
-        }
+        m[k] = make_short2(-1, -1);
+        if (u < p.out_w && v < p.out_h) m[k] = __ldg(p.remap_xy + v * p.out_w + u);
     }
-    x0 = __reduce_min_sync(0xffffffffu, x0);
-    y0 = __reduce_min_sync(0xffffffffu, y0);
-    x1 = __reduce_max_sync(0xffffffffu, x1);
-    y1 = __reduce_max_sync(0xffffffffu, y1);
-    if (lane == 0) {
-        s_box[0][warp] = x0;
-        s_box[1][warp] = y0;
-        s_box[2][warp] = x1;
-        s_box[3][warp] = y1;
-    }
-    __syncthreads();
-    x0 = __reduce_min_sync(0xffffffffu, s_box[0][lane & 7]);
-    y0 = __reduce_min_sync(0xffffffffu, s_box[1][lane & 7]);
-    x1 = __reduce_max_sync(0xffffffffu, s_box[2][lane & 7]);
-    y1 = __reduce_max_sync(0xffffffffu, s_box[3][lane & 7]);
 
     int val[4] = {0, 0, 0, 0};
     if (x1 >= 0) {
@@ -564,6 +566,9 @@ __global__ void __launch_bounds__(256, 8) epilogue_projector_kernel(const Epilog
             }
             __syncthreads();
 #pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h) inside |= 1u << k;
+#pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (!(inside & (1u << k))) continue;
                 const unsigned short* colp = s_h + (m[k].y - ry0) * rw + (m[k].x - rx0);
@@ -577,6 +582,9 @@ __global__ void __launch_bounds__(256, 8) epilogue_projector_kernel(const Epilog
                 val[k] = static_cast<int>(best);
             }
         } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h) inside |= 1u << k;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (!(inside & (1u << k))) continue;
