@@ -18,8 +18,10 @@ DEPS = SOURCES + ["xm_device.cuh", "xm_frame_kernels.cuh", "xm_stage_kernels.cuh
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
+    "-rdc=true",  # K1 tail-launches its fix-up from the device (CUDA dynamic parallelism)
     "-Xcompiler", "-fPIC", "-shared",
 ]
+LINK_LIBS = ["-lcudadevrt"]
 
 
 def needs_build():
@@ -35,7 +37,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES + LINK_LIBS
     proc = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
     if verbose or proc.returncode:
         sys.stderr.write(proc.stdout + proc.stderr)

@@ -94,6 +94,7 @@ struct XmCtx {
     int opt_lookahead = 1;
     int opt_ctas_per_sm = 0;  // 0 = occupancy query
     int opt_smem_cols_bytes = 12 * 1024;
+    int opt_debug_skip = 0;   // timing experiments only
     int opt_safe_tables = 1;  // use the check-free scatter when the tables were verified
     int opt_stages = 3;  // depth of the shared-memory event ring of K1
     int opt_region_cells = 64 * 64;
@@ -307,9 +308,10 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     p.cap_cols = c->cap_cols;
     p.lookahead = c->opt_lookahead;
     p.stages = c->opt_stages;
-    p.conditional = 0;
-    p.verify = assumed ? 1 : 0;
+    p.debug_skip = c->opt_debug_skip;
     p.arm_fixup = fixup ? 1 : 0;
+    p.fix_reduce_grid = grid_for(a->n_events, 256, 8, c->sm_count * 8);
+    p.smem_bytes = c->ev_smem;
 
     if (c->opt_profile) {
         rc = profile_mark(c, s);
@@ -318,24 +320,11 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     if (a->n_events > 0) {
         const int occ = c->opt_ctas_per_sm > 0 ? c->opt_ctas_per_sm : (f64 ? c->ev_occ_f64 : c->ev_occ_i64);
         const int grid = grid_for(a->n_events, xm::kEvThreads, xm::kEvPerThread, c->sm_count * occ);
+        // when an event violates the assumed bounds the last CTA of K1 tail-launches the exact
+        // two-pass fix-up from the device (no extra host launches in the common case)
         const EvKernel k1 = ev_kernel(f64, c->lut_safe && c->xmap_safe && c->opt_safe_tables);
         k1<<<grid, xm::kEvThreads, c->ev_smem, s>>>(p);
         XM_LAUNCHED();
-        if (fixup) {
-            // runs only if K1 found an event outside the assumed bounds (state->redo)
-            const int rgrid = grid_for(a->n_events, 256, 8, c->sm_count * 8);
-            if (f64)
-                xm::bounds_reduce_kernel<true><<<rgrid, 256, 0, s>>>(p.events, p.n, p.polarity, 1, c->d_state);
-            else
-                xm::bounds_reduce_kernel<false><<<rgrid, 256, 0, s>>>(p.events, p.n, p.polarity, 1, c->d_state);
-            XM_LAUNCHED();
-            p.conditional = 1;
-            p.verify = 0;
-            p.arm_fixup = 0;
-            p.epoch = epoch + 1;
-            k1<<<grid, xm::kEvThreads, c->ev_smem, s>>>(p);
-            XM_LAUNCHED();
-        }
     }
 
     if (c->opt_profile) {
@@ -548,6 +537,10 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         if (v < 1 || v > xm::kMaxStages) return fail(XM_ERR_INVALID_ARG, "stages must be 1..%d", xm::kMaxStages);
         c->opt_stages = v;
         return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
+    }
+    if (!strcmp(key, "debug_skip")) {
+        c->opt_debug_skip = v;
+        return XM_OK;
     }
     if (!strcmp(key, "safe_tables")) {
         c->opt_safe_tables = v != 0;

@@ -57,10 +57,11 @@ struct EventParams {
     FrameState* state;
     int cap_cols;     // X-map columns that fit the shared-memory window (0 = never stage)
     int lookahead;    // extra columns fetched ahead of a time-sorted stream
-    int conditional;  // 1: this launch is the fix-up pass, runs only if state->redo
-    int verify;       // 1: bounds were assumed (sorted / given) -> check every event against them
-    int arm_fixup;    // 1: the last CTA arms the fix-up pass when a violation was seen
+    int arm_fixup;    // 1: the last CTA launches the exact fix-up when an event violated the assumed bounds
+    int fix_reduce_grid;  // grid of the fix-up's bounds reduction
+    int smem_bytes;       // dynamic shared memory of this launch (re-used by the fix-up launch)
     int stages;       // depth of the shared-memory event ring (1..kMaxStages)
+    int debug_skip;   // timing experiments only (results are WRONG): 1 = no LUT gather, 2 = no scatter atomics, 4 = no X-map lookup
 };
 
 __device__ __forceinline__ bool event_valid(const EventFields& e, int polarity) {
@@ -223,7 +224,10 @@ __device__ __forceinline__ void front_half(const EventParams& p, const TimeCol<F
                 const unsigned ex = static_cast<unsigned>(raw.x) & 0xffffu, ey = static_cast<unsigned>(raw.x) >> 16;
                 if (ex < static_cast<unsigned>(p.cam_w) && ey < static_cast<unsigned>(p.cam_h)) {
                     pix = static_cast<int>(ey) * p.cam_w + static_cast<int>(ex);
-                    cp_async_4(s_lut + k * kEvThreads + tid, p.lut_xy + pix);
+                    if (p.debug_skip & 1)
+                        s_lut[k * kEvThreads + tid] = static_cast<int>(((ey * 2u + 150u) << 16) | (ex * 2u));
+                    else
+                        cp_async_4(s_lut + k * kEvThreads + tid, p.lut_xy + pix);
                     const long long t_bits = (static_cast<long long>(raw.w) << 32) | static_cast<unsigned>(raw.z);
                     bool viol;
                     if (FAST) {
@@ -263,7 +267,9 @@ __device__ __forceinline__ void back_half(const EventParams& p, const ChunkRegs&
         const int ycr = lut >> 16;
         if (static_cast<unsigned>(ycr) >= y_lim) continue;  // x_maps_disparity.py:23: 0 <= y_rect < H - 1
         int xp;
-        if (FROM_SMEM)
+        if (p.debug_skip & 4)
+            xp = xcr + p.x_offset + (ycr & 63);
+        else if (FROM_SMEM)
             xp = s_cols[(r.col[k] - win_lo) * p.col_stride + ycr];
         else
             xp = __ldg(p.xmap_t + static_cast<long long>(r.col[k]) * p.col_stride + ycr);
@@ -284,7 +290,10 @@ __device__ __forceinline__ void back_half(const EventParams& p, const ChunkRegs&
             }
             cell = ycr * p.rect_w + xpr;
         }
-        atomicMax(p.map + cell, make_key32(p.epoch, idx_base + static_cast<unsigned>(k * kEvThreads), disp));
+        if (p.debug_skip & 2)
+            n_inl += static_cast<unsigned>(cell) & 1u;
+        else
+            atomicMax(p.map + cell, make_key32(p.epoch, idx_base + static_cast<unsigned>(k * kEvThreads), disp));
     }
 }
 
@@ -300,8 +309,6 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
     short* s_cols = reinterpret_cast<short*>(ring + p.stages * (kEvChunk * 16));
 
     FrameState* st = p.state;
-    if (p.conditional && !*reinterpret_cast<volatile unsigned*>(&st->redo)) return;
-
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -461,6 +468,15 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
                 st->redo = 1;
                 st->epoch_used = p.epoch + 1;
                 st->flags = f & ~(kStatusPixelOob | kStatusScatterOob);
+                // Exact fix-up, launched from the device into the tail-launch stream (CUDA dynamic
+                // parallelism): both grids run, in this order, after this grid has drained and before
+                // the next kernel of the host stream (the epilogue) starts.  Costs nothing when the
+                // optimistic bounds hold.
+                bounds_reduce_kernel<F64><<<p.fix_reduce_grid, 256, 0, cudaStreamTailLaunch>>>(p.events, p.n, p.polarity, 0, st);
+                EventParams q = p;
+                q.epoch = p.epoch + 1;
+                q.arm_fixup = 0;
+                events_kernel<F64, SAFE><<<gridDim.x, kEvThreads, p.smem_bytes, cudaStreamTailLaunch>>>(q);
             }
         }
     }
