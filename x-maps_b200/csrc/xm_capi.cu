@@ -94,9 +94,8 @@ struct XmCtx {
     int opt_lookahead = 1;
     int opt_ctas_per_sm = 0;  // 0 = occupancy query
     int opt_smem_cols_bytes = 12 * 1024;
-    int opt_debug_skip = 0;   // timing experiments only
     int opt_safe_tables = 1;  // use the check-free scatter when the tables were verified
-    int opt_stages = 3;  // depth of the shared-memory event ring of K1
+    int opt_stages = 2;  // depth of the shared-memory event ring of K1
     int opt_region_cells = 64 * 64;
     // per-kernel CUDA-event timing (option "profile"): pairs around K1 and K2 of every frame
     int opt_profile = 0;
@@ -308,7 +307,6 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     p.cap_cols = c->cap_cols;
     p.lookahead = c->opt_lookahead;
     p.stages = c->opt_stages;
-    p.debug_skip = c->opt_debug_skip;
     p.arm_fixup = fixup ? 1 : 0;
     p.fix_reduce_grid = grid_for(a->n_events, 256, 8, c->sm_count * 8);
     p.smem_bytes = c->ev_smem;
@@ -537,10 +535,6 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         if (v < 1 || v > xm::kMaxStages) return fail(XM_ERR_INVALID_ARG, "stages must be 1..%d", xm::kMaxStages);
         c->opt_stages = v;
         return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
-    }
-    if (!strcmp(key, "debug_skip")) {
-        c->opt_debug_skip = v;
-        return XM_OK;
     }
     if (!strcmp(key, "safe_tables")) {
         c->opt_safe_tables = v != 0;

@@ -165,6 +165,29 @@ struct TimeCol {
         return exact(num);
     }
 
+    // Branch-free hot-loop variant (valid only when `fast`): the caller patches `tie` cases with
+    // exact_from_bits().  The returned column is meaningful only if !viol && !tie.
+    __device__ __forceinline__ int column_fast_nb(long long t_bits, bool& viol, bool& tie) const {
+        double num;
+        if (F64) {
+            const double t = __longlong_as_double(t_bits);
+            viol = !(t >= lo_f && t <= hi_f);
+            num = __dsub_rn(t, lo_f);
+        } else {
+            const unsigned long long dt = static_cast<unsigned long long>(t_bits) - lo_u;
+            viol = dt > range;
+            num = static_cast<double>(static_cast<unsigned>(dt));
+        }
+        const double a = __dmul_rn(num, inv);
+        const int k = __double2int_rn(a);
+        tie = !(fabs(__dsub_rn(a, static_cast<double>(k))) < 0.4999);
+        return k;
+    }
+    __device__ __forceinline__ int exact_from_bits(long long t_bits) const {
+        if (F64) return exact(__dsub_rn(__longlong_as_double(t_bits), lo_f));
+        return exact(static_cast<double>(static_cast<long long>(static_cast<unsigned long long>(t_bits) - lo_u)));
+    }
+
     // Hot-loop variant, valid only when `fast`: returns a column in [0, T_PX_SCALE] (0 if `viol`).
     __device__ __forceinline__ int column_fast(long long t_bits, bool& viol) const {
         double num;

@@ -61,7 +61,6 @@ struct EventParams {
     int fix_reduce_grid;  // grid of the fix-up's bounds reduction
     int smem_bytes;       // dynamic shared memory of this launch (re-used by the fix-up launch)
     int stages;       // depth of the shared-memory event ring (1..kMaxStages)
-    int debug_skip;   // timing experiments only (results are WRONG): 1 = no LUT gather, 2 = no scatter atomics, 4 = no X-map lookup
 };
 
 __device__ __forceinline__ bool event_valid(const EventFields& e, int polarity) {
@@ -206,48 +205,88 @@ struct ChunkRegs {
     int pix[kEvPerThread];  // camera pixel index
 };
 
+// Column range of a chunk: `lo` = min column as unsigned (dropped events contribute UINT_MAX),
+// `hi` = max column (dropped events contribute -1).
+struct ColRange {
+    unsigned lo;
+    int hi;
+    __device__ __forceinline__ void add(int col) {
+        lo = min(lo, static_cast<unsigned>(col));
+        hi = max(hi, col);
+    }
+};
+
 // FRONT half.  FULL: the chunk has kEvChunk events (no per-event bound check).  FAST: TimeCol::fast.
 // The packed-LUT words are gathered asynchronously into `s_lut` (one cp.async group per chunk).
+// The FAST variant is written branch-free so that the kEvPerThread independent dependency chains
+// (shared load -> unpack -> float64 column) interleave; the rare exact-tie case is patched up after.
 template <bool F64, bool FULL, bool FAST>
 __device__ __forceinline__ void front_half(const EventParams& p, const TimeCol<F64>& tc, const int4* stage, int* s_lut, int tid,
-                                           int limit, unsigned pol_mask, ChunkRegs& r, unsigned& cmin, int& cmax,
-                                           unsigned& n_valid, unsigned& flags) {
+                                           int limit, unsigned pol_mask, ChunkRegs& r, ColRange& range, unsigned& n_valid,
+                                           unsigned& flags) {
+    if (FAST) {
+        int4 raw[kEvPerThread];
 #pragma unroll
-    for (int k = 0; k < kEvPerThread; ++k) {
-        int cc = -1;
-        int pix = 0;
-        if (FULL || k * kEvThreads + tid < limit) {
-            const int4 raw = stage[k * kEvThreads + tid];
+        for (int k = 0; k < kEvPerThread; ++k) raw[k] = stage[k * kEvThreads + tid];
+        unsigned tie_mask = 0;
+#pragma unroll
+        for (int k = 0; k < kEvPerThread; ++k) {
+            const bool in = FULL || k * kEvThreads + tid < limit;
+            const unsigned ex = static_cast<unsigned>(raw[k].x) & 0xffffu, ey = static_cast<unsigned>(raw[k].x) >> 16;
             // polarity: keep p == 1 (pol_mask = 0xffff) or everything (pol_mask = 0)
-            if ((((static_cast<unsigned>(raw.y) & 0xffffu) ^ 1u) & pol_mask) == 0u) {
-                ++n_valid;
-                const unsigned ex = static_cast<unsigned>(raw.x) & 0xffffu, ey = static_cast<unsigned>(raw.x) >> 16;
-                if (ex < static_cast<unsigned>(p.cam_w) && ey < static_cast<unsigned>(p.cam_h)) {
-                    pix = static_cast<int>(ey) * p.cam_w + static_cast<int>(ex);
-                    if (p.debug_skip & 1)
-                        s_lut[k * kEvThreads + tid] = static_cast<int>(((ey * 2u + 150u) << 16) | (ex * 2u));
-                    else
+            const bool valid = in && (((static_cast<unsigned>(raw[k].y) ^ 1u) & pol_mask) == 0u);
+            const bool ok = valid && ex < static_cast<unsigned>(p.cam_w) && ey < static_cast<unsigned>(p.cam_h);
+            const int pix = ok ? static_cast<int>(ey) * p.cam_w + static_cast<int>(ex) : 0;
+            if (ok) cp_async_4(s_lut + k * kEvThreads + tid, p.lut_xy + pix);
+            const long long t_bits = (static_cast<long long>(raw[k].w) << 32) | static_cast<unsigned>(raw[k].z);
+            bool viol, tie;
+            int cc = tc.column_fast_nb(t_bits, viol, tie);
+            viol = viol && ok;
+            tie_mask |= (ok && !viol && tie) ? (1u << k) : 0u;
+            n_valid += valid ? 1u : 0u;
+            flags |= (valid && !ok) ? kStatusPixelOob : 0u;  // the reference raises IndexError here
+            flags |= viol ? kStatusTBounds : 0u;
+            cc = ok ? (viol ? 0 : cc) : -1;
+            r.col[k] = cc;
+            r.pix[k] = pix;
+        }
+        if (tie_mask) {  // exact ties of the rounding: evaluate the reference's own expression
+#pragma unroll
+            for (int k = 0; k < kEvPerThread; ++k)
+                if (tie_mask & (1u << k))
+                    r.col[k] = tc.exact_from_bits((static_cast<long long>(raw[k].w) << 32) | static_cast<unsigned>(raw[k].z));
+        }
+#pragma unroll
+        for (int k = 0; k < kEvPerThread; ++k) range.add(r.col[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kEvPerThread; ++k) {
+            int cc = -1;
+            int pix = 0;
+            if (FULL || k * kEvThreads + tid < limit) {
+                const int4 raw = stage[k * kEvThreads + tid];
+                if ((((static_cast<unsigned>(raw.y) & 0xffffu) ^ 1u) & pol_mask) == 0u) {
+                    ++n_valid;
+                    const unsigned ex = static_cast<unsigned>(raw.x) & 0xffffu, ey = static_cast<unsigned>(raw.x) >> 16;
+                    if (ex < static_cast<unsigned>(p.cam_w) && ey < static_cast<unsigned>(p.cam_h)) {
+                        pix = static_cast<int>(ey) * p.cam_w + static_cast<int>(ex);
                         cp_async_4(s_lut + k * kEvThreads + tid, p.lut_xy + pix);
-                    const long long t_bits = (static_cast<long long>(raw.w) << 32) | static_cast<unsigned>(raw.z);
-                    bool viol;
-                    if (FAST) {
-                        cc = tc.column_fast(t_bits, viol);
-                    } else {
+                        const long long t_bits = (static_cast<long long>(raw.w) << 32) | static_cast<unsigned>(raw.z);
+                        bool viol;
                         cc = tc.column(t_bits, viol);
                         if (cc < 0) cc += p.xmap_w;  // NumPy negative index (only reachable with wrong bounds)
                         viol = viol || cc < 0 || cc >= p.xmap_w;
                         if (viol) cc = 0;
+                        flags |= viol ? kStatusTBounds : 0u;
+                    } else {
+                        flags |= kStatusPixelOob;  // the reference raises IndexError here
                     }
-                    flags |= viol ? kStatusTBounds : 0u;
-                } else {
-                    flags |= kStatusPixelOob;  // the reference raises IndexError here
                 }
             }
+            r.col[k] = cc;
+            r.pix[k] = pix;
+            range.add(cc);
         }
-        r.col[k] = cc;
-        r.pix[k] = pix;
-        cmin = min(cmin, static_cast<unsigned>(cc));  // -1 -> UINT_MAX: ignored
-        cmax = max(cmax, cc);
     }
     cp_async_commit();
 }
@@ -255,10 +294,37 @@ __device__ __forceinline__ void front_half(const EventParams& p, const TimeCol<F
 // BACK half.  SAFE: the tables were verified at upload so that every inlier's scatter target lies
 // inside the map (no wrap / bound checks).  FROM_SMEM: X-map columns come from the shared window
 // (kept a separate instantiation so that the hot path only ever waits on shared-memory loads).
+// The SAFE + FROM_SMEM variant is branch-free (predicated loads / atomics).
 template <bool SAFE, bool FROM_SMEM>
 __device__ __forceinline__ void back_half(const EventParams& p, const ChunkRegs& r, const int* s_lut, const short* s_cols, int win_lo,
                                           int tid, unsigned idx_base, unsigned& n_inl, unsigned& flags) {
     const unsigned y_lim = static_cast<unsigned>(p.xmap_h - 1);
+    if constexpr (SAFE && FROM_SMEM) {
+        int lut[kEvPerThread];
+#pragma unroll
+        for (int k = 0; k < kEvPerThread; ++k) lut[k] = s_lut[k * kEvThreads + tid];
+        int xp[kEvPerThread];
+        bool y_ok[kEvPerThread];
+#pragma unroll
+        for (int k = 0; k < kEvPerThread; ++k) {
+            const int ycr = lut[k] >> 16;
+            // x_maps_disparity.py:23: 0 <= y_rect < H - 1 (last row excluded)
+            y_ok[k] = r.col[k] >= 0 && static_cast<unsigned>(ycr) < y_lim;
+            const int off = y_ok[k] ? (r.col[k] - win_lo) * p.col_stride + ycr : 0;
+            xp[k] = s_cols[off];
+        }
+#pragma unroll
+        for (int k = 0; k < kEvPerThread; ++k) {
+            const int xcr = static_cast<short>(lut[k] & 0xffff);
+            const int ycr = lut[k] >> 16;
+            const int disp = static_cast<short>(xp[k] - xcr - p.x_offset);  // int16 arithmetic wraps
+            const bool inl = y_ok[k] && disp >= 0;
+            n_inl += inl ? 1u : 0u;
+            // x_rect + disp = x_map - x_offset, in [0, rect_w) for verified tables
+            const int cell = p.view == 1 ? r.pix[k] : ycr * p.rect_w + (xp[k] - p.x_offset);
+            if (inl) atomicMax(p.map + cell, make_key32(p.epoch, idx_base + static_cast<unsigned>(k * kEvThreads), disp));
+        }
+    } else {
 #pragma unroll
     for (int k = 0; k < kEvPerThread; ++k) {
         if (r.col[k] < 0) continue;
@@ -267,9 +333,7 @@ __device__ __forceinline__ void back_half(const EventParams& p, const ChunkRegs&
         const int ycr = lut >> 16;
         if (static_cast<unsigned>(ycr) >= y_lim) continue;  // x_maps_disparity.py:23: 0 <= y_rect < H - 1
         int xp;
-        if (p.debug_skip & 4)
-            xp = xcr + p.x_offset + (ycr & 63);
-        else if (FROM_SMEM)
+        if (FROM_SMEM)
             xp = s_cols[(r.col[k] - win_lo) * p.col_stride + ycr];
         else
             xp = __ldg(p.xmap_t + static_cast<long long>(r.col[k]) * p.col_stride + ycr);
@@ -290,10 +354,8 @@ __device__ __forceinline__ void back_half(const EventParams& p, const ChunkRegs&
             }
             cell = ycr * p.rect_w + xpr;
         }
-        if (p.debug_skip & 2)
-            n_inl += static_cast<unsigned>(cell) & 1u;
-        else
-            atomicMax(p.map + cell, make_key32(p.epoch, idx_base + static_cast<unsigned>(k * kEvThreads), disp));
+        atomicMax(p.map + cell, make_key32(p.epoch, idx_base + static_cast<unsigned>(k * kEvThreads), disp));
+    }
     }
 }
 
@@ -302,8 +364,7 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
     extern __shared__ __align__(128) unsigned char ev_smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(ev_smem);         // [kMaxStages]
     uint64_t* winbar = reinterpret_cast<uint64_t*>(ev_smem + 64);  // X-map window copy
-    unsigned* s_min = reinterpret_cast<unsigned*>(ev_smem + 128);  // [2][8]
-    int* s_max = reinterpret_cast<int*>(ev_smem + 192);            // [2][8]
+    unsigned* s_range = reinterpret_cast<unsigned*>(ev_smem + 128);  // [2][8] per-warp column range words
     int* s_lut = reinterpret_cast<int*>(ev_smem + kEvSmemHeader);  // [2][kEvChunk]
     unsigned char* ring = ev_smem + kEvSmemHeader + kEvLutBytes;
     short* s_cols = reinterpret_cast<short*>(ring + p.stages * (kEvChunk * 16));
@@ -353,25 +414,22 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
         const int4* stage = reinterpret_cast<const int4*>(ring + f_slot * (kEvChunk * 16));
         int* lut_dst = s_lut + (c & 1) * kEvChunk;
         const int limit = span_len - c * kEvChunk;
-        unsigned cmin = 0xffffffffu;
-        int cmax = -1;
+        ColRange range{0xffffffffu, -1};
         if (limit >= kEvChunk) {
             if (tc.fast)
-                front_half<F64, true, true>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, cmin, cmax, n_valid, flags);
+                front_half<F64, true, true>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, range, n_valid, flags);
             else
-                front_half<F64, true, false>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, cmin, cmax, n_valid, flags);
+                front_half<F64, true, false>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, range, n_valid, flags);
         } else {
             if (tc.fast)
-                front_half<F64, false, true>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, cmin, cmax, n_valid, flags);
+                front_half<F64, false, true>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, range, n_valid, flags);
             else
-                front_half<F64, false, false>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, cmin, cmax, n_valid, flags);
+                front_half<F64, false, false>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, range, n_valid, flags);
         }
-        cmin = __reduce_min_sync(0xffffffffu, cmin);
-        cmax = __reduce_max_sync(0xffffffffu, cmax);
-        if (lane == 0) {
-            s_min[(c & 1) * 8 + warp] = cmin;
-            s_max[(c & 1) * 8 + warp] = cmax;
-        }
+        const unsigned lo = __reduce_min_sync(0xffffffffu, range.lo);
+        const int hi = __reduce_max_sync(0xffffffffu, range.hi);
+        // one word per warp: (max << 16) | min; 0xffffffff = no valid event (columns are < 2^15)
+        if (lane == 0) s_range[(c & 1) * 8 + warp] = hi < 0 ? 0xffffffffu : ((static_cast<unsigned>(hi) << 16) | lo);
     };
 
     // after the block barrier that follows front(c): recycle the stage, decide how chunk c reads the X-map
@@ -382,8 +440,9 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
             f_slot = 0;
             f_phase ^= 1u;
         }
-        const int cmin = static_cast<int>(__reduce_min_sync(0xffffffffu, s_min[(c & 1) * 8 + (lane & 7)]));
-        const int cmax = __reduce_max_sync(0xffffffffu, s_max[(c & 1) * 8 + (lane & 7)]);
+        const unsigned w = s_range[(c & 1) * 8 + (lane & 7)];
+        const int cmin = static_cast<int>(__reduce_min_sync(0xffffffffu, w & 0xffffu));
+        const int cmax = __reduce_max_sync(0xffffffffu, w == 0xffffffffu ? -1 : static_cast<int>(w >> 16));
         if (cmax < 0) return 0;
         const int need = cmax - cmin + 1;
         if (need > p.cap_cols) return 2;
