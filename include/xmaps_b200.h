@@ -138,6 +138,10 @@ int xm_ctx_set_colormap(XmCtx* ctx, const uint8_t* h_bgr256);
  *   "stages"          depth of K1's shared-memory event ring (16 KB per stage, TMA-filled)      [2]
   *   "safe_tables"     0/1  allow the check-free scatter of K1 when the tables were verified at upload
  *                     (every defined X-map cell in [x_offset, x_offset + rect_w), LUT x > -x_offset) [1]
+   *   "pdl"             1: programmatic dependent launch between K1 / K2 / the next frame's K1 (used only
+ *                     when "auto_fixup" is 0 or the bounds are exact: it cannot be combined with the
+ *                     device-side fix-up launch)                                             [1]
+ *   "k2_variant"      1: sliding-window projector epilogue (7x7 dilate, even rect_w), 0: per-tap [1]
  *   "lookahead"       extra columns fetched ahead of a time-sorted stream                       [1]
  *   "auto_fixup"      0/1  with XM_TBOUNDS_SORTED / _GIVEN: when an event lies outside the assumed
  *                     bounds, redo the frame on the device with exact (reduced) bounds         [1]

@@ -78,7 +78,11 @@ struct XmCtx {
     bool have_turbo = false;
     unsigned long long* d_map = nullptr;
     long long map_cells = 0;
-    xm::FrameState* d_state = nullptr;
+    xm::FrameState* d_state = nullptr;  // ring of kStateSlots blocks; frame f uses slot f % kStateSlots
+    unsigned long long frame_no = 0;    // operations that used a state slot so far
+    int last_slot = 0;                  // slot of the most recent frame (xm_frame_status)
+    bool slot_dirty[4] = {false, false, false, false};
+    bool prev_was_frame = false;        // the previous launch on the stream was a fused frame's epilogue
     unsigned epoch = 0;
     // compaction scratch
     unsigned* d_counts = nullptr;
@@ -94,6 +98,8 @@ struct XmCtx {
     int opt_lookahead = 1;
     int opt_ctas_per_sm = 0;  // 0 = occupancy query
     int opt_smem_cols_bytes = 12 * 1024;
+    int opt_k2_variant = 1;   // 1: sliding-window epilogue (7x7, even rect_w), 0: per-tap epilogue
+    int opt_pdl = 1;          // programmatic dependent launch between K1 / K2 / next K1
     int opt_safe_tables = 1;  // use the check-free scatter when the tables were verified
     int opt_stages = 2;  // depth of the shared-memory event ring of K1
     int opt_region_cells = 64 * 64;
@@ -111,6 +117,35 @@ struct XmCtx {
 
 namespace {
 
+constexpr int kStateSlots = 4;
+
+// Picks the state block of the next operation.  Fused frames rely on the block having been cleared
+// by the epilogue of the frame before the previous one; anything else (first frames, stage-by-stage
+// calls in between) is cleared here.
+int acquire_state_slot(XmCtx* c, cudaStream_t s, bool need_clean, cudaError_t* err) {
+    *err = cudaSuccess;
+    const int slot = static_cast<int>(c->frame_no % kStateSlots);
+    c->frame_no += 1;
+    if (need_clean && c->slot_dirty[slot]) {
+        *err = cudaMemsetAsync(c->d_state + slot, 0, sizeof(xm::FrameState), s);
+        c->slot_dirty[slot] = false;
+        c->prev_was_frame = false;  // a memset sits between the kernels: no programmatic dependency
+    }
+    c->last_slot = slot;
+    return slot;
+}
+
+// state block for a stage-by-stage call (cleared here unless the callee resets it itself)
+int staged_state(XmCtx* c, cudaStream_t s, bool need_clean, xm::FrameState** out) {
+    cudaError_t err;
+    const int slot = acquire_state_slot(c, s, need_clean, &err);
+    XM_CUDA(err);
+    c->slot_dirty[slot] = true;
+    c->prev_was_frame = false;
+    *out = c->d_state + slot;
+    return XM_OK;
+}
+
 unsigned next_epoch(XmCtx* c, unsigned count, cudaStream_t s, cudaError_t* err) {
     // epochs live in the top 16 bits of a key; 0 means "never written".  On wrap the map is cleared.
     *err = cudaSuccess;
@@ -127,6 +162,23 @@ using EvKernel = void (*)(xm::EventParams);
 EvKernel ev_kernel(bool f64, bool safe) {
     if (f64) return safe ? xm::events_kernel<true, true> : xm::events_kernel<true, false>;
     return safe ? xm::events_kernel<false, true> : xm::events_kernel<false, false>;
+}
+
+// Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may start
+// while its predecessor in the stream is still running and synchronises with griddepcontrol.wait.
+template <typename P>
+cudaError_t launch_pdl(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, const P& params) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = pdl ? attr : nullptr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, params);
 }
 
 int configure_event_kernels(XmCtx* c) {
@@ -206,20 +258,20 @@ xm::OutputSpec make_output(const XmCtx* c, int kind, double depth_scale, float z
 }
 
 // Launches K0 for one frame.  `epoch` is the epoch K1 will use.
-int launch_bounds(XmCtx* c, const void* d_events, long long n, uint32_t flags, int time_bounds, long long t_min, long long t_max,
-                  unsigned epoch, cudaStream_t s) {
+int launch_bounds(XmCtx* c, xm::FrameState* st, const void* d_events, long long n, uint32_t flags, int time_bounds, long long t_min,
+                  long long t_max, unsigned epoch, cudaStream_t s) {
     const int polarity = (flags & XM_FLAG_POLARITY) ? 1 : 0;
     const bool f64 = (flags & XM_FLAG_TIME_F64) != 0;
     const int4* ev = static_cast<const int4*>(d_events);
     const int mode = time_bounds == XM_TBOUNDS_SORTED ? 0 : 1;
-    xm::bounds_init_kernel<<<1, 64, 0, s>>>(ev, n, polarity, mode, t_min, t_max, epoch, c->d_state);
+    xm::bounds_init_kernel<<<1, 64, 0, s>>>(ev, n, polarity, mode, t_min, t_max, epoch, st);
     XM_LAUNCHED();
     if (time_bounds == XM_TBOUNDS_REDUCE) {
         int grid = grid_for(n, 256, 8, c->sm_count * 8);
         if (f64)
-            xm::bounds_reduce_kernel<true><<<grid, 256, 0, s>>>(ev, n, polarity, 0, c->d_state);
+            xm::bounds_reduce_kernel<true><<<grid, 256, 0, s>>>(ev, n, polarity, st);
         else
-            xm::bounds_reduce_kernel<false><<<grid, 256, 0, s>>>(ev, n, polarity, 0, c->d_state);
+            xm::bounds_reduce_kernel<false><<<grid, 256, 0, s>>>(ev, n, polarity, st);
         XM_LAUNCHED();
     }
     return XM_OK;
@@ -270,6 +322,7 @@ int profile_mark(XmCtx* c, cudaStream_t s) {
         }
     }
     XM_CUDA(cudaEventRecord(c->prof_events[c->prof_used++], s));
+    c->prev_was_frame = false;  // an event record sits between the kernels
     return XM_OK;
 }
 
@@ -281,14 +334,27 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     cudaError_t err;
     const unsigned epoch = next_epoch(c, fixup ? 2u : 1u, s, &err);
     XM_CUDA(err);
+    const int slot = acquire_state_slot(c, s, true, &err);
+    XM_CUDA(err);
+    xm::FrameState* st = c->d_state + slot;
+    int rc = XM_OK;
+    const int polarity = (a->flags & XM_FLAG_POLARITY) ? 1 : 0;
 
-    int rc = launch_bounds(c, a->d_events, a->n_events, a->flags, a->time_bounds, a->t_min, a->t_max, epoch, s);
-    if (rc) return rc;
+    if (a->time_bounds == XM_TBOUNDS_REDUCE && a->n_events > 0) {
+        // exact two-pass form: one extra pass over the stream publishes t.min() / t.max() into the state
+        const int rgrid = grid_for(a->n_events, 256, 8, c->sm_count * 8);
+        if (f64)
+            xm::bounds_reduce_kernel<true><<<rgrid, 256, 0, s>>>(static_cast<const int4*>(a->d_events), a->n_events, polarity, st);
+        else
+            xm::bounds_reduce_kernel<false><<<rgrid, 256, 0, s>>>(static_cast<const int4*>(a->d_events), a->n_events, polarity, st);
+        XM_LAUNCHED();
+        c->prev_was_frame = false;
+    }
 
     xm::EventParams p;
     p.events = static_cast<const int4*>(a->d_events);
     p.n = a->n_events;
-    p.polarity = (a->flags & XM_FLAG_POLARITY) ? 1 : 0;
+    p.polarity = polarity;
     p.lut_xy = c->d_lut_xy;
     p.cam_w = c->cam_w;
     p.cam_h = c->cam_h;
@@ -303,7 +369,14 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     p.view = a->view;
     p.map = c->d_map;
     p.epoch = epoch;
-    p.state = c->d_state;
+    p.state = st;
+    p.bounds_mode = a->time_bounds == XM_TBOUNDS_SORTED ? 0 : (a->time_bounds == XM_TBOUNDS_GIVEN ? 1 : 2);
+    p.given_lo = a->t_min;
+    p.given_hi = a->t_max;
+    // griddepcontrol and a device-side tail launch do not mix in one kernel (measured: the grid hangs),
+    // so programmatic dependent launch is only used when K1 cannot launch its fix-up
+    const bool use_pdl = c->opt_pdl && !fixup;
+    p.use_pdl = use_pdl ? 1 : 0;
     p.cap_cols = c->cap_cols;
     p.lookahead = c->opt_lookahead;
     p.stages = c->opt_stages;
@@ -321,8 +394,12 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
         // when an event violates the assumed bounds the last CTA of K1 tail-launches the exact
         // two-pass fix-up from the device (no extra host launches in the common case)
         const EvKernel k1 = ev_kernel(f64, c->lut_safe && c->xmap_safe && c->opt_safe_tables);
-        k1<<<grid, xm::kEvThreads, c->ev_smem, s>>>(p);
+        // programmatic dependent launch: K1's input-only prologue may overlap the previous frame's epilogue
+        XM_CUDA(launch_pdl(k1, dim3(grid), dim3(xm::kEvThreads), c->ev_smem, s, use_pdl && c->prev_was_frame, p));
         XM_LAUNCHED();
+        c->prev_was_frame = true;
+    } else {
+        c->prev_was_frame = false;
     }
 
     if (c->opt_profile) {
@@ -331,7 +408,15 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     }
     xm::EpilogueParams q;
     q.map = c->d_map;
-    q.state = c->d_state;
+    q.state = st;
+    q.epoch = epoch;
+    q.use_pdl = use_pdl ? 1 : 0;
+    {   // this epilogue clears the state block of the frame after next (ring of kStateSlots)
+        const int rslot = (slot + 2) % kStateSlots;
+        q.recycle = c->d_state + rslot;
+        c->slot_dirty[rslot] = false;
+        c->slot_dirty[slot] = true;
+    }
     q.remap_xy = c->d_remap_xy;
     q.tile_box = c->d_tile_box;
     q.rect_w = c->rect_w;
@@ -340,20 +425,25 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     q.region_cap = c->opt_region_cells;
     q.out = make_output(c, a->output, c->depth_scale, a->z_near, a->z_far);
     q.dst = a->d_out;
+    const bool pdl2 = use_pdl && c->prev_was_frame;  // K2 directly follows this frame's K1
     if (a->view == XM_VIEW_CAMERA) {
         q.out_w = c->cam_w;
         q.out_h = c->cam_h;
         const int grid = grid_for(static_cast<long long>(c->cam_w) * c->cam_h, 256, 2, c->sm_count * 8);
-        xm::epilogue_camera_kernel<<<grid, 256, 0, s>>>(q);
+        XM_CUDA(launch_pdl(xm::epilogue_camera_kernel, dim3(grid), dim3(256), 0, s, pdl2, q));
     } else {
         q.out_w = c->proj_w;
         q.out_h = c->proj_h;
         dim3 grid((c->proj_w + xm::kTile - 1) / xm::kTile, (c->proj_h + xm::kTile - 1) / xm::kTile);
-        if (c->dilate == 7)
-            xm::epilogue_projector_kernel<3><<<grid, 256, static_cast<size_t>(c->opt_region_cells) * 4, s>>>(q);
+        const size_t smem = static_cast<size_t>(c->opt_region_cells) * 4;
+        if (c->dilate == 7 && !(c->rect_w & 1) && c->opt_k2_variant == 1)
+            XM_CUDA(launch_pdl(xm::epilogue_projector7_kernel, grid, dim3(256), smem, s, pdl2, q));
+        else if (c->dilate == 7)
+            XM_CUDA(launch_pdl(xm::epilogue_projector_kernel<3>, grid, dim3(256), smem, s, pdl2, q));
         else
-            xm::epilogue_projector_kernel<0><<<grid, 256, static_cast<size_t>(c->opt_region_cells) * 4, s>>>(q);
+            XM_CUDA(launch_pdl(xm::epilogue_projector_kernel<0>, grid, dim3(256), smem, s, pdl2, q));
     }
+    c->prev_was_frame = true;
     XM_LAUNCHED();
     if (c->opt_profile) {
         rc = profile_mark(c, s);
@@ -463,8 +553,8 @@ int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
     if (static_cast<long long>(cam_px) > c->map_cells) c->map_cells = static_cast<long long>(cam_px);
     if (cudaMalloc(&c->d_map, static_cast<size_t>(c->map_cells) * 8) != cudaSuccess ||
         cudaMemset(c->d_map, 0, static_cast<size_t>(c->map_cells) * 8) != cudaSuccess ||
-        cudaMalloc(&c->d_state, sizeof(xm::FrameState)) != cudaSuccess ||
-        cudaMemset(c->d_state, 0, sizeof(xm::FrameState)) != cudaSuccess || cudaMalloc(&c->d_turbo, 768) != cudaSuccess ||
+        cudaMalloc(&c->d_state, kStateSlots * sizeof(xm::FrameState)) != cudaSuccess ||
+        cudaMemset(c->d_state, 0, kStateSlots * sizeof(xm::FrameState)) != cudaSuccess || cudaMalloc(&c->d_turbo, 768) != cudaSuccess ||
         cudaMemset(c->d_turbo, 0, 768) != cudaSuccess)
         return bail(fail(XM_ERR_CUDA, "allocating the scatter map failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (cudaMalloc(&c->d_depth_lut, 32768 * sizeof(float)) != cudaSuccess)
@@ -536,6 +626,14 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         c->opt_stages = v;
         return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
     }
+    if (!strcmp(key, "k2_variant")) {
+        c->opt_k2_variant = v != 0;
+        return XM_OK;
+    }
+    if (!strcmp(key, "pdl")) {
+        c->opt_pdl = v != 0;
+        return XM_OK;
+    }
     if (!strcmp(key, "safe_tables")) {
         c->opt_safe_tables = v != 0;
         return XM_OK;
@@ -585,6 +683,8 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     if (!strcmp(key, "stage_xmap")) *value = c->opt_stage_xmap;
     else if (!strcmp(key, "smem_cols_bytes")) *value = c->opt_smem_cols_bytes;
     else if (!strcmp(key, "stages")) *value = c->opt_stages;
+    else if (!strcmp(key, "pdl")) *value = c->opt_pdl;
+    else if (!strcmp(key, "k2_variant")) *value = c->opt_k2_variant;
     else if (!strcmp(key, "safe_tables")) *value = c->opt_safe_tables && c->lut_safe && c->xmap_safe;
     else if (!strcmp(key, "auto_fixup")) *value = c->opt_auto_fixup;
     else if (!strcmp(key, "lookahead")) *value = c->opt_lookahead;
@@ -635,7 +735,7 @@ int xm_frame_status(XmCtx* c, XmFrameStatus* h, void* stream) {
     DeviceGuard guard(c->device);
     xm::FrameState st;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    XM_CUDA(cudaMemcpyAsync(&st, c->d_state, sizeof(st), cudaMemcpyDeviceToHost, s));
+    XM_CUDA(cudaMemcpyAsync(&st, c->d_state + c->last_slot, sizeof(st), cudaMemcpyDeviceToHost, s));
     XM_CUDA(cudaStreamSynchronize(s));
     h->n_events = 0;
     h->n_valid = static_cast<int64_t>(st.n_valid);
@@ -643,7 +743,7 @@ int xm_frame_status(XmCtx* c, XmFrameStatus* h, void* stream) {
     h->t_min = st.t_lo_bits;
     h->t_max = st.t_hi_bits;
     h->flags = st.flags;
-    h->epoch = st.epoch_used;
+    h->epoch = c->epoch;
     h->fixup_ran = st.redo;
     return XM_OK;
 }
@@ -708,8 +808,11 @@ int xm_rectify_i16(XmCtx* c, const void* d_events, int64_t n, int16_t* d_x, int1
     if (n == 0) return XM_OK;
     DeviceGuard guard(c->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    xm::FrameState* st;
+    int rc = staged_state(c, s, true, &st);
+    if (rc) return rc;
     xm::rectify_i16_kernel<<<grid_for(n, 256, 4, c->sm_count * 8), 256, 0, s>>>(static_cast<const int4*>(d_events), n, c->d_lut_xy,
-                                                                                c->cam_w, c->cam_h, d_x, d_y, c->d_state);
+                                                                                c->cam_w, c->cam_h, d_x, d_y, st);
     XM_LAUNCHED();
     return XM_OK;
 }
@@ -720,8 +823,11 @@ int xm_rectify_f32(XmCtx* c, const void* d_events, int64_t n, float* d_x, float*
     if (n == 0) return XM_OK;
     DeviceGuard guard(c->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    xm::FrameState* st;
+    int rc = staged_state(c, s, true, &st);
+    if (rc) return rc;
     xm::rectify_f32_kernel<<<grid_for(n, 256, 4, c->sm_count * 8), 256, 0, s>>>(
-        static_cast<const int4*>(d_events), n, c->d_lut_x_f32, c->d_lut_y_f32, c->cam_w, c->cam_h, d_x, d_y, c->d_state);
+        static_cast<const int4*>(d_events), n, c->d_lut_x_f32, c->d_lut_y_f32, c->cam_w, c->cam_h, d_x, d_y, st);
     XM_LAUNCHED();
     return XM_OK;
 }
@@ -736,7 +842,10 @@ int xm_event_disparity(XmCtx* c, const XmFrameArgs* a, const int16_t* d_x_rect, 
     if (!c->d_xmap_t) return fail(XM_ERR_NO_XMAP, "no X-map");
     DeviceGuard guard(c->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int rc = launch_bounds(c, a->d_events, a->n_events, a->flags, a->time_bounds, a->t_min, a->t_max, c->epoch, s);
+    xm::FrameState* st;
+    int rc = staged_state(c, s, false, &st);
+    if (rc) return rc;
+    rc = launch_bounds(c, st, a->d_events, a->n_events, a->flags, a->time_bounds, a->t_min, a->t_max, c->epoch, s);
     if (rc) return rc;
     if (a->n_events == 0) return XM_OK;
     xm::DisparityParams p;
@@ -756,7 +865,7 @@ int xm_event_disparity(XmCtx* c, const XmFrameArgs* a, const int16_t* d_x_rect, 
     p.x_offset = c->x_offset;
     p.disp_full = d_disp_full;
     p.mask = d_mask;
-    p.state = c->d_state;
+    p.state = st;
     p.verify = a->time_bounds != XM_TBOUNDS_REDUCE;
     const int grid = grid_for(a->n_events, 256, 4, c->sm_count * 8);
     if (a->flags & XM_FLAG_TIME_F64)
@@ -804,9 +913,12 @@ int xm_scatter_last_wins(XmCtx* c, const int16_t* d_rows, const int16_t* d_cols,
     cudaError_t err;
     const unsigned epoch = next_epoch(c, 1, s, &err);
     XM_CUDA(err);
+    xm::FrameState* st;
+    int rc = staged_state(c, s, true, &st);
+    if (rc) return rc;
     if (n > 0) {
         xm::scatter_keys_kernel<<<grid_for(n, 256, 4, c->sm_count * 8), 256, 0, s>>>(d_rows, d_cols, d_vals, n, h, w, c->d_map, epoch,
-                                                                                    c->d_state);
+                                                                                    st);
         XM_LAUNCHED();
     }
     const long long cells = static_cast<long long>(h) * w;

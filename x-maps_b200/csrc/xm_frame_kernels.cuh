@@ -21,13 +21,13 @@ namespace xm {
 struct FrameState {
     long long t_lo_bits;  // bounds in use: int64, or float64 bit pattern
     long long t_hi_bits;
-    long long red_lo;     // reduction scratch, "sortable" domain
-    long long red_hi;
+    unsigned long long red_lo;  // reduction scratch, encoded so that 0 is the identity of atomicMax:
+    unsigned long long red_hi;  //   red_lo = max(~u), red_hi = max(u + 1), u = order-preserving unsigned image of t
     unsigned long long n_valid;
     unsigned long long n_inliers;
     unsigned int flags;       // XM_STATUS_*
     unsigned int redo;        // 1: the optimistic bounds were wrong, the fix-up pass is running / ran
-    unsigned int epoch_used;  // epoch whose keys the epilogue must read
+    unsigned int epoch_used;  // (staged path only) epoch of the last scatter
     unsigned int blocks_done; // last-block detection
     unsigned int any_valid;   // reduction saw at least one valid event
     unsigned int pad;
@@ -57,43 +57,44 @@ struct EventParams {
     FrameState* state;
     int cap_cols;     // X-map columns that fit the shared-memory window (0 = never stage)
     int lookahead;    // extra columns fetched ahead of a time-sorted stream
+    int bounds_mode;  // 0: first / last valid event (found by every CTA), 1: given_lo / given_hi, 2: state->t_lo/hi_bits
+    long long given_lo, given_hi;
+    int use_pdl;      // 1: execute the griddepcontrol instructions (0 for device-launched fix-up grids)
     int arm_fixup;    // 1: the last CTA launches the exact fix-up when an event violated the assumed bounds
     int fix_reduce_grid;  // grid of the fix-up's bounds reduction
     int smem_bytes;       // dynamic shared memory of this launch (re-used by the fix-up launch)
     int stages;       // depth of the shared-memory event ring (1..kMaxStages)
 };
 
+// order-preserving map of a timestamp (int64, or float64 bit pattern) to uint64
+template <bool F64>
+__device__ __forceinline__ unsigned long long time_to_ordered(long long t_bits) {
+    const long long k = F64 ? f64_bits_to_sortable(t_bits) : t_bits;
+    return static_cast<unsigned long long>(k) ^ 0x8000000000000000ULL;
+}
+template <bool F64>
+__device__ __forceinline__ long long ordered_to_time(unsigned long long u) {
+    const long long k = static_cast<long long>(u ^ 0x8000000000000000ULL);
+    return F64 ? sortable_to_f64_bits(k) : k;
+}
+
+// Programmatic dependent launch (PDL): let the next kernel of the stream start its prologue while
+// this one runs / wait until everything the previous kernel wrote is visible.  Both are no-ops for
+// launches without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ bool event_valid(const EventFields& e, int polarity) {
     return !polarity || e.p == 1;
 }
 
 // ---------------------------------------------------------------------------------------------
-// K0a: bounds from the ends of a time-sorted frame + reset of the per-frame counters.
-//   mode 0: first / last valid event      mode 1: bounds given by the caller
-// One CTA of 64 threads: warp 0 scans forward, warp 1 backward (normally one step each).
+// Bounds of a time-sorted frame: t of the first / last valid event.  Called by the first two warps
+// of a CTA (warp 0 scans forward, warp 1 backward; normally one step each); the results land in
+// out[0] / out[1] (0 if the frame has no valid event).
 // ---------------------------------------------------------------------------------------------
-__global__ void bounds_init_kernel(const int4* __restrict__ events, long long n, int polarity, int mode,
-                                   long long given_lo, long long given_hi, unsigned epoch, FrameState* st) {
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        st->n_valid = 0;
-        st->n_inliers = 0;
-        st->flags = 0;
-        st->redo = 0;
-        st->epoch_used = epoch;
-        st->blocks_done = 0;
-        st->any_valid = 0;
-        st->red_lo = 0x7fffffffffffffffLL;
-        st->red_hi = static_cast<long long>(0x8000000000000000ULL);
-    }
-    if (mode == 1) {
-        if (threadIdx.x == 0) {
-            st->t_lo_bits = given_lo;
-            st->t_hi_bits = given_hi;
-        }
-        return;
-    }
+__device__ __forceinline__ void scan_sorted_bounds(const int4* __restrict__ events, long long n, int polarity, int warp, int lane,
+                                                   long long* out) {
     long long found = -1;
     if (warp == 0) {
         for (long long base = 0; base < n; base += 32) {
@@ -106,7 +107,7 @@ __global__ void bounds_init_kernel(const int4* __restrict__ events, long long n,
                 break;
             }
         }
-        if (lane == 0) st->t_lo_bits = found >= 0 ? unpack_event(__ldg(events + found)).t_bits : 0;
+        if (lane == 0) out[0] = found >= 0 ? unpack_event(__ldg(events + found)).t_bits : 0;
     } else if (warp == 1) {
         for (long long top = n; top > 0; top -= 32) {
             long long i = top - 1 - lane;
@@ -118,55 +119,83 @@ __global__ void bounds_init_kernel(const int4* __restrict__ events, long long n,
                 break;
             }
         }
-        if (lane == 0) st->t_hi_bits = found >= 0 ? unpack_event(__ldg(events + found)).t_bits : 0;
+        if (lane == 0) out[1] = found >= 0 ? unpack_event(__ldg(events + found)).t_bits : 0;
     }
+}
+
+// K0a (stage-by-stage path only; the fused path finds its bounds inside K1): reset the state block
+// and set the bounds.   mode 0: first / last valid event      mode 1: bounds given by the caller
+__global__ void bounds_init_kernel(const int4* __restrict__ events, long long n, int polarity, int mode,
+                                   long long given_lo, long long given_hi, unsigned epoch, FrameState* st) {
+    if (threadIdx.x == 0) {
+        st->n_valid = 0;
+        st->n_inliers = 0;
+        st->flags = 0;
+        st->redo = 0;
+        st->epoch_used = epoch;
+        st->blocks_done = 0;
+        st->any_valid = 0;
+        st->red_lo = 0;
+        st->red_hi = 0;
+    }
+    if (mode == 1) {
+        if (threadIdx.x == 0) {
+            st->t_lo_bits = given_lo;
+            st->t_hi_bits = given_hi;
+        }
+        return;
+    }
+    scan_sorted_bounds(events, n, polarity, threadIdx.x >> 5, threadIdx.x & 31, &st->t_lo_bits);
 }
 
 // ---------------------------------------------------------------------------------------------
 // K0b: exact min / max over all valid events (one extra pass over the stream).  The last CTA to
-// finish publishes the result.  With conditional = 1 it only runs when the optimistic bounds of
-// K0a were found wrong by K1 (state->redo).
+// finish publishes the result into state->t_lo_bits / t_hi_bits and clears the frame counters.
+// Used by XM_TBOUNDS_REDUCE and, tail-launched from K1, by the fix-up of wrong optimistic bounds.
 // ---------------------------------------------------------------------------------------------
 template <bool F64>
 __global__ void __launch_bounds__(256) bounds_reduce_kernel(const int4* __restrict__ events, long long n, int polarity,
-                                                            int conditional, FrameState* st) {
-    if (conditional && !*reinterpret_cast<volatile unsigned*>(&st->redo)) return;
-    long long lo = 0x7fffffffffffffffLL;
-    long long hi = static_cast<long long>(0x8000000000000000ULL);
+                                                            FrameState* st) {
+    unsigned long long lo = 0xffffffffffffffffULL, hi = 0;  // ordered domain
+    bool any = false;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         // default L2 policy: the second pass (K1) re-reads these lines and may still find them in L2
         EventFields e = unpack_event(ld_event_plain(events + i));
         if (event_valid(e, polarity)) {
-            long long key = F64 ? f64_bits_to_sortable(e.t_bits) : e.t_bits;
-            lo = key < lo ? key : lo;
-            hi = key > hi ? key : hi;
+            const unsigned long long u = time_to_ordered<F64>(e.t_bits);
+            lo = u < lo ? u : lo;
+            hi = u > hi ? u : hi;
+            any = true;
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        long long l2 = __shfl_xor_sync(0xffffffffu, lo, o);
-        long long h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o);
+        const unsigned long long h2 = __shfl_xor_sync(0xffffffffu, hi, o);
         lo = l2 < lo ? l2 : lo;
         hi = h2 > hi ? h2 : hi;
     }
+    any = __any_sync(0xffffffffu, any);
     __shared__ unsigned s_last;
-    if ((threadIdx.x & 31) == 0 && lo <= hi) {
-        atomicMin(&st->red_lo, lo);
-        atomicMax(&st->red_hi, hi);
-        st->any_valid = 1;
+    if ((threadIdx.x & 31) == 0 && any) {
+        atomicMax(&st->red_lo, ~lo);
+        atomicMax(&st->red_hi, hi + 1ULL);
     }
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
         __threadfence();
-        long long rl = *reinterpret_cast<volatile long long*>(&st->red_lo);
-        long long rh = *reinterpret_cast<volatile long long*>(&st->red_hi);
-        bool any = rl <= rh;
-        st->t_lo_bits = any ? (F64 ? sortable_to_f64_bits(rl) : rl) : 0;
-        st->t_hi_bits = any ? (F64 ? sortable_to_f64_bits(rh) : rh) : 0;
+        const unsigned long long rl = *reinterpret_cast<volatile unsigned long long*>(&st->red_lo);
+        const unsigned long long rh = *reinterpret_cast<volatile unsigned long long*>(&st->red_hi);
+        const bool found = rh != 0ULL;
+        st->t_lo_bits = found ? ordered_to_time<F64>(~rl) : 0;
+        st->t_hi_bits = found ? ordered_to_time<F64>(rh - 1ULL) : 0;
+        st->any_valid = found ? 1u : 0u;
         st->blocks_done = 0;
         st->n_valid = 0;
         st->n_inliers = 0;
@@ -390,16 +419,39 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
         tma_load_1d_hint(ring + slot * (kEvChunk * 16), span_ptr + c * kEvChunk, bytes, full + slot, pol);
     };
 
+    if (p.use_pdl) pdl_launch_dependents();  // the epilogue may start its (table-only) prologue right away
+    long long* s_bounds = reinterpret_cast<long long*>(ev_smem + 80);  // [2]
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) mbar_init(full + s, 1);
         mbar_init(winbar, 1);
         const int pre = n_chunks < p.stages ? n_chunks : p.stages;
-        for (int c = 0; c < pre; ++c) issue_chunk(c, c);  // prologue: fill the ring
+        for (int c = 0; c < pre; ++c) issue_chunk(c, c);  // prologue: fill the ring (inputs only)
     }
+    // t.min() / t.max() of a time-sorted frame are its first / last valid event; every CTA looks them
+    // up itself (two cached 512-byte reads) instead of waiting for a separate kernel
+    if (p.bounds_mode == 0) scan_sorted_bounds(p.events, p.n, p.polarity, warp, lane, s_bounds);
     __syncthreads();
+    // everything above only reads inputs; below this line the kernel touches the state block and the
+    // scatter map, which the previous frame's epilogue may still be using
+    if (p.use_pdl) pdl_wait();
 
+    long long t_lo, t_hi;
+    if (p.bounds_mode == 0) {
+        t_lo = s_bounds[0];
+        t_hi = s_bounds[1];
+    } else if (p.bounds_mode == 1) {
+        t_lo = p.given_lo;
+        t_hi = p.given_hi;
+    } else {
+        t_lo = st->t_lo_bits;
+        t_hi = st->t_hi_bits;
+    }
+    if (p.bounds_mode != 2 && blockIdx.x == 0 && tid == 0) {  // for xm_frame_status
+        st->t_lo_bits = t_lo;
+        st->t_hi_bits = t_hi;
+    }
     TimeCol<F64> tc;
-    tc.init(st->t_lo_bits, st->t_hi_bits, p.t_px_scale);
+    tc.init(t_lo, t_hi, p.t_px_scale);
 
     unsigned n_valid = 0, n_inl = 0, flags = 0;
     int win_lo = 0, win_n = 0;
@@ -525,16 +577,17 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
             st->blocks_done = 0;
             if (f & kStatusTBounds) {
                 st->redo = 1;
-                st->epoch_used = p.epoch + 1;
                 st->flags = f & ~(kStatusPixelOob | kStatusScatterOob);
                 // Exact fix-up, launched from the device into the tail-launch stream (CUDA dynamic
                 // parallelism): both grids run, in this order, after this grid has drained and before
                 // the next kernel of the host stream (the epilogue) starts.  Costs nothing when the
                 // optimistic bounds hold.
-                bounds_reduce_kernel<F64><<<p.fix_reduce_grid, 256, 0, cudaStreamTailLaunch>>>(p.events, p.n, p.polarity, 0, st);
+                bounds_reduce_kernel<F64><<<p.fix_reduce_grid, 256, 0, cudaStreamTailLaunch>>>(p.events, p.n, p.polarity, st);
                 EventParams q = p;
                 q.epoch = p.epoch + 1;
                 q.arm_fixup = 0;
+                q.use_pdl = 0;
+                q.bounds_mode = 2;
                 events_kernel<F64, SAFE><<<gridDim.x, kEvThreads, p.smem_bytes, cudaStreamTailLaunch>>>(q);
             }
         }
@@ -547,6 +600,9 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
 struct EpilogueParams {
     const unsigned long long* map;
     const FrameState* state;
+    unsigned epoch;          // epoch of the frame's first pass; the fix-up pass (state->redo) used epoch + 1
+    FrameState* recycle;     // state block of the frame after next: cleared here (ring of 4), or NULL
+    int use_pdl;             // 1: execute the griddepcontrol instructions
     const short2* remap_xy;
     const short4* tile_box;  // per 32x32 output tile: bounding box (x0, y0, x1, y1) of its remap targets; x1 < 0: none
     int rect_w, rect_h;
@@ -557,8 +613,19 @@ struct EpilogueParams {
     void* dst;
 };
 
+__device__ __forceinline__ void recycle_state(FrameState* st) {
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(st);
+#pragma unroll
+    for (int i = 0; i < static_cast<int>(sizeof(FrameState) / 8); ++i) w[i] = 0ULL;
+}
+
 __global__ void __launch_bounds__(256) epilogue_camera_kernel(const EpilogueParams p) {
-    const unsigned epoch = p.state->epoch_used;
+    if (p.use_pdl) {
+        pdl_launch_dependents();
+        pdl_wait();
+    }
+    const unsigned epoch = p.epoch + p.state->redo;
+    if (p.recycle && blockIdx.x == 0 && threadIdx.x == 0) recycle_state(p.recycle);
     const long long n = static_cast<long long>(p.out_w) * p.out_h;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -583,7 +650,7 @@ __global__ void __launch_bounds__(256, 7) epilogue_projector_kernel(const Epilog
     unsigned short* s_raw = reinterpret_cast<unsigned short*>(ev_smem);
     unsigned short* s_h = s_raw + p.region_cap;
 
-    const unsigned epoch = p.state->epoch_used;
+    if (p.use_pdl) pdl_launch_dependents();
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int u0 = blockIdx.x * kTile, v0 = blockIdx.y * kTile;
@@ -603,6 +670,11 @@ __global__ void __launch_bounds__(256, 7) epilogue_projector_kernel(const Epilog
         m[k] = make_short2(-1, -1);
         if (u < p.out_w && v < p.out_h) m[k] = __ldg(p.remap_xy + v * p.out_w + u);
     }
+
+    // up to here only calibration tables were read; the key map and the state block belong to K1
+    if (p.use_pdl) pdl_wait();
+    const unsigned epoch = p.epoch + p.state->redo;
+    if (p.recycle && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) recycle_state(p.recycle);
 
     int val[4] = {0, 0, 0, 0};
     if (x1 >= 0) {
@@ -668,6 +740,168 @@ __global__ void __launch_bounds__(256, 7) epilogue_projector_kernel(const Epilog
                     const int gy = m[k].y + dy;
                     if (gy < 0 || gy >= p.rect_h) continue;
                     for (int dx = -r; dx <= r; ++dx) {
+                        const int gx = m[k].x + dx;
+                        if (gx < 0 || gx >= p.rect_w) continue;
+                        best = max(best, key_disparity(p.map[gy * p.rect_w + gx], epoch));
+                    }
+                }
+                val[k] = best;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int u = u0 + lane, v = v0 + warp + k * 8;
+        if (u < p.out_w && v < p.out_h) emit_pixel_int(p.out, p.dst, v * p.out_w + u, val[k]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 (projector view), 7x7 dilate, even rect_w: the hot variant.
+//
+// Same tiling, but the dilation is done as a full separable pass over the tile's source region with
+// register sliding windows instead of 7 taps per cell:
+//   A  region (bounding box + halo, left edge aligned to an even x) decoded from the key map with
+//      128-bit loads (two cells) into shared memory as packed u16 pairs, rows padded with zeros
+//   B  horizontal 7-max: a thread takes 16 cells of a row as 8 words and produces 8 outputs with
+//      the 2-4-7 max ladder (32 max ops instead of 48 loads + 48 max)
+//   C  vertical 7-max on column PAIRS with per-halfword SIMD max (__vmaxu2): 14 words in, 8 x 2
+//      outputs, same ladder
+//   D  every output pixel reads its dilated value at its own (x_rect, y_rect) and converts.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRowPad = 4;    // zero cells left of the data in every shared-memory row
+constexpr int kRowExtra = 16;  // total padding per row (4 left + 12 right)
+
+__device__ __forceinline__ unsigned magic_div(int d) { return 0xffffffffu / static_cast<unsigned>(d) + 1u; }
+
+__global__ void __launch_bounds__(256, 7) epilogue_projector7_kernel(const EpilogueParams p) {
+    extern __shared__ __align__(128) unsigned char ev_smem[];
+    unsigned short* bufA = reinterpret_cast<unsigned short*>(ev_smem);
+    unsigned short* bufB = bufA + p.region_cap;
+    constexpr int R = 3;
+
+    if (p.use_pdl) pdl_launch_dependents();
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int u0 = blockIdx.x * kTile, v0 = blockIdx.y * kTile;
+
+    const short4 box = __ldg(p.tile_box + blockIdx.y * gridDim.x + blockIdx.x);
+    const int x0 = box.x, y0 = box.y, x1 = box.z, y1 = box.w;
+    if (p.out.kind == 0 && p.out.depth_lut && tid < 128) prefetch_l1(p.out.depth_lut + tid * 32);
+
+    short2 m[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int u = u0 + lane, v = v0 + warp + k * 8;
+        m[k] = make_short2(-1, -1);
+        if (u < p.out_w && v < p.out_h) m[k] = __ldg(p.remap_xy + v * p.out_w + u);
+    }
+
+    // up to here only calibration tables were read; the key map and the state block belong to K1
+    if (p.use_pdl) pdl_wait();
+    const unsigned epoch = p.epoch + p.state->redo;
+    if (p.recycle && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) recycle_state(p.recycle);
+
+    int val[4] = {0, 0, 0, 0};
+    if (x1 >= 0) {
+        const int rx0 = (x0 - R) & ~1;                 // even
+        const int rw = (x1 + R - rx0 + 2) & ~1;        // even number of data cells
+        const int ry0 = y0 - R, rh = y1 - y0 + 1 + 2 * R;
+        const int stride = rw + kRowExtra;             // cells per shared-memory row
+        if (stride * rh <= p.region_cap) {
+            // ---- A: decode the region (pads included, written as zeros) -------------------------
+            {
+                const int pairs = stride >> 1;
+                const unsigned mg = magic_div(pairs);
+                unsigned* dst = reinterpret_cast<unsigned*>(bufA);
+                for (int c = tid; c < pairs * rh; c += 256) {
+                    const int ry = static_cast<int>(__umulhi(static_cast<unsigned>(c), mg));
+                    const int cx = 2 * (c - ry * pairs) - kRowPad;  // data coordinate of the pair's first cell (even)
+                    const int gx = rx0 + cx, gy = ry0 + ry;
+                    unsigned packed = 0;
+                    if (cx >= 0 && cx < rw && gx >= 0 && gx < p.rect_w && gy >= 0 && gy < p.rect_h) {
+                        const ulonglong2 kk = __ldcg(reinterpret_cast<const ulonglong2*>(p.map + gy * p.rect_w + gx));
+                        packed = static_cast<unsigned>(key_disparity(kk.x, epoch)) | (static_cast<unsigned>(key_disparity(kk.y, epoch)) << 16);
+                    }
+                    dst[c] = packed;
+                }
+            }
+            __syncthreads();
+            // ---- B: horizontal 7-max, 8 outputs per task ------------------------------------------
+            {
+                const int segs = (rw + 7) >> 3;
+                const unsigned mg = magic_div(segs);
+                for (int t = tid; t < segs * rh; t += 256) {
+                    const int ry = static_cast<int>(__umulhi(static_cast<unsigned>(t), mg));
+                    const int seg = t - ry * segs;
+                    const unsigned* src = reinterpret_cast<const unsigned*>(bufA + ry * stride) + 4 * seg;
+                    unsigned v[16];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const unsigned w = src[i];
+                        v[2 * i] = w & 0xffffu;
+                        v[2 * i + 1] = w >> 16;
+                    }
+                    // v[i] = padded cell 8*seg + i = data cell 8*seg + i - 4; out[j] = max(v[j+1 .. j+7])
+                    unsigned m2[15], m4[13];
+#pragma unroll
+                    for (int i = 1; i < 15; ++i) m2[i] = max(v[i], v[i + 1]);
+#pragma unroll
+                    for (int i = 1; i < 13; ++i) m4[i] = max(m2[i], m2[i + 2]);
+                    unsigned* dst = reinterpret_cast<unsigned*>(bufB + ry * stride) + 4 * seg + 2;
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const unsigned a = max(m4[j + 1], m4[j + 4]);
+                        const unsigned b = max(m4[j + 2], m4[j + 5]);
+                        dst[j >> 1] = a | (b << 16);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- C: vertical 7-max on column pairs, 8 output rows per task -----------------------------
+            {
+                const int orows = rh - 2 * R;  // rows a pixel of this tile can map to: [R, rh - R)
+                const int vsegs = (orows + 7) >> 3;
+                const int cpairs = rw >> 1;
+                const unsigned mg = magic_div(cpairs);
+                for (int t = tid; t < vsegs * cpairs; t += 256) {
+                    const int vs = static_cast<int>(__umulhi(static_cast<unsigned>(t), mg));
+                    const int q = t - vs * cpairs;
+                    const int word = (kRowPad >> 1) + q;  // word index of the pair inside a row
+                    const int rbase = 8 * vs;             // first input row; output rows R + 8*vs + j
+                    unsigned x[14];
+#pragma unroll
+                    for (int i = 0; i < 14; ++i) {
+                        const int ry = rbase + i;
+                        x[i] = ry < rh ? reinterpret_cast<const unsigned*>(bufB + ry * stride)[word] : 0u;
+                    }
+                    unsigned m2[13], m4[11];
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) m2[i] = __vmaxu2(x[i], x[i + 1]);
+#pragma unroll
+                    for (int i = 0; i < 11; ++i) m4[i] = __vmaxu2(m2[i], m2[i + 2]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int ry = R + rbase + j;
+                        if (ry < rh - R) reinterpret_cast<unsigned*>(bufA + ry * stride)[word] = __vmaxu2(m4[j], m4[j + 3]);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- D: gather ----------------------------------------------------------------------------
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h)
+                    val[k] = bufA[(m[k].y - ry0) * stride + (m[k].x - rx0) + kRowPad];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!(m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h)) continue;
+                int best = 0;
+                for (int dy = -R; dy <= R; ++dy) {
+                    const int gy = m[k].y + dy;
+                    if (gy < 0 || gy >= p.rect_h) continue;
+                    for (int dx = -R; dx <= R; ++dx) {
                         const int gx = m[k].x + dx;
                         if (gx < 0 || gx >= p.rect_w) continue;
                         best = max(best, key_disparity(p.map[gy * p.rect_w + gx], epoch));
