@@ -74,6 +74,7 @@ struct XmCtx {
     short2* d_remap_xy = nullptr;
     short4* d_tile_box = nullptr;  // bounding box of the remap targets of every 32x32 output tile
     unsigned char* d_turbo = nullptr;
+    unsigned long long* d_dbg = nullptr;  // per-CTA phase timestamps (option debug & 8)
     float* d_depth_lut = nullptr;  // [32768], exact depth of every integer disparity
     bool have_turbo = false;
     unsigned long long* d_map = nullptr;
@@ -102,6 +103,10 @@ struct XmCtx {
     int opt_pdl = 1;          // programmatic dependent launch between K1 / K2 / next K1
     int opt_safe_tables = 1;  // use the check-free scatter when the tables were verified
     int opt_stages = 2;  // depth of the shared-memory event ring of K1
+    int opt_debug = 0;        // timing experiments only
+    int opt_win_stages = 2;   // depth of the X-map window ring (warp-specialised K1)
+    int opt_k1_variant = 2;   // 2: lean warp-specialised K1 (integer time, verified tables; else falls back to 1),
+                              // 1: warp-specialised K1 (mbarrier pipelines), 0: block-barrier K1
     int opt_region_cells = 64 * 64;
     // per-kernel CUDA-event timing (option "profile"): pairs around K1 and K2 of every frame
     int opt_profile = 0;
@@ -159,7 +164,12 @@ unsigned next_epoch(XmCtx* c, unsigned count, cudaStream_t s, cudaError_t* err) 
 }
 
 using EvKernel = void (*)(xm::EventParams);
-EvKernel ev_kernel(bool f64, bool safe) {
+EvKernel ev_kernel(bool f64, bool safe, int variant = 0, bool cam = false) {
+    if (variant == 2 && !f64 && safe) return cam ? xm::events_lean_kernel<true> : xm::events_lean_kernel<false>;
+    if (variant >= 1) {
+        if (f64) return safe ? xm::events_ws_kernel<true, true> : xm::events_ws_kernel<true, false>;
+        return safe ? xm::events_ws_kernel<false, true> : xm::events_ws_kernel<false, false>;
+    }
     if (f64) return safe ? xm::events_kernel<true, true> : xm::events_kernel<true, false>;
     return safe ? xm::events_kernel<false, true> : xm::events_kernel<false, false>;
 }
@@ -186,22 +196,26 @@ int configure_event_kernels(XmCtx* c) {
     if (c->opt_stage_xmap && c->col_stride > 0) cols = c->opt_smem_cols_bytes / (c->col_stride * 2);
     if (cols > c->xmap_w) cols = c->xmap_w;
     c->cap_cols = cols;
-    c->ev_smem = xm::events_smem_bytes(c->opt_stages, cols * c->col_stride * 2);
+    const int win_bytes = cols * c->col_stride * 2;
+    const int variant = c->opt_k1_variant;
+    const int threads = variant >= 1 ? xm::kWsThreads : xm::kEvThreads;
+    c->ev_smem = variant >= 1 ? xm::events_ws_smem_bytes(c->opt_stages, c->opt_win_stages, win_bytes)
+                              : xm::events_smem_bytes(c->opt_stages, win_bytes);
     // the attribute is per function, not per context: always allow the device maximum so that
     // contexts with different X-map geometries can coexist in one process
     int optin = 0;
     XM_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     c->ev_occ_i64 = c->ev_occ_f64 = 1 << 30;
     for (int f64 = 0; f64 < 2; ++f64)
-        for (int safe = 0; safe < 2; ++safe) {
-            EvKernel k = ev_kernel(f64 != 0, safe != 0);
+        for (int safe = 0; safe < 3; ++safe) {  // safe == 2: the second (camera-view) lean instantiation
+            EvKernel k = ev_kernel(f64 != 0, safe != 0, variant, safe == 2);
             cudaFuncAttributes fa;
             XM_CUDA(cudaFuncGetAttributes(&fa, k));
             const int dyn = optin - static_cast<int>(fa.sharedSizeBytes);
             if (c->ev_smem > dyn) return fail(XM_ERR_UNSUPPORTED, "event kernel needs %d B of shared memory, device allows %d", c->ev_smem, dyn);
             XM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
             int occ = 0;
-            XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, xm::kEvThreads, c->ev_smem));
+            XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, c->ev_smem));
             int& dst = f64 ? c->ev_occ_f64 : c->ev_occ_i64;
             dst = occ < dst ? occ : dst;
         }
@@ -380,6 +394,9 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     p.cap_cols = c->cap_cols;
     p.lookahead = c->opt_lookahead;
     p.stages = c->opt_stages;
+    p.win_stages = c->opt_win_stages;
+    p.debug = c->opt_debug;
+    p.dbg = (c->opt_debug & 8) ? c->d_dbg : nullptr;
     p.arm_fixup = fixup ? 1 : 0;
     p.fix_reduce_grid = grid_for(a->n_events, 256, 8, c->sm_count * 8);
     p.smem_bytes = c->ev_smem;
@@ -393,9 +410,10 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
         const int grid = grid_for(a->n_events, xm::kEvThreads, xm::kEvPerThread, c->sm_count * occ);
         // when an event violates the assumed bounds the last CTA of K1 tail-launches the exact
         // two-pass fix-up from the device (no extra host launches in the common case)
-        const EvKernel k1 = ev_kernel(f64, c->lut_safe && c->xmap_safe && c->opt_safe_tables);
+        const EvKernel k1 = ev_kernel(f64, c->lut_safe && c->xmap_safe && c->opt_safe_tables, c->opt_k1_variant, a->view == XM_VIEW_CAMERA);
+        const int threads = c->opt_k1_variant >= 1 ? xm::kWsThreads : xm::kEvThreads;
         // programmatic dependent launch: K1's input-only prologue may overlap the previous frame's epilogue
-        XM_CUDA(launch_pdl(k1, dim3(grid), dim3(xm::kEvThreads), c->ev_smem, s, use_pdl && c->prev_was_frame, p));
+        XM_CUDA(launch_pdl(k1, dim3(grid), dim3(threads), c->ev_smem, s, use_pdl && c->prev_was_frame, p));
         XM_LAUNCHED();
         c->prev_was_frame = true;
     } else {
@@ -583,6 +601,7 @@ int xm_ctx_destroy(XmCtx* c) {
     cudaFree(c->d_tile_box);
     cudaFree(c->d_turbo);
     cudaFree(c->d_depth_lut);
+    cudaFree(c->d_dbg);
     cudaFree(c->d_map);
     cudaFree(c->d_state);
     cudaFree(c->d_counts);
@@ -622,8 +641,26 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
     }
     if (!strcmp(key, "stages")) {
-        if (v < 1 || v > xm::kMaxStages) return fail(XM_ERR_INVALID_ARG, "stages must be 1..%d", xm::kMaxStages);
+        if (v < 1 || v > xm::kWsMaxStages) return fail(XM_ERR_INVALID_ARG, "stages must be 1..%d", xm::kWsMaxStages);
         c->opt_stages = v;
+        return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
+    }
+    if (!strcmp(key, "debug")) {
+        c->opt_debug = v;
+        if ((v & 8) && !c->d_dbg) {
+            XM_CUDA(cudaMalloc(&c->d_dbg, 4096 * 8 * sizeof(unsigned long long)));
+            XM_CUDA(cudaMemset(c->d_dbg, 0, 4096 * 8 * sizeof(unsigned long long)));
+        }
+        return XM_OK;
+    }
+    if (!strcmp(key, "win_stages")) {
+        if (v < 1 || v > xm::kWsMaxStages) return fail(XM_ERR_INVALID_ARG, "win_stages must be 1..%d", xm::kWsMaxStages);
+        c->opt_win_stages = v;
+        return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
+    }
+    if (!strcmp(key, "k1_variant")) {
+        if (v < 0 || v > 2) return fail(XM_ERR_INVALID_ARG, "k1_variant must be 0, 1 or 2");
+        c->opt_k1_variant = v;
         return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
     }
     if (!strcmp(key, "k2_variant")) {
@@ -682,7 +719,10 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     if (!c || !key || !value) return fail(XM_ERR_INVALID_ARG, "null argument");
     if (!strcmp(key, "stage_xmap")) *value = c->opt_stage_xmap;
     else if (!strcmp(key, "smem_cols_bytes")) *value = c->opt_smem_cols_bytes;
+    else if (!strcmp(key, "debug_ptr")) *value = static_cast<int64_t>(reinterpret_cast<uintptr_t>(c->d_dbg));
     else if (!strcmp(key, "stages")) *value = c->opt_stages;
+    else if (!strcmp(key, "win_stages")) *value = c->opt_win_stages;
+    else if (!strcmp(key, "k1_variant")) *value = c->opt_k1_variant;
     else if (!strcmp(key, "pdl")) *value = c->opt_pdl;
     else if (!strcmp(key, "k2_variant")) *value = c->opt_k2_variant;
     else if (!strcmp(key, "safe_tables")) *value = c->opt_safe_tables && c->lut_safe && c->xmap_safe;

@@ -208,6 +208,48 @@ struct TimeCol {
     }
 };
 
+// Integer timestamps, all-integer evaluation.  With dt = t - min, R = max - min, s = T_PX_SCALE the
+// reference's rint(fl(fl(dt / R) * s)) equals floor((2 dt s + R) / (2 R)) unless 2 dt s + R is a multiple
+// of 2R (an exact .5 tie, where half-even and the double rounding decide): the float64 result is within
+// 4e-13 of dt s / R while a non-tie is at least 1 / (2R) > 2e-10 away from any half-integer.  The
+// division by the frame constant 2R is a multiply-high with a magic number (exact for n < 2^31).
+struct IntCol {
+    unsigned long long lo;
+    unsigned range, scale2, d, M;
+    int sh;
+    bool ok;  // R > 0 and (2 s + 1) R < 2^31 (frames up to ~1.5 s at T_PX_SCALE = 719)
+
+    __device__ __forceinline__ void init(long long lo_bits, long long hi_bits, int t_px_scale) {
+        lo = static_cast<unsigned long long>(lo_bits);
+        const unsigned long long r = hi_bits > lo_bits ? static_cast<unsigned long long>(hi_bits) - lo : 0ULL;
+        const unsigned long long nmax = r * static_cast<unsigned long long>(2 * t_px_scale + 1);
+        ok = r > 0 && t_px_scale > 0 && r < 0x40000000ULL && nmax < 0x80000000ULL;
+        range = static_cast<unsigned>(r);
+        scale2 = 2u * static_cast<unsigned>(t_px_scale);
+        d = 2u * range;
+        M = 0;
+        sh = 0;
+        if (ok) {
+            const int e = 31 - __clz(d);  // floor(log2 d), d >= 2
+            if ((d & (d - 1u)) == 0u) {   // power of two: n / d = (n >> 1) >> (e - 1)
+                M = 0x80000000u;
+                sh = e - 1;
+            } else {                      // 2^e < d < 2^(e+1): M = ceil(2^(32+e) / d) fits 32 bits
+                M = static_cast<unsigned>(((1ULL << (32 + e)) + d - 1u) / d);
+                sh = e;
+            }
+        }
+    }
+    // column of t; `bad`: t outside [min, max] or an exact rounding tie (caller takes the float64 path)
+    __device__ __forceinline__ unsigned column(long long t_bits, bool& bad) const {
+        const unsigned long long dt = static_cast<unsigned long long>(t_bits) - lo;
+        const unsigned n = static_cast<unsigned>(dt) * scale2 + range;
+        const unsigned q = __umulhi(n, M) >> sh;
+        bad = dt > range || n == q * d;
+        return q;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Scatter keys: the reference's `map[rows, cols] = vals` keeps the LAST duplicate.  Each event
 // contributes key = epoch:16 | event_index:32 | disparity:16 and the map keeps the maximum, i.e.
@@ -337,6 +379,53 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// raw 32-bit shared-address variants (the address arithmetic is hoisted out of the hot loops)
+__device__ __forceinline__ void mbar_wait_a(unsigned bar_addr, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "XM_WAITA_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra XM_DONEA_%=;\n\t"
+        "bra XM_WAITA_%=;\n\t"
+        "XM_DONEA_%=:\n\t"
+        "}" ::"r"(bar_addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(unsigned bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ int4 lds128_a(unsigned addr) {
+    int4 r;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ int lds32_a(unsigned addr) {
+    int r;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ int lds_s16_a(unsigned addr) {
+    int r;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void cp_async_4_a(unsigned smem_addr, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gmem_src) : "memory");
+}
+// predicated 64-bit max reduction (no return value -> RED)
+__device__ __forceinline__ void red_max_u64_if(unsigned long long* addr, unsigned long long val, bool pred) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %2, 0;\n\t"
+        "@q red.global.max.u64 [%0], %1;\n\t"
+        "}" ::"l"(addr),
+        "l"(val), "r"(static_cast<int>(pred))
+        : "memory");
 }
 
 // same with an L2 cache-policy hint (evict-first for the one-pass event stream)

@@ -64,6 +64,9 @@ struct EventParams {
     int fix_reduce_grid;  // grid of the fix-up's bounds reduction
     int smem_bytes;       // dynamic shared memory of this launch (re-used by the fix-up launch)
     int stages;       // depth of the shared-memory event ring (1..kMaxStages)
+    int win_stages;   // (warp-specialised K1) depth of the X-map window ring
+    unsigned long long* dbg;  // optional per-CTA phase timestamps (8 words per CTA), or NULL
+    int debug;        // timing experiments only (results WRONG): 1 = coalesced LUT gather, 2 = coalesced scatter cells
 };
 
 // order-preserving map of a timestamp (int64, or float64 bit pattern) to uint64
@@ -266,7 +269,7 @@ __device__ __forceinline__ void front_half(const EventParams& p, const TimeCol<F
             const bool valid = in && (((static_cast<unsigned>(raw[k].y) ^ 1u) & pol_mask) == 0u);
             const bool ok = valid && ex < static_cast<unsigned>(p.cam_w) && ey < static_cast<unsigned>(p.cam_h);
             const int pix = ok ? static_cast<int>(ey) * p.cam_w + static_cast<int>(ex) : 0;
-            if (ok) cp_async_4(s_lut + k * kEvThreads + tid, p.lut_xy + pix);
+            if (ok) cp_async_4(s_lut + k * kEvThreads + tid, p.lut_xy + ((p.debug & 1) ? ((k * kEvThreads + tid) & 0xffff) : pix));
             const long long t_bits = (static_cast<long long>(raw[k].w) << 32) | static_cast<unsigned>(raw[k].z);
             bool viol, tie;
             int cc = tc.column_fast_nb(t_bits, viol, tie);
@@ -589,6 +592,602 @@ __global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams
                 q.use_pdl = 0;
                 q.bounds_mode = 2;
                 events_kernel<F64, SAFE><<<gridDim.x, kEvThreads, p.smem_bytes, cudaStreamTailLaunch>>>(q);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1, warp-specialised variant (default).
+//
+// Same work per event as events_kernel, but without any CTA-wide barrier in the steady state:
+//   * warp 8 is the PRODUCER: one lane streams the CTA's span through a ring of event stages
+//     (TMA bulk copies, `full_ev` / `empty_ev` mbarriers) and, for every chunk, stages the X-map time
+//     columns between the columns of the chunk's first and last event into a ring of window buffers
+//     (`full_win` / `empty_win`); the window's (first column, count) travels in shared memory.
+//   * warps 0-7 are CONSUMERS: each runs the front half of chunk c+1 (events out of the stage,
+//     stage released right away, LUT gathers started with cp.async) and then the back half of chunk c
+//     (window lookup, disparity, scatter).  An event whose column is not in its chunk's window
+//     (unsorted input, or more columns than the window holds) reads the X-map through L2 instead,
+//     so no block-wide agreement on the column range is needed any more.
+// Warps drift apart by up to the ring depth; the only synchronisation is mbarrier arrive / wait.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWsThreads = kEvThreads + 32;
+constexpr int kWsMaxStages = 4;
+
+__host__ __device__ inline int events_ws_smem_bytes(int ev_stages, int win_stages, int win_bytes) {
+    return kEvSmemHeader + kEvLutBytes + ev_stages * kEvChunk * 16 + win_stages * win_bytes;
+}
+
+template <bool SAFE>
+__device__ __forceinline__ void back_ws(const EventParams& p, const ChunkRegs& r, const int* s_lut, const short* s_win, int win_lo,
+                                        int win_n, int tid, unsigned idx_base, unsigned& n_inl, unsigned& flags) {
+    const unsigned y_lim = static_cast<unsigned>(p.xmap_h - 1);
+    int lut[kEvPerThread];
+#pragma unroll
+    for (int k = 0; k < kEvPerThread; ++k) lut[k] = s_lut[k * kEvThreads + tid];
+    int xp[kEvPerThread];
+    bool y_ok[kEvPerThread];
+    unsigned miss = 0;
+#pragma unroll
+    for (int k = 0; k < kEvPerThread; ++k) {
+        const int ycr = lut[k] >> 16;
+        // x_maps_disparity.py:23: 0 <= y_rect < H - 1 (last row excluded)
+        y_ok[k] = r.col[k] >= 0 && static_cast<unsigned>(ycr) < y_lim;
+        const int rel = r.col[k] - win_lo;
+        const bool in_win = static_cast<unsigned>(rel) < static_cast<unsigned>(win_n);
+        xp[k] = s_win[(y_ok[k] && in_win) ? rel * p.col_stride + ycr : 0];
+        miss |= (y_ok[k] && !in_win) ? (1u << k) : 0u;
+    }
+    if (miss) {  // column outside the staged window: read the transposed table through L2
+#pragma unroll
+        for (int k = 0; k < kEvPerThread; ++k)
+            if (miss & (1u << k)) xp[k] = __ldg(p.xmap_t + static_cast<long long>(r.col[k]) * p.col_stride + (lut[k] >> 16));
+    }
+#pragma unroll
+    for (int k = 0; k < kEvPerThread; ++k) {
+        const int xcr = static_cast<short>(lut[k] & 0xffff);
+        const int ycr = lut[k] >> 16;
+        const int disp = static_cast<short>(xp[k] - xcr - p.x_offset);  // int16 arithmetic wraps
+        bool inl = y_ok[k] && disp >= 0;
+        n_inl += inl ? 1u : 0u;
+        int cell;
+        if (p.view == 1) {
+            cell = r.pix[k];
+        } else if (SAFE) {
+            cell = ycr * p.rect_w + (xp[k] - p.x_offset);  // = x_rect + disp, in [0, rect_w) for verified tables
+        } else {
+            int xpr = static_cast<short>(xcr + disp);
+            xpr += xpr < 0 ? p.rect_w : 0;  // NumPy negative index wraps once
+            const bool in_map = xpr >= 0 && xpr < p.rect_w && ycr < p.rect_h;
+            flags |= (inl && !in_map) ? kStatusScatterOob : 0u;  // the reference raises IndexError here
+            inl = inl && in_map;
+            cell = ycr * p.rect_w + xpr;
+        }
+        if (p.debug & 2) cell = static_cast<int>((idx_base + static_cast<unsigned>(k * kEvThreads)) & 0xfffffu);
+        if (inl) atomicMax(p.map + cell, make_key32(p.epoch, idx_base + static_cast<unsigned>(k * kEvThreads), disp));
+    }
+}
+
+template <bool F64, bool SAFE>
+__global__ void __launch_bounds__(kWsThreads, 3) events_ws_kernel(const EventParams p) {
+    extern __shared__ __align__(128) unsigned char ev_smem[];
+    uint64_t* full_ev = reinterpret_cast<uint64_t*>(ev_smem);         // [kWsMaxStages]
+    uint64_t* empty_ev = reinterpret_cast<uint64_t*>(ev_smem + 32);   // [kWsMaxStages]
+    uint64_t* full_win = reinterpret_cast<uint64_t*>(ev_smem + 64);   // [kWsMaxStages]
+    uint64_t* empty_win = reinterpret_cast<uint64_t*>(ev_smem + 96);  // [kWsMaxStages]
+    int2* win_meta = reinterpret_cast<int2*>(ev_smem + 128);          // [kWsMaxStages] (first column, count)
+    long long* s_bounds = reinterpret_cast<long long*>(ev_smem + 160);  // [2]
+    int* s_lut = reinterpret_cast<int*>(ev_smem + kEvSmemHeader);     // [2][kEvChunk]
+    unsigned char* ring = ev_smem + kEvSmemHeader + kEvLutBytes;
+    const int win_bytes = p.cap_cols * p.col_stride * 2;
+    unsigned char* win_ring = ring + p.stages * (kEvChunk * 16);
+
+    FrameState* st = p.state;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const bool producer = warp == kEvThreads / 32;
+
+    // span of this CTA: equal shares, boundaries on multiples of 32 events (512 B)
+    const long long per = ((p.n + gridDim.x - 1) / gridDim.x + 31) & ~31LL;
+    const long long span_lo = per * blockIdx.x < p.n ? per * blockIdx.x : p.n;
+    const long long span_hi = span_lo + per < p.n ? span_lo + per : p.n;
+    const int span_len = static_cast<int>(span_hi - span_lo);
+    const int n_chunks = (span_len + kEvChunk - 1) / kEvChunk;
+    const int4* span_ptr = p.events + span_lo;
+    const unsigned pol_mask = p.polarity ? 0xffffu : 0u;
+
+    if (p.use_pdl) pdl_launch_dependents();
+    if (tid == 0) {
+        for (int s = 0; s < kWsMaxStages; ++s) {
+            mbar_init(full_ev + s, 1);
+            mbar_init(empty_ev + s, kEvThreads / 32);
+            mbar_init(full_win + s, 1);
+            mbar_init(empty_win + s, kEvThreads / 32);
+        }
+    }
+    // t.min() / t.max() of a time-sorted frame are its first / last valid event; every CTA looks them
+    // up itself (two cached 512-byte reads) instead of waiting for a separate kernel
+    if (p.bounds_mode == 0) scan_sorted_bounds(p.events, p.n, p.polarity, warp, lane, s_bounds);
+    __syncthreads();
+    // everything above only reads inputs; below this line the kernel touches the state block and the
+    // scatter map, which the previous frame's epilogue may still be using
+    if (p.use_pdl) pdl_wait();
+
+    long long t_lo, t_hi;
+    if (p.bounds_mode == 0) {
+        t_lo = s_bounds[0];
+        t_hi = s_bounds[1];
+    } else if (p.bounds_mode == 1) {
+        t_lo = p.given_lo;
+        t_hi = p.given_hi;
+    } else {
+        t_lo = st->t_lo_bits;
+        t_hi = st->t_hi_bits;
+    }
+    if (p.bounds_mode != 2 && blockIdx.x == 0 && tid == 0) {  // for xm_frame_status
+        st->t_lo_bits = t_lo;
+        st->t_hi_bits = t_hi;
+    }
+    TimeCol<F64> tc;
+    tc.init(t_lo, t_hi, p.t_px_scale);
+
+    unsigned n_valid = 0, n_inl = 0, flags = 0;
+
+    if (producer) {
+        if (lane == 0) {
+            const uint64_t pol = make_evict_first_policy();
+            int se = 0, sw = 0;
+            unsigned pe = 0, pw = 0;  // parity of the empty barriers' phase to wait for (from the second round on)
+            for (int c = 0; c < n_chunks; ++c) {
+                const int first = c * kEvChunk;
+                const int count = min(kEvChunk, span_len - first);
+                // time stamps of the chunk's first and last record (any polarity) bound its columns
+                long long ta = 0, tb = 0;
+                if (p.cap_cols > 0) {
+                    const int4 a = __ldg(span_ptr + first), b = __ldg(span_ptr + first + count - 1);
+                    ta = (static_cast<long long>(a.w) << 32) | static_cast<unsigned>(a.z);
+                    tb = (static_cast<long long>(b.w) << 32) | static_cast<unsigned>(b.z);
+                }
+                if (c >= p.stages) mbar_wait(empty_ev + se, pe);
+                mbar_expect_tx(full_ev + se, static_cast<unsigned>(count) * 16u);
+                tma_load_1d_hint(ring + se * (kEvChunk * 16), span_ptr + first, static_cast<unsigned>(count) * 16u, full_ev + se, pol);
+                if (++se == p.stages) {
+                    se = 0;
+                    if (c >= p.stages) pe ^= 1u;
+                }
+                if (p.cap_cols > 0) {
+                    bool va, vb;
+                    int ca = tc.column(ta, va), cb = tc.column(tb, vb);
+                    ca = min(max(ca, 0), p.xmap_w - 1);
+                    cb = min(max(cb, 0), p.xmap_w - 1);
+                    const int lo = min(ca, cb);
+                    const int n = min(min(max(ca, cb) - lo + 1, p.cap_cols), p.xmap_w - lo);
+                    if (c >= p.win_stages) mbar_wait(empty_win + sw, pw);
+                    win_meta[sw] = make_int2(lo, n);
+                    const unsigned bytes = static_cast<unsigned>(n) * p.col_stride * 2u;
+                    mbar_expect_tx(full_win + sw, bytes);
+                    tma_load_1d(win_ring + sw * win_bytes, p.xmap_t + static_cast<long long>(lo) * p.col_stride, bytes, full_win + sw);
+                    if (++sw == p.win_stages) {
+                        sw = 0;
+                        if (c >= p.win_stages) pw ^= 1u;
+                    }
+                }
+            }
+        }
+    } else {
+        int fe = 0, bw = 0;        // ring positions of the next front (events) / back (window)
+        unsigned fpe = 0, bpw = 0;  // parities of the full barriers
+        auto front = [&](int c, ChunkRegs& r) {
+            mbar_wait(full_ev + fe, fpe);
+            const int4* stage = reinterpret_cast<const int4*>(ring + fe * (kEvChunk * 16));
+            int* lut_dst = s_lut + (c & 1) * kEvChunk;
+            const int limit = span_len - c * kEvChunk;
+            ColRange range{0xffffffffu, -1};
+            if (limit >= kEvChunk) {
+                if (tc.fast)
+                    front_half<F64, true, true>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, range, n_valid, flags);
+                else
+                    front_half<F64, true, false>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, range, n_valid, flags);
+            } else {
+                if (tc.fast)
+                    front_half<F64, false, true>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, range, n_valid, flags);
+                else
+                    front_half<F64, false, false>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, range, n_valid, flags);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_ev + fe);  // this warp has its events in registers
+            if (++fe == p.stages) {
+                fe = 0;
+                fpe ^= 1u;
+            }
+        };
+        ChunkRegs cur;
+        if (n_chunks > 0) front(0, cur);
+        for (int c = 0; c < n_chunks; ++c) {
+            ChunkRegs nxt;
+            const bool has_next = c + 1 < n_chunks;
+            if (has_next) {
+                front(c + 1, nxt);
+                cp_async_wait<1>();  // the gathers of chunk c have landed; those of chunk c+1 stay in flight
+            } else {
+                cp_async_wait<0>();
+            }
+            int win_lo = 0, win_n = 0;
+            const short* s_win = reinterpret_cast<const short*>(win_ring);
+            if (p.cap_cols > 0) {
+                mbar_wait(full_win + bw, bpw);
+                const int2 meta = win_meta[bw];
+                win_lo = meta.x;
+                win_n = meta.y;
+                s_win = reinterpret_cast<const short*>(win_ring + bw * win_bytes);
+            }
+            const unsigned idx_base = static_cast<unsigned>(span_lo) + static_cast<unsigned>(c * kEvChunk + tid);
+            back_ws<SAFE>(p, cur, s_lut + (c & 1) * kEvChunk, s_win, win_lo, win_n, tid, idx_base, n_inl, flags);
+            if (p.cap_cols > 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_win + bw);
+                if (++bw == p.win_stages) {
+                    bw = 0;
+                    bpw ^= 1u;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kEvPerThread; ++k) {
+                cur.col[k] = nxt.col[k];
+                cur.pix[k] = nxt.pix[k];
+            }
+        }
+    }
+
+    // per-CTA statistics -> one atomic per warp
+    n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+    n_inl = __reduce_add_sync(0xffffffffu, n_inl);
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0) {
+        if (n_valid) atomicAdd(&st->n_valid, static_cast<unsigned long long>(n_valid));
+        if (n_inl) atomicAdd(&st->n_inliers, static_cast<unsigned long long>(n_inl));
+        if (flags) atomicOr(&st->flags, flags);
+    }
+    if (p.arm_fixup) {
+        // last CTA: if any event violated the assumed bounds, launch the exact fix-up (see events_kernel)
+        __shared__ unsigned s_last;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            s_last = (atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last && tid == 0) {
+            __threadfence();
+            unsigned f = *reinterpret_cast<volatile unsigned*>(&st->flags);
+            st->blocks_done = 0;
+            if (f & kStatusTBounds) {
+                st->redo = 1;
+                st->flags = f & ~(kStatusPixelOob | kStatusScatterOob);
+                bounds_reduce_kernel<F64><<<p.fix_reduce_grid, 256, 0, cudaStreamTailLaunch>>>(p.events, p.n, p.polarity, st);
+                EventParams q = p;
+                q.epoch = p.epoch + 1;
+                q.arm_fixup = 0;
+                q.use_pdl = 0;
+                q.bounds_mode = 2;
+                events_ws_kernel<F64, SAFE><<<gridDim.x, kWsThreads, p.smem_bytes, cudaStreamTailLaunch>>>(q);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1, lean variant: the warp-specialised pipeline of events_ws_kernel with the per-event
+// instruction stream cut down for the common case -- integer timestamps (IntCol: no float64 in the
+// hot loop), verified tables (no scatter bound checks), raw shared-memory addresses hoisted out of
+// the loop, validity / inlier bookkeeping as bit masks.  Every exceptional event (outside the assumed
+// time bounds, exact rounding tie, pixel outside the image, column outside the staged window) is
+// flagged in a mask and handled by a slow path that evaluates the reference's own expressions.
+// CAM: camera-view scatter (cell = event pixel) instead of projector view.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <bool CAM>
+__global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventParams p) {
+    extern __shared__ __align__(128) unsigned char ev_smem[];
+    if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 0] = global_timer_ns();
+    uint64_t* full_ev = reinterpret_cast<uint64_t*>(ev_smem);
+    uint64_t* empty_ev = reinterpret_cast<uint64_t*>(ev_smem + 32);
+    uint64_t* full_win = reinterpret_cast<uint64_t*>(ev_smem + 64);
+    uint64_t* empty_win = reinterpret_cast<uint64_t*>(ev_smem + 96);
+    int2* win_meta = reinterpret_cast<int2*>(ev_smem + 128);
+    long long* s_bounds = reinterpret_cast<long long*>(ev_smem + 160);
+    unsigned char* ring = ev_smem + kEvSmemHeader + kEvLutBytes;
+    const int win_bytes = p.cap_cols * p.col_stride * 2;
+    unsigned char* win_ring = ring + p.stages * (kEvChunk * 16);
+
+    FrameState* st = p.state;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const bool producer = warp == kEvThreads / 32;
+
+    const long long per = ((p.n + gridDim.x - 1) / gridDim.x + 31) & ~31LL;
+    const long long span_lo = per * blockIdx.x < p.n ? per * blockIdx.x : p.n;
+    const long long span_hi = span_lo + per < p.n ? span_lo + per : p.n;
+    const int span_len = static_cast<int>(span_hi - span_lo);
+    const int n_chunks = (span_len + kEvChunk - 1) / kEvChunk;
+    const int4* span_ptr = p.events + span_lo;
+    const unsigned pol_mask = p.polarity ? 0xffffu : 0u;
+
+    if (p.use_pdl) pdl_launch_dependents();
+    if (tid == 0) {
+        for (int s = 0; s < kWsMaxStages; ++s) {
+            mbar_init(full_ev + s, 1);
+            mbar_init(empty_ev + s, kEvThreads / 32);
+            mbar_init(full_win + s, 1);
+            mbar_init(empty_win + s, kEvThreads / 32);
+        }
+    }
+    if (p.bounds_mode == 0) scan_sorted_bounds(p.events, p.n, p.polarity, warp, lane, s_bounds);
+    __syncthreads();
+    if (p.use_pdl) pdl_wait();
+
+    long long t_lo, t_hi;
+    if (p.bounds_mode == 0) {
+        t_lo = s_bounds[0];
+        t_hi = s_bounds[1];
+    } else if (p.bounds_mode == 1) {
+        t_lo = p.given_lo;
+        t_hi = p.given_hi;
+    } else {
+        t_lo = st->t_lo_bits;
+        t_hi = st->t_hi_bits;
+    }
+    if (p.bounds_mode != 2 && blockIdx.x == 0 && tid == 0) {
+        st->t_lo_bits = t_lo;
+        st->t_hi_bits = t_hi;
+    }
+    TimeCol<false> tc;  // float64 path: slow cases and the producer's window columns
+    tc.init(t_lo, t_hi, p.t_px_scale);
+    IntCol ic;
+    ic.init(t_lo, t_hi, p.t_px_scale);
+    if (p.dbg && tid == 0) p.dbg[blockIdx.x * 8 + 1] = global_timer_ns();
+
+    unsigned n_valid = 0, n_inl = 0, flags = 0;
+
+    if (producer) {
+        if (lane == 0) {
+            const uint64_t pol = make_evict_first_policy();
+            int se = 0, sw = 0;
+            unsigned pe = 0, pw = 0;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int first = c * kEvChunk;
+                const int count = min(kEvChunk, span_len - first);
+                long long ta = 0, tb = 0;
+                if (p.cap_cols > 0) {
+                    const int4 a = __ldg(span_ptr + first), b = __ldg(span_ptr + first + count - 1);
+                    ta = (static_cast<long long>(a.w) << 32) | static_cast<unsigned>(a.z);
+                    tb = (static_cast<long long>(b.w) << 32) | static_cast<unsigned>(b.z);
+                }
+                if (c >= p.stages) mbar_wait(empty_ev + se, pe);
+                mbar_expect_tx(full_ev + se, static_cast<unsigned>(count) * 16u);
+                tma_load_1d_hint(ring + se * (kEvChunk * 16), span_ptr + first, static_cast<unsigned>(count) * 16u, full_ev + se, pol);
+                if (++se == p.stages) {
+                    se = 0;
+                    if (c >= p.stages) pe ^= 1u;
+                }
+                if (p.cap_cols > 0) {
+                    bool va, vb;
+                    int ca = tc.column(ta, va), cb = tc.column(tb, vb);
+                    ca = min(max(ca, 0), p.xmap_w - 1);
+                    cb = min(max(cb, 0), p.xmap_w - 1);
+                    const int lo = min(ca, cb);
+                    const int n = min(min(max(ca, cb) - lo + 1, p.cap_cols), p.xmap_w - lo);
+                    if (c >= p.win_stages) mbar_wait(empty_win + sw, pw);
+                    win_meta[sw] = make_int2(lo, n);
+                    const unsigned bytes = static_cast<unsigned>(n) * p.col_stride * 2u;
+                    mbar_expect_tx(full_win + sw, bytes);
+                    tma_load_1d(win_ring + sw * win_bytes, p.xmap_t + static_cast<long long>(lo) * p.col_stride, bytes, full_win + sw);
+                    if (++sw == p.win_stages) {
+                        sw = 0;
+                        if (c >= p.win_stages) pw ^= 1u;
+                    }
+                }
+            }
+        }
+    } else {
+        // raw shared addresses, computed once
+        const unsigned sbase = smem_u32(ev_smem);
+        const unsigned a_full_ev = sbase, a_empty_ev = sbase + 32, a_full_win = sbase + 64, a_empty_win = sbase + 96;
+        const unsigned a_meta = sbase + 128;
+        const unsigned a_lut = sbase + kEvSmemHeader + tid * 4;                   // + (c & 1) * 4096 + k * 1024
+        const unsigned a_ring = sbase + kEvSmemHeader + kEvLutBytes + tid * 16;   // + slot * 16384 + k * 4096
+        const unsigned a_win = sbase + kEvSmemHeader + kEvLutBytes + p.stages * (kEvChunk * 16);
+        const unsigned y_lim = static_cast<unsigned>(p.xmap_h - 1);
+        const unsigned cam_w = static_cast<unsigned>(p.cam_w), cam_h = static_cast<unsigned>(p.cam_h);
+        const int col_stride = p.col_stride, x_offset = p.x_offset, rect_w = p.rect_w;
+        const int* const lut_xy = p.lut_xy;
+        unsigned long long* const map = p.map;
+        const unsigned epoch16 = p.epoch << 16;
+        const bool ic_ok = ic.ok;
+
+        int fe = 0, bw = 0;
+        unsigned fpe = 0, bpw = 0;
+
+        // FRONT half of chunk c: events out of the stage, LUT gathers started, columns computed
+        auto front = [&](int c, int (&col)[kEvPerThread], int (&pix)[kEvPerThread]) {
+            mbar_wait_a(a_full_ev + fe * 8, fpe);
+            const unsigned a_stage = a_ring + fe * (kEvChunk * 16);
+            const unsigned a_lut_c = a_lut + (c & 1) * (kEvChunk * 4);
+            const int limit = span_len - c * kEvChunk;
+            int4 raw[kEvPerThread];
+#pragma unroll
+            for (int k = 0; k < kEvPerThread; ++k) raw[k] = lds128_a(a_stage + k * (kEvThreads * 16));
+            unsigned vmask = 0, bad_mask = 0;
+#pragma unroll
+            for (int k = 0; k < kEvPerThread; ++k) {
+                const unsigned ex = static_cast<unsigned>(raw[k].x) & 0xffffu, ey = static_cast<unsigned>(raw[k].x) >> 16;
+                bool valid = ((static_cast<unsigned>(raw[k].y) ^ 1u) & pol_mask) == 0u;  // polarity: p == 1, or everything
+                if (limit < kEvChunk) valid = valid && (k * kEvThreads + tid < limit);
+                const bool ok = valid && ex < cam_w && ey < cam_h;
+                const int px = static_cast<int>(ey * cam_w + ex);
+                if (ok) cp_async_4_a(a_lut_c + k * (kEvThreads * 4), lut_xy + px);
+                const long long t_bits = (static_cast<long long>(raw[k].w) << 32) | static_cast<unsigned>(raw[k].z);
+                bool bad;
+                const unsigned q = ic.column(t_bits, bad);
+                col[k] = ok ? static_cast<int>(q) : -1;
+                if (CAM) pix[k] = px;
+                vmask |= valid ? (1u << k) : 0u;
+                bad_mask |= (valid && (!ok || bad || !ic_ok)) ? (1u << k) : 0u;
+            }
+            cp_async_commit();
+            n_valid += __popc(vmask);
+            if (bad_mask) {  // slow path: the reference's own float64 expression / error flags
+#pragma unroll
+                for (int k = 0; k < kEvPerThread; ++k) {
+                    if (!(bad_mask & (1u << k))) continue;
+                    if (col[k] < 0) {
+                        flags |= kStatusPixelOob;  // the reference raises IndexError here
+                        continue;
+                    }
+                    const long long t_bits = (static_cast<long long>(raw[k].w) << 32) | static_cast<unsigned>(raw[k].z);
+                    bool viol;
+                    int cc = tc.column(t_bits, viol);
+                    if (cc < 0) cc += p.xmap_w;  // NumPy negative index (only reachable with wrong bounds)
+                    viol = viol || cc < 0 || cc >= p.xmap_w;
+                    if (viol) {
+                        flags |= kStatusTBounds;
+                        cc = 0;
+                    }
+                    col[k] = cc;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(a_empty_ev + fe * 8);  // this warp has its events in registers
+            if (++fe == p.stages) {
+                fe = 0;
+                fpe ^= 1u;
+            }
+        };
+
+        int col_cur[kEvPerThread], pix_cur[kEvPerThread];
+        if (n_chunks > 0) front(0, col_cur, pix_cur);
+        if (p.dbg && tid == 0) p.dbg[blockIdx.x * 8 + 2] = global_timer_ns();
+        for (int c = 0; c < n_chunks; ++c) {
+            if (p.dbg && tid == 0 && c == 1) p.dbg[blockIdx.x * 8 + 3] = global_timer_ns();
+            if (p.dbg && tid == 0 && c == n_chunks - 1) p.dbg[blockIdx.x * 8 + 4] = global_timer_ns();
+            int col_nxt[kEvPerThread], pix_nxt[kEvPerThread];
+            const bool has_next = c + 1 < n_chunks;
+            if (has_next) {
+                front(c + 1, col_nxt, pix_nxt);
+                cp_async_wait<1>();  // the gathers of chunk c have landed; those of chunk c+1 stay in flight
+            } else {
+                cp_async_wait<0>();
+            }
+            // ---- BACK half of chunk c ---------------------------------------------------------------
+            int win_lo = 0;
+            unsigned win_n = 0;
+            unsigned a_win_c = a_lut;  // any valid address: without a window every lookup misses
+            if (p.cap_cols > 0) {
+                mbar_wait_a(a_full_win + bw * 8, bpw);
+                win_lo = lds32_a(a_meta + bw * 8);
+                win_n = static_cast<unsigned>(lds32_a(a_meta + bw * 8 + 4));
+                a_win_c = a_win + bw * win_bytes;
+            }
+            const unsigned a_lut_c = a_lut + (c & 1) * (kEvChunk * 4);
+            int lut[kEvPerThread], xp[kEvPerThread];
+#pragma unroll
+            for (int k = 0; k < kEvPerThread; ++k) lut[k] = lds32_a(a_lut_c + k * (kEvThreads * 4));
+            unsigned hit_mask = 0, miss_mask = 0;
+#pragma unroll
+            for (int k = 0; k < kEvPerThread; ++k) {
+                const unsigned ycr = static_cast<unsigned>(lut[k] >> 16);
+                const unsigned rel = static_cast<unsigned>(col_cur[k] - win_lo);  // dropped events (col = -1) wrap to huge
+                const bool y_ok = ycr < y_lim;  // x_maps_disparity.py:23: 0 <= y_rect < H - 1 (last row excluded)
+                const bool hit = y_ok && rel < win_n;
+                xp[k] = lds_s16_a(a_win_c + (hit ? (rel * col_stride + ycr) * 2u : 0u));
+                hit_mask |= hit ? (1u << k) : 0u;
+                miss_mask |= (y_ok && !hit && col_cur[k] >= 0) ? (1u << k) : 0u;
+            }
+            if (miss_mask) {  // column outside the staged window: read the transposed table through L2
+#pragma unroll
+                for (int k = 0; k < kEvPerThread; ++k)
+                    if (miss_mask & (1u << k))
+                        xp[k] = __ldg(p.xmap_t + static_cast<long long>(col_cur[k]) * col_stride + (lut[k] >> 16));
+                hit_mask |= miss_mask;
+            }
+            const unsigned idx0 = static_cast<unsigned>(span_lo) + static_cast<unsigned>(c * kEvChunk + tid);
+            unsigned imask = 0;
+#pragma unroll
+            for (int k = 0; k < kEvPerThread; ++k) {
+                const int xcr = static_cast<short>(lut[k] & 0xffff);
+                const int ycr = lut[k] >> 16;
+                const int disp = static_cast<short>(xp[k] - xcr - x_offset);  // int16 arithmetic wraps
+                const bool inl = ((hit_mask >> k) & 1u) && disp >= 0;
+                // projector view: x_rect + disp = x_map - x_offset, in [0, rect_w) for verified tables
+                const int cell = CAM ? pix_cur[k] : ycr * rect_w + (xp[k] - x_offset);
+                const unsigned idx = idx0 + static_cast<unsigned>(k * kEvThreads);
+                const unsigned long long key =
+                    (static_cast<unsigned long long>(epoch16 | (idx >> 16)) << 32) | ((idx << 16) | static_cast<unsigned>(disp));
+                red_max_u64_if(map + cell, key, inl);
+                imask |= inl ? (1u << k) : 0u;
+            }
+            n_inl += __popc(imask);
+            if (p.cap_cols > 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(a_empty_win + bw * 8);
+                if (++bw == p.win_stages) {
+                    bw = 0;
+                    bpw ^= 1u;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kEvPerThread; ++k) {
+                col_cur[k] = col_nxt[k];
+                if (CAM) pix_cur[k] = pix_nxt[k];
+            }
+        }
+    }
+
+    if (p.dbg && tid == 0) p.dbg[blockIdx.x * 8 + 5] = global_timer_ns();
+    n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+    n_inl = __reduce_add_sync(0xffffffffu, n_inl);
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0) {
+        if (n_valid) atomicAdd(&st->n_valid, static_cast<unsigned long long>(n_valid));
+        if (n_inl) atomicAdd(&st->n_inliers, static_cast<unsigned long long>(n_inl));
+        if (flags) atomicOr(&st->flags, flags);
+    }
+    if (p.arm_fixup) {
+        __shared__ unsigned s_last;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            s_last = (atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (p.dbg && tid == 0) {
+            p.dbg[blockIdx.x * 8 + 6] = global_timer_ns();
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p.dbg[blockIdx.x * 8 + 7] = smid;
+        }
+        if (s_last && tid == 0) {
+            __threadfence();
+            unsigned f = *reinterpret_cast<volatile unsigned*>(&st->flags);
+            st->blocks_done = 0;
+            if (f & kStatusTBounds) {
+                st->redo = 1;
+                st->flags = f & ~(kStatusPixelOob | kStatusScatterOob);
+                bounds_reduce_kernel<false><<<p.fix_reduce_grid, 256, 0, cudaStreamTailLaunch>>>(p.events, p.n, p.polarity, st);
+                EventParams q = p;
+                q.epoch = p.epoch + 1;
+                q.arm_fixup = 0;
+                q.use_pdl = 0;
+                q.bounds_mode = 2;
+                events_lean_kernel<CAM><<<gridDim.x, kWsThreads, p.smem_bytes, cudaStreamTailLaunch>>>(q);
             }
         }
     }
