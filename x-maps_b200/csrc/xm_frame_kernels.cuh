@@ -30,7 +30,7 @@ struct FrameState {
     unsigned int epoch_used;  // (staged path only) epoch of the last scatter
     unsigned int blocks_done; // last-block detection
     unsigned int any_valid;   // reduction saw at least one valid event
-    unsigned int pad;
+    unsigned int next_chunk;  // dynamic chunk scheduler of the lean K1
 };
 
 constexpr unsigned kStatusTBounds = 0x1u;
@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(256) bounds_reduce_kernel(const int4* __restri
         st->blocks_done = 0;
         st->n_valid = 0;
         st->n_inliers = 0;
+        st->next_chunk = 0;
     }
 }
 
@@ -901,8 +902,10 @@ __global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventP
     uint64_t* empty_ev = reinterpret_cast<uint64_t*>(ev_smem + 32);
     uint64_t* full_win = reinterpret_cast<uint64_t*>(ev_smem + 64);
     uint64_t* empty_win = reinterpret_cast<uint64_t*>(ev_smem + 96);
-    int2* win_meta = reinterpret_cast<int2*>(ev_smem + 128);
-    long long* s_bounds = reinterpret_cast<long long*>(ev_smem + 160);
+    int2* win_meta = reinterpret_cast<int2*>(ev_smem + 128);   // [4] (first column, count) of a window stage
+    int* ev_meta = reinterpret_cast<int*>(ev_smem + 160);      // [4] global chunk index of an event stage, -1 = no more work
+    long long* s_bounds = reinterpret_cast<long long*>(ev_smem + 176);
+    uint64_t* bounds_bar = reinterpret_cast<uint64_t*>(ev_smem + 192);
     unsigned char* ring = ev_smem + kEvSmemHeader + kEvLutBytes;
     const int win_bytes = p.cap_cols * p.col_stride * 2;
     unsigned char* win_ring = ring + p.stages * (kEvChunk * 16);
@@ -912,13 +915,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventP
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const bool producer = warp == kEvThreads / 32;
-
-    const long long per = ((p.n + gridDim.x - 1) / gridDim.x + 31) & ~31LL;
-    const long long span_lo = per * blockIdx.x < p.n ? per * blockIdx.x : p.n;
-    const long long span_hi = span_lo + per < p.n ? span_lo + per : p.n;
-    const int span_len = static_cast<int>(span_hi - span_lo);
-    const int n_chunks = (span_len + kEvChunk - 1) / kEvChunk;
-    const int4* span_ptr = p.events + span_lo;
+    const int total_chunks = static_cast<int>((p.n + kEvChunk - 1) / kEvChunk);  // chunks are handed out dynamically
     const unsigned pol_mask = p.polarity ? 0xffffu : 0u;
 
     if (p.use_pdl) pdl_launch_dependents();
@@ -929,9 +926,71 @@ __global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventP
             mbar_init(full_win + s, 1);
             mbar_init(empty_win + s, kEvThreads / 32);
         }
+        mbar_init(bounds_bar, p.bounds_mode == 0 ? 2 : 1);
     }
-    if (p.bounds_mode == 0) scan_sorted_bounds(p.events, p.n, p.polarity, warp, lane, s_bounds);
     __syncthreads();
+
+    unsigned n_valid = 0, n_inl = 0, flags = 0;
+
+    // ---- producer state (lane 0 of the last warp) ---------------------------------------------------
+    int se = 0, sw = 0;
+    unsigned pe = 0, pw = 0;
+    int issued = 0;       // event stages filled so far
+    bool drained = false;  // the global chunk counter ran out
+    const uint64_t pol = make_evict_first_policy();
+    // grabs the next chunk and streams it into the ring; returns its index (-1: none left, sentinel posted)
+    auto produce_events = [&]() -> int {
+        const int g = drained ? total_chunks : static_cast<int>(atomicAdd(&st->next_chunk, 1u));
+        if (issued >= p.stages) mbar_wait(empty_ev + se, pe);
+        int ret = g;
+        if (g >= total_chunks) {
+            drained = true;
+            ev_meta[se] = -1;
+            mbar_arrive(full_ev + se);  // completes the phase: consumers wake up and see the sentinel
+            ret = -1;
+        } else {
+            const long long first = static_cast<long long>(g) * kEvChunk;
+            const unsigned count = static_cast<unsigned>(min(static_cast<long long>(kEvChunk), p.n - first));
+            ev_meta[se] = g;
+            mbar_expect_tx(full_ev + se, count * 16u);
+            tma_load_1d_hint(ring + se * (kEvChunk * 16), p.events + first, count * 16u, full_ev + se, pol);
+        }
+        ++issued;
+        if (++se == p.stages) {
+            se = 0;
+            if (issued > p.stages) pe ^= 1u;
+        }
+        return ret;
+    };
+
+    // Without programmatic launch nothing else is running: start streaming the first chunks before the
+    // time bounds are known (the X-map windows, which need them, follow below).
+    int early[kWsMaxStages];
+    int n_early = 0;
+    if (producer && lane == 0 && !p.use_pdl) {
+        for (; n_early < p.stages; ++n_early) {
+            early[n_early] = produce_events();
+            if (early[n_early] < 0) {
+                ++n_early;
+                break;
+            }
+        }
+    }
+
+    // ---- time bounds ----------------------------------------------------------------------------
+    // t.min() / t.max() of a time-sorted frame are its first / last valid event: warps 0 and 1 look them up
+    if (p.bounds_mode == 0) {
+        if (warp < 2) {
+            scan_sorted_bounds(p.events, p.n, p.polarity, warp, lane, s_bounds);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bounds_bar);
+        }
+    } else if (tid == 0) {
+        mbar_arrive(bounds_bar);
+    }
+    mbar_wait(bounds_bar, 0);
+    // everything above only reads inputs (and, without PDL, this frame's own chunk counter); below the
+    // kernel touches the state block and the scatter map, which the previous frame's epilogue may still use
     if (p.use_pdl) pdl_wait();
 
     long long t_lo, t_hi;
@@ -955,55 +1014,54 @@ __global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventP
     ic.init(t_lo, t_hi, p.t_px_scale);
     if (p.dbg && tid == 0) p.dbg[blockIdx.x * 8 + 1] = global_timer_ns();
 
-    unsigned n_valid = 0, n_inl = 0, flags = 0;
-
     if (producer) {
         if (lane == 0) {
-            const uint64_t pol = make_evict_first_policy();
-            int se = 0, sw = 0;
-            unsigned pe = 0, pw = 0;
-            for (int c = 0; c < n_chunks; ++c) {
-                const int first = c * kEvChunk;
-                const int count = min(kEvChunk, span_len - first);
-                long long ta = 0, tb = 0;
-                if (p.cap_cols > 0) {
-                    const int4 a = __ldg(span_ptr + first), b = __ldg(span_ptr + first + count - 1);
-                    ta = (static_cast<long long>(a.w) << 32) | static_cast<unsigned>(a.z);
-                    tb = (static_cast<long long>(b.w) << 32) | static_cast<unsigned>(b.z);
+            // stages the X-map columns between the columns of the chunk's first and last record
+            auto produce_window = [&](int g) {
+                const long long first = static_cast<long long>(g) * kEvChunk;
+                const long long last = min(p.n, first + kEvChunk) - 1;
+                const int4 a = __ldg(p.events + first), b = __ldg(p.events + last);
+                const long long ta = (static_cast<long long>(a.w) << 32) | static_cast<unsigned>(a.z);
+                const long long tb = (static_cast<long long>(b.w) << 32) | static_cast<unsigned>(b.z);
+                bool va, vb;
+                int ca = tc.column(ta, va), cb = tc.column(tb, vb);
+                ca = min(max(ca, 0), p.xmap_w - 1);
+                cb = min(max(cb, 0), p.xmap_w - 1);
+                const int lo = min(ca, cb);
+                const int n = min(min(max(ca, cb) - lo + 1, p.cap_cols), p.xmap_w - lo);
+                if (g >= 0) {
                 }
-                if (c >= p.stages) mbar_wait(empty_ev + se, pe);
-                mbar_expect_tx(full_ev + se, static_cast<unsigned>(count) * 16u);
-                tma_load_1d_hint(ring + se * (kEvChunk * 16), span_ptr + first, static_cast<unsigned>(count) * 16u, full_ev + se, pol);
-                if (++se == p.stages) {
-                    se = 0;
-                    if (c >= p.stages) pe ^= 1u;
+                mbar_wait(empty_win + sw, pw ^ 1u);  // first round: passes immediately (phase -1 counts as done)
+                win_meta[sw] = make_int2(lo, n);
+                const unsigned bytes = static_cast<unsigned>(n) * p.col_stride * 2u;
+                mbar_expect_tx(full_win + sw, bytes);
+                tma_load_1d(win_ring + sw * win_bytes, p.xmap_t + static_cast<long long>(lo) * p.col_stride, bytes, full_win + sw);
+                if (++sw == p.win_stages) {
+                    sw = 0;
+                    pw ^= 1u;
                 }
-                if (p.cap_cols > 0) {
-                    bool va, vb;
-                    int ca = tc.column(ta, va), cb = tc.column(tb, vb);
-                    ca = min(max(ca, 0), p.xmap_w - 1);
-                    cb = min(max(cb, 0), p.xmap_w - 1);
-                    const int lo = min(ca, cb);
-                    const int n = min(min(max(ca, cb) - lo + 1, p.cap_cols), p.xmap_w - lo);
-                    if (c >= p.win_stages) mbar_wait(empty_win + sw, pw);
-                    win_meta[sw] = make_int2(lo, n);
-                    const unsigned bytes = static_cast<unsigned>(n) * p.col_stride * 2u;
-                    mbar_expect_tx(full_win + sw, bytes);
-                    tma_load_1d(win_ring + sw * win_bytes, p.xmap_t + static_cast<long long>(lo) * p.col_stride, bytes, full_win + sw);
-                    if (++sw == p.win_stages) {
-                        sw = 0;
-                        if (c >= p.win_stages) pw ^= 1u;
-                    }
+            };
+            bool more = true;
+            for (int i = 0; i < n_early; ++i) {
+                if (early[i] < 0) {
+                    more = false;
+                    break;
                 }
+                if (p.cap_cols > 0) produce_window(early[i]);
+            }
+            while (more) {
+                const int g = produce_events();
+                if (g < 0) break;
+                if (p.cap_cols > 0) produce_window(g);
             }
         }
     } else {
         // raw shared addresses, computed once
         const unsigned sbase = smem_u32(ev_smem);
         const unsigned a_full_ev = sbase, a_empty_ev = sbase + 32, a_full_win = sbase + 64, a_empty_win = sbase + 96;
-        const unsigned a_meta = sbase + 128;
-        const unsigned a_lut = sbase + kEvSmemHeader + tid * 4;                   // + (c & 1) * 4096 + k * 1024
-        const unsigned a_ring = sbase + kEvSmemHeader + kEvLutBytes + tid * 16;   // + slot * 16384 + k * 4096
+        const unsigned a_wmeta = sbase + 128, a_emeta = sbase + 160;
+        const unsigned a_lut = sbase + kEvSmemHeader + tid * 4;                  // + parity * 4096 + k * 1024
+        const unsigned a_ring = sbase + kEvSmemHeader + kEvLutBytes + tid * 16;  // + slot * 16384 + k * 4096
         const unsigned a_win = sbase + kEvSmemHeader + kEvLutBytes + p.stages * (kEvChunk * 16);
         const unsigned y_lim = static_cast<unsigned>(p.xmap_h - 1);
         const unsigned cam_w = static_cast<unsigned>(p.cam_w), cam_h = static_cast<unsigned>(p.cam_h);
@@ -1015,13 +1073,19 @@ __global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventP
 
         int fe = 0, bw = 0;
         unsigned fpe = 0, bpw = 0;
+        unsigned fpar = 0;  // LUT double-buffer half the next front half writes
 
-        // FRONT half of chunk c: events out of the stage, LUT gathers started, columns computed
-        auto front = [&](int c, int (&col)[kEvPerThread], int (&pix)[kEvPerThread]) {
+        // FRONT half of the next chunk: events out of the stage, LUT gathers started, columns computed.
+        // Returns the chunk's global index, -1 when the producer has run out of work.
+        auto front = [&](int (&col)[kEvPerThread], int (&pix)[kEvPerThread]) -> int {
             mbar_wait_a(a_full_ev + fe * 8, fpe);
+            const int g = lds32_a(a_emeta + fe * 4);
+            if (g < 0) return -1;
             const unsigned a_stage = a_ring + fe * (kEvChunk * 16);
-            const unsigned a_lut_c = a_lut + (c & 1) * (kEvChunk * 4);
-            const int limit = span_len - c * kEvChunk;
+            const unsigned a_lut_c = a_lut + fpar * (kEvChunk * 4);
+            fpar ^= 1u;
+            const long long left = p.n - static_cast<long long>(g) * kEvChunk;
+            const int limit = left < kEvChunk ? static_cast<int>(left) : kEvChunk;
             int4 raw[kEvPerThread];
 #pragma unroll
             for (int k = 0; k < kEvPerThread; ++k) raw[k] = lds128_a(a_stage + k * (kEvThreads * 16));
@@ -1033,7 +1097,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventP
                 if (limit < kEvChunk) valid = valid && (k * kEvThreads + tid < limit);
                 const bool ok = valid && ex < cam_w && ey < cam_h;
                 const int px = static_cast<int>(ey * cam_w + ex);
-                if (ok) cp_async_4_a(a_lut_c + k * (kEvThreads * 4), lut_xy + px);
+                if (ok) cp_async_4_a(a_lut_c + k * (kEvThreads * 4), lut_xy + ((p.debug & 4) ? (px & 0x3fff) : ((p.debug & 1) ? ((k * kEvThreads + tid) & 0xffff) : px)));
                 const long long t_bits = (static_cast<long long>(raw[k].w) << 32) | static_cast<unsigned>(raw[k].z);
                 bool bad;
                 const unsigned q = ic.column(t_bits, bad);
@@ -1070,33 +1134,35 @@ __global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventP
                 fe = 0;
                 fpe ^= 1u;
             }
+            return g;
         };
 
         int col_cur[kEvPerThread], pix_cur[kEvPerThread];
-        if (n_chunks > 0) front(0, col_cur, pix_cur);
+        int g_cur = front(col_cur, pix_cur);
+        unsigned bpar = 0;  // LUT double-buffer half the next back half reads
         if (p.dbg && tid == 0) p.dbg[blockIdx.x * 8 + 2] = global_timer_ns();
-        for (int c = 0; c < n_chunks; ++c) {
-            if (p.dbg && tid == 0 && c == 1) p.dbg[blockIdx.x * 8 + 3] = global_timer_ns();
-            if (p.dbg && tid == 0 && c == n_chunks - 1) p.dbg[blockIdx.x * 8 + 4] = global_timer_ns();
+        int iter = 0;
+        while (g_cur >= 0) {
+            if (p.dbg && tid == 0 && iter == 1) p.dbg[blockIdx.x * 8 + 3] = global_timer_ns();
+            ++iter;
             int col_nxt[kEvPerThread], pix_nxt[kEvPerThread];
-            const bool has_next = c + 1 < n_chunks;
-            if (has_next) {
-                front(c + 1, col_nxt, pix_nxt);
-                cp_async_wait<1>();  // the gathers of chunk c have landed; those of chunk c+1 stay in flight
-            } else {
+            const int g_nxt = front(col_nxt, pix_nxt);
+            if (g_nxt >= 0)
+                cp_async_wait<1>();  // the gathers of the current chunk have landed; the next chunk's stay in flight
+            else
                 cp_async_wait<0>();
-            }
-            // ---- BACK half of chunk c ---------------------------------------------------------------
+            // ---- BACK half of the current chunk ----------------------------------------------------------
             int win_lo = 0;
             unsigned win_n = 0;
             unsigned a_win_c = a_lut;  // any valid address: without a window every lookup misses
             if (p.cap_cols > 0) {
                 mbar_wait_a(a_full_win + bw * 8, bpw);
-                win_lo = lds32_a(a_meta + bw * 8);
-                win_n = static_cast<unsigned>(lds32_a(a_meta + bw * 8 + 4));
+                win_lo = lds32_a(a_wmeta + bw * 8);
+                win_n = static_cast<unsigned>(lds32_a(a_wmeta + bw * 8 + 4));
                 a_win_c = a_win + bw * win_bytes;
             }
-            const unsigned a_lut_c = a_lut + (c & 1) * (kEvChunk * 4);
+            const unsigned a_lut_c = a_lut + bpar * (kEvChunk * 4);
+            bpar ^= 1u;
             int lut[kEvPerThread], xp[kEvPerThread];
 #pragma unroll
             for (int k = 0; k < kEvPerThread; ++k) lut[k] = lds32_a(a_lut_c + k * (kEvThreads * 4));
@@ -1118,7 +1184,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventP
                         xp[k] = __ldg(p.xmap_t + static_cast<long long>(col_cur[k]) * col_stride + (lut[k] >> 16));
                 hit_mask |= miss_mask;
             }
-            const unsigned idx0 = static_cast<unsigned>(span_lo) + static_cast<unsigned>(c * kEvChunk + tid);
+            const unsigned idx0 = static_cast<unsigned>(g_cur) * kEvChunk + static_cast<unsigned>(tid);
             unsigned imask = 0;
 #pragma unroll
             for (int k = 0; k < kEvPerThread; ++k) {
@@ -1131,7 +1197,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventP
                 const unsigned idx = idx0 + static_cast<unsigned>(k * kEvThreads);
                 const unsigned long long key =
                     (static_cast<unsigned long long>(epoch16 | (idx >> 16)) << 32) | ((idx << 16) | static_cast<unsigned>(disp));
-                red_max_u64_if(map + cell, key, inl);
+                red_max_u64_if(map + ((p.debug & 2) ? static_cast<int>(idx & 0xfffffu) : cell), key, inl);
                 imask |= inl ? (1u << k) : 0u;
             }
             n_inl += __popc(imask);
@@ -1148,6 +1214,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventP
                 col_cur[k] = col_nxt[k];
                 if (CAM) pix_cur[k] = pix_nxt[k];
             }
+            g_cur = g_nxt;
         }
     }
 
