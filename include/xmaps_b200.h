@@ -138,7 +138,9 @@ int xm_ctx_set_colormap(XmCtx* ctx, const uint8_t* h_bgr256);
  *   "stages"          depth of K1's shared-memory event ring (16 KB per stage, TMA-filled)      [2]
   *   "safe_tables"     0/1  allow the check-free scatter of K1 when the tables were verified at upload
  *                     (every defined X-map cell in [x_offset, x_offset + rect_w), LUT x > -x_offset) [1]
-   *   "pdl"             1: programmatic dependent launch between K1 / K2 / the next frame's K1 (used only
+    *   "fused"           1: one fused kernel per frame (events + grid barrier + epilogue) where the lean path
+ *                     applies (integer time, verified tables, 7x7 dilate); 0: separate K1 / K2 kernels [1]
+ *   "pdl"             1: programmatic dependent launch between K1 / K2 / the next frame's K1 (used only
  *                     when "auto_fixup" is 0 or the bounds are exact: it cannot be combined with the
  *                     device-side fix-up launch)                                             [1]
  *   "k2_variant"      1: sliding-window projector epilogue (7x7 dilate, even rect_w), 0: per-tap [1]
@@ -146,7 +148,7 @@ int xm_ctx_set_colormap(XmCtx* ctx, const uint8_t* h_bgr256);
  *   "auto_fixup"      0/1  with XM_TBOUNDS_SORTED / _GIVEN: when an event lies outside the assumed
  *                     bounds, redo the frame on the device with exact (reduced) bounds         [1]
  *   "ctas_per_sm"     resident CTAs per SM for the event kernel, 0 = occupancy query            [0]
- *   "region_cells"    shared-memory cells per buffer of the projector-view epilogue             [4096]
+ *   "region_cells"    shared-memory cells per buffer of the projector-view epilogue             [3072]
  *   "profile"         1 / 0: record CUDA events around K1 (per-event kernel) and K2 (per-pixel
  *                     epilogue) of every frame; -1 resets the accumulators.  Read back with
  *                     "profile_k1_ns", "profile_k2_ns", "profile_frames" (these synchronise)

@@ -24,9 +24,11 @@ a = buf.cpu().numpy().reshape(4096, 8)
 a = a[a[:, 0] > 0]
 t0 = a[:, 0].min()
 rel = (a[:, :7] - t0) / 1e3
-names = ["entry", "prologue done", "front(0) done", "loop c=1", "loop last", "loop end", "after last-block sync"]
+names = ["entry", "prologue done", "front(0) done", "loop c=1", "kernel end (fused)", "phase 1 end", "after grid barrier"]
 print("CTAs:", len(a), " SMs:", len(np.unique(a[:, 7])))
 for i, n in enumerate(names):
     col = rel[:, i]
     print(f"{n:24s} min {col.min():7.2f}  p50 {np.median(col):7.2f}  max {col.max():7.2f} us")
-print("per-CTA loop duration (c=1 -> last): p50 %.2f  max %.2f us" % (np.median(rel[:, 4] - rel[:, 3]), (rel[:, 4] - rel[:, 3]).max()))
+print("phase 2 per CTA (barrier -> end): p50 %.2f  max %.2f us" % (np.median(rel[:, 4] - rel[:, 6]), (rel[:, 4] - rel[:, 6]).max()))
+print("raw row 0:", a[0].tolist())
+print("raw row 5:", a[5].tolist())

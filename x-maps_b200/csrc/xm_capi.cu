@@ -15,6 +15,7 @@
 
 #include "../../include/xmaps_b200.h"
 #include "xm_stage_kernels.cuh"
+#include "xm_fused_kernel.cuh"
 
 namespace {
 
@@ -100,6 +101,8 @@ struct XmCtx {
     int opt_ctas_per_sm = 0;  // 0 = occupancy query
     int opt_smem_cols_bytes = 12 * 1024;
     int opt_k2_variant = 1;   // 1: sliding-window epilogue (7x7, even rect_w), 0: per-tap epilogue
+    int opt_fused = 1;        // 1: one fused kernel per frame where the lean path applies
+    int fused_occ = 0;        // resident CTAs per SM of frame_kernel
     int opt_pdl = 1;          // programmatic dependent launch between K1 / K2 / next K1
     int opt_safe_tables = 1;  // use the check-free scatter when the tables were verified
     int opt_stages = 2;  // depth of the shared-memory event ring of K1
@@ -107,7 +110,7 @@ struct XmCtx {
     int opt_win_stages = 2;   // depth of the X-map window ring (warp-specialised K1)
     int opt_k1_variant = 2;   // 2: lean warp-specialised K1 (integer time, verified tables; else falls back to 1),
                               // 1: warp-specialised K1 (mbarrier pipelines), 0: block-barrier K1
-    int opt_region_cells = 64 * 64;
+    int opt_region_cells = 48 * 64;
     // per-kernel CUDA-event timing (option "profile"): pairs around K1 and K2 of every frame
     int opt_profile = 0;
     std::vector<cudaEvent_t> prof_events;  // 3 per frame: before K1, after K1 (+ fix-up), after K2
@@ -220,6 +223,25 @@ int configure_event_kernels(XmCtx* c) {
             dst = occ < dst ? occ : dst;
         }
     if (c->ev_occ_i64 < 1 || c->ev_occ_f64 < 1) return fail(XM_ERR_UNSUPPORTED, "event kernel does not fit an SM (smem %d B)", c->ev_smem);
+    c->fused_occ = 0;
+    if (variant == 2) {
+        int occ_min = 1 << 30;
+        for (int cam = 0; cam < 2; ++cam) {
+            void (*k)(xm::FrameParams) = cam ? xm::frame_kernel<true> : xm::frame_kernel<false>;
+            cudaFuncAttributes fa;
+            XM_CUDA(cudaFuncGetAttributes(&fa, k));
+            const int dyn = optin - static_cast<int>(fa.sharedSizeBytes);
+            if (c->ev_smem > dyn) {
+                occ_min = 0;
+                break;
+            }
+            XM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+            int occ = 0;
+            XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, xm::kWsThreads, c->ev_smem));
+            occ_min = occ < occ_min ? occ : occ_min;
+        }
+        c->fused_occ = occ_min;
+    }
     return XM_OK;
 }
 
@@ -400,6 +422,59 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     p.arm_fixup = fixup ? 1 : 0;
     p.fix_reduce_grid = grid_for(a->n_events, 256, 8, c->sm_count * 8);
     p.smem_bytes = c->ev_smem;
+
+    // ---- one fused kernel per frame (lean path) -----------------------------------------------------
+    const bool tables_safe = c->lut_safe && c->xmap_safe && c->opt_safe_tables;
+    const bool fused = c->opt_fused && c->opt_k1_variant == 2 && c->fused_occ > 0 && !f64 && tables_safe &&
+                       a->time_bounds != XM_TBOUNDS_REDUCE &&
+                       (a->view == XM_VIEW_CAMERA || (c->dilate == 7 && !(c->rect_w & 1))) &&
+                       static_cast<size_t>(c->opt_region_cells) * 4 * (xm::kEvThreads / xm::kTileGroup) + xm::kEvSmemHeader <=
+                           static_cast<size_t>(c->ev_smem);
+    if (fused) {
+        xm::FrameParams fp;
+        fp.ev = p;
+        fp.ev.use_pdl = c->opt_pdl ? 1 : 0;  // no device-side launch in this kernel: PDL is always possible
+        fp.ev.arm_fixup = fixup ? 1 : 0;
+        xm::EpilogueParams& q = fp.ep;
+        q.map = c->d_map;
+        q.state = st;
+        q.epoch = epoch;
+        q.use_pdl = 0;
+        const int rslot = (slot + 2) % kStateSlots;
+        q.recycle = c->d_state + rslot;
+        c->slot_dirty[rslot] = false;
+        c->slot_dirty[slot] = true;
+        q.remap_xy = c->d_remap_xy;
+        q.tile_box = c->d_tile_box;
+        q.rect_w = c->rect_w;
+        q.rect_h = c->rect_h;
+        q.radius = c->dilate / 2;
+        q.region_cap = c->opt_region_cells;
+        q.out = make_output(c, a->output, c->depth_scale, a->z_near, a->z_far);
+        q.dst = a->d_out;
+        q.out_w = a->view == XM_VIEW_CAMERA ? c->cam_w : c->proj_w;
+        q.out_h = a->view == XM_VIEW_CAMERA ? c->cam_h : c->proj_h;
+        fp.tiles_x = (c->proj_w + xm::kTile - 1) / xm::kTile;
+        fp.tiles_y = (c->proj_h + xm::kTile - 1) / xm::kTile;
+        // all CTAs must be co-resident (grid-wide barrier inside): never more than occupancy x SMs
+        const int occ = c->opt_ctas_per_sm > 0 && c->opt_ctas_per_sm < c->fused_occ ? c->opt_ctas_per_sm : c->fused_occ;
+        const int grid = c->sm_count * occ;
+        if (c->opt_profile) {
+            rc = profile_mark(c, s);
+            if (rc) return rc;
+        }
+        void (*k)(xm::FrameParams) = a->view == XM_VIEW_CAMERA ? xm::frame_kernel<true> : xm::frame_kernel<false>;
+        XM_CUDA(launch_pdl(k, dim3(grid), dim3(xm::kWsThreads), c->ev_smem, s, c->opt_pdl && c->prev_was_frame, fp));
+        XM_LAUNCHED();
+        c->prev_was_frame = true;
+        if (c->opt_profile) {
+            rc = profile_mark(c, s);
+            if (rc) return rc;
+            rc = profile_mark(c, s);
+            if (rc) return rc;
+        }
+        return XM_OK;
+    }
 
     if (c->opt_profile) {
         rc = profile_mark(c, s);
@@ -667,6 +742,10 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         c->opt_k2_variant = v != 0;
         return XM_OK;
     }
+    if (!strcmp(key, "fused")) {
+        c->opt_fused = v != 0;
+        return XM_OK;
+    }
     if (!strcmp(key, "pdl")) {
         c->opt_pdl = v != 0;
         return XM_OK;
@@ -724,6 +803,7 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     else if (!strcmp(key, "win_stages")) *value = c->opt_win_stages;
     else if (!strcmp(key, "k1_variant")) *value = c->opt_k1_variant;
     else if (!strcmp(key, "pdl")) *value = c->opt_pdl;
+    else if (!strcmp(key, "fused")) *value = c->opt_fused;
     else if (!strcmp(key, "k2_variant")) *value = c->opt_k2_variant;
     else if (!strcmp(key, "safe_tables")) *value = c->opt_safe_tables && c->lut_safe && c->xmap_safe;
     else if (!strcmp(key, "auto_fixup")) *value = c->opt_auto_fixup;

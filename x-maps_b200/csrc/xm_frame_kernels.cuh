@@ -31,6 +31,8 @@ struct FrameState {
     unsigned int blocks_done; // last-block detection
     unsigned int any_valid;   // reduction saw at least one valid event
     unsigned int next_chunk;  // dynamic chunk scheduler of the lean K1
+    unsigned int next_tile;   // fused kernel: epilogue tile scheduler
+    unsigned int fix_chunk;   // fused kernel: chunk scheduler of the fix-up pass
 };
 
 constexpr unsigned kStatusTBounds = 0x1u;
@@ -895,8 +897,8 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 
 template <bool CAM>
-__global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventParams p) {
-    extern __shared__ __align__(128) unsigned char ev_smem[];
+__device__ __forceinline__ void lean_events_phase(const EventParams& p, unsigned char* ev_smem, unsigned& n_valid, unsigned& n_inl,
+                                                  unsigned& flags) {
     if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 0] = global_timer_ns();
     uint64_t* full_ev = reinterpret_cast<uint64_t*>(ev_smem);
     uint64_t* empty_ev = reinterpret_cast<uint64_t*>(ev_smem + 32);
@@ -929,8 +931,6 @@ __global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventP
         mbar_init(bounds_bar, p.bounds_mode == 0 ? 2 : 1);
     }
     __syncthreads();
-
-    unsigned n_valid = 0, n_inl = 0, flags = 0;
 
     // ---- producer state (lane 0 of the last warp) ---------------------------------------------------
     int se = 0, sw = 0;
@@ -1218,6 +1218,16 @@ __global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventP
         }
     }
 
+}
+
+template <bool CAM>
+__global__ void __launch_bounds__(kWsThreads, 3) events_lean_kernel(const EventParams p) {
+    extern __shared__ __align__(128) unsigned char ev_smem[];
+    FrameState* st = p.state;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    unsigned n_valid = 0, n_inl = 0, flags = 0;
+    lean_events_phase<CAM>(p, ev_smem, n_valid, n_inl, flags);
     if (p.dbg && tid == 0) p.dbg[blockIdx.x * 8 + 5] = global_timer_ns();
     n_valid = __reduce_add_sync(0xffffffffu, n_valid);
     n_inl = __reduce_add_sync(0xffffffffu, n_inl);
@@ -1440,35 +1450,38 @@ constexpr int kRowExtra = 16;  // total padding per row (4 left + 12 right)
 
 __device__ __forceinline__ unsigned magic_div(int d) { return 0xffffffffu / static_cast<unsigned>(d) + 1u; }
 
-__global__ void __launch_bounds__(256, 7) epilogue_projector7_kernel(const EpilogueParams p) {
-    extern __shared__ __align__(128) unsigned char ev_smem[];
-    unsigned short* bufA = reinterpret_cast<unsigned short*>(ev_smem);
-    unsigned short* bufB = bufA + p.region_cap;
+// One 32x32 output tile, processed by a group of NT threads (NT = 64, 128 or 256; `gtid` = index inside
+// the group) that synchronises on the named barrier `bar_id`: several groups of one CTA can work on
+// different tiles at the same time, which is what hides the L2 latency of the region loads.
+template <int NT>
+__device__ __forceinline__ void group_sync(int bar_id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT) : "memory");
+}
+
+template <int NT>
+__device__ __forceinline__ void proj7_tile(const EpilogueParams& p, int bx, int by, int tiles_x, unsigned epoch, unsigned short* bufA,
+                                           unsigned short* bufB, int gtid, int bar_id) {
     constexpr int R = 3;
+    constexpr int PX = kTile * kTile / NT;  // output pixels per thread
+    constexpr int ROWS = NT / 32;           // tile rows covered by one pass of the group
+    const int tid = gtid;
+    const int lane = gtid & 31, warp = gtid >> 5;
+    const int u0 = bx * kTile, v0 = by * kTile;
 
-    if (p.use_pdl) pdl_launch_dependents();
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int u0 = blockIdx.x * kTile, v0 = blockIdx.y * kTile;
-
-    const short4 box = __ldg(p.tile_box + blockIdx.y * gridDim.x + blockIdx.x);
+    const short4 box = __ldg(p.tile_box + by * tiles_x + bx);
     const int x0 = box.x, y0 = box.y, x1 = box.z, y1 = box.w;
-    if (p.out.kind == 0 && p.out.depth_lut && tid < 128) prefetch_l1(p.out.depth_lut + tid * 32);
 
-    short2 m[4];
+    short2 m[PX];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int u = u0 + lane, v = v0 + warp + k * 8;
+    for (int k = 0; k < PX; ++k) {
+        const int u = u0 + lane, v = v0 + warp + k * ROWS;
         m[k] = make_short2(-1, -1);
         if (u < p.out_w && v < p.out_h) m[k] = __ldg(p.remap_xy + v * p.out_w + u);
     }
 
-    // up to here only calibration tables were read; the key map and the state block belong to K1
-    if (p.use_pdl) pdl_wait();
-    const unsigned epoch = p.epoch + p.state->redo;
-    if (p.recycle && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) recycle_state(p.recycle);
-
-    int val[4] = {0, 0, 0, 0};
+    int val[PX];
+#pragma unroll
+    for (int k = 0; k < PX; ++k) val[k] = 0;
     if (x1 >= 0) {
         const int rx0 = (x0 - R) & ~1;                 // even
         const int rw = (x1 + R - rx0 + 2) & ~1;        // even number of data cells
@@ -1480,7 +1493,7 @@ __global__ void __launch_bounds__(256, 7) epilogue_projector7_kernel(const Epilo
                 const int pairs = stride >> 1;
                 const unsigned mg = magic_div(pairs);
                 unsigned* dst = reinterpret_cast<unsigned*>(bufA);
-                for (int c = tid; c < pairs * rh; c += 256) {
+                for (int c = tid; c < pairs * rh; c += NT) {
                     const int ry = static_cast<int>(__umulhi(static_cast<unsigned>(c), mg));
                     const int cx = 2 * (c - ry * pairs) - kRowPad;  // data coordinate of the pair's first cell (even)
                     const int gx = rx0 + cx, gy = ry0 + ry;
@@ -1492,12 +1505,12 @@ __global__ void __launch_bounds__(256, 7) epilogue_projector7_kernel(const Epilo
                     dst[c] = packed;
                 }
             }
-            __syncthreads();
+            group_sync<NT>(bar_id);
             // ---- B: horizontal 7-max, 8 outputs per task ------------------------------------------
             {
                 const int segs = (rw + 7) >> 3;
                 const unsigned mg = magic_div(segs);
-                for (int t = tid; t < segs * rh; t += 256) {
+                for (int t = tid; t < segs * rh; t += NT) {
                     const int ry = static_cast<int>(__umulhi(static_cast<unsigned>(t), mg));
                     const int seg = t - ry * segs;
                     const unsigned* src = reinterpret_cast<const unsigned*>(bufA + ry * stride) + 4 * seg;
@@ -1523,14 +1536,14 @@ __global__ void __launch_bounds__(256, 7) epilogue_projector7_kernel(const Epilo
                     }
                 }
             }
-            __syncthreads();
+            group_sync<NT>(bar_id);
             // ---- C: vertical 7-max on column pairs, 8 output rows per task -----------------------------
             {
                 const int orows = rh - 2 * R;  // rows a pixel of this tile can map to: [R, rh - R)
                 const int vsegs = (orows + 7) >> 3;
                 const int cpairs = rw >> 1;
                 const unsigned mg = magic_div(cpairs);
-                for (int t = tid; t < vsegs * cpairs; t += 256) {
+                for (int t = tid; t < vsegs * cpairs; t += NT) {
                     const int vs = static_cast<int>(__umulhi(static_cast<unsigned>(t), mg));
                     const int q = t - vs * cpairs;
                     const int word = (kRowPad >> 1) + q;  // word index of the pair inside a row
@@ -1553,15 +1566,15 @@ __global__ void __launch_bounds__(256, 7) epilogue_projector7_kernel(const Epilo
                     }
                 }
             }
-            __syncthreads();
+            group_sync<NT>(bar_id);
             // ---- D: gather ----------------------------------------------------------------------------
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < PX; ++k)
                 if (m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h)
                     val[k] = bufA[(m[k].y - ry0) * stride + (m[k].x - rx0) + kRowPad];
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < PX; ++k) {
                 if (!(m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h)) continue;
                 int best = 0;
                 for (int dy = -R; dy <= R; ++dy) {
@@ -1578,10 +1591,24 @@ __global__ void __launch_bounds__(256, 7) epilogue_projector7_kernel(const Epilo
         }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int u = u0 + lane, v = v0 + warp + k * 8;
+    for (int k = 0; k < PX; ++k) {
+        const int u = u0 + lane, v = v0 + warp + k * ROWS;
         if (u < p.out_w && v < p.out_h) emit_pixel_int(p.out, p.dst, v * p.out_w + u, val[k]);
     }
+}
+
+__global__ void __launch_bounds__(256, 7) epilogue_projector7_kernel(const EpilogueParams p) {
+    extern __shared__ __align__(128) unsigned char ev_smem[];
+    unsigned short* bufA = reinterpret_cast<unsigned short*>(ev_smem);
+    unsigned short* bufB = bufA + p.region_cap;
+    if (p.use_pdl) pdl_launch_dependents();
+    const int tid = threadIdx.x;
+    if (p.out.kind == 0 && p.out.depth_lut && tid < 128) prefetch_l1(p.out.depth_lut + tid * 32);
+    // the key map and the state block belong to K1
+    if (p.use_pdl) pdl_wait();
+    const unsigned epoch = p.epoch + p.state->redo;
+    if (p.recycle && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) recycle_state(p.recycle);
+    proj7_tile<256>(p, blockIdx.x, blockIdx.y, gridDim.x, epoch, bufA, bufB, tid, 0);
 }
 
 }  // namespace xm
