@@ -346,10 +346,16 @@ def run_ours(args):
     lut_bytes = CAM_W * CAM_H * 4
     xmap_bytes = tables.x_map.size * 2
     k1_bytes = 16 * n + lut_bytes + xmap_bytes
+    kernel_name = "xm::events_lean_kernel (K1: polarity + rectify LUT + X-map lookup + disparity + scatter)"
+    fused = bool(eng.get_option("fused")) and eng.get_option("k1_variant") == 2 and k2_us < 0.5
+    if fused:
+        # one kernel per frame: K1's bytes + the remap table read + the depth frame written (B(N_in))
+        k1_bytes += PROJ_W * PROJ_H * 4 * 2
+        kernel_name = "xm::frame_kernel (whole frame: per-event phase + grid barrier + dilate/remap/depth epilogue)"
     achieved = k1_bytes / (k1_us * 1e-6) / 1e9 if k1_us > 0 else 0.0
     roofline = {
         "bound": "hbm",
-        "kernel": "xm::events_kernel (K1: polarity + rectify LUT + X-map lookup + disparity + scatter)",
+        "kernel": kernel_name,
         "achieved": achieved,
         "peak": peak,
         "peak_source": peak_src,
@@ -361,7 +367,7 @@ def run_ours(args):
         "k2_us_per_launch": k2_us,
         "frame_us": ms * 1e3 / (F * args.steps),
     }
-    traffic_file = os.path.join(ROOT, "profiles", "k1_dram_bytes.json")
+    traffic_file = os.path.join(ROOT, "profiles", "frame_dram_bytes.json" if fused else "k1_dram_bytes.json")
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as fh:

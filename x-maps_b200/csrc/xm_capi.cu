@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -662,6 +663,25 @@ int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
         if (rc) return bail(rc);
     }
     *out = c;
+    // XMAPS_B200_OPTS="key=value,key=value": option overrides for every new context (tuning / A-B runs)
+    if (const char* env = getenv("XMAPS_B200_OPTS")) {
+        std::string e(env);
+        size_t pos = 0;
+        while (pos < e.size()) {
+            size_t end = e.find(',', pos);
+            if (end == std::string::npos) end = e.size();
+            const std::string kv = e.substr(pos, end - pos);
+            const size_t eq = kv.find('=');
+            if (eq != std::string::npos) {
+                rc = xm_ctx_set_option(c, kv.substr(0, eq).c_str(), atoll(kv.c_str() + eq + 1));
+                if (rc) {
+                    *out = nullptr;
+                    return bail(rc);
+                }
+            }
+            pos = end + 1;
+        }
+    }
     return XM_OK;
 }
 
