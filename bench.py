@@ -288,7 +288,8 @@ def run_ours(args):
     def render(fr, dst):
         eng.frame_batch(fr, view=VIEW_PROJECTOR, output=OUT_DEPTH, out=dst)
 
-    sharder = FrameSharder(render, rank, world, dst=0, chunk=args.gather_chunk)
+    chunk = args.gather_chunk if args.gather_chunk > 0 else (32 if world == 1 or args.no_gather else 16)
+    sharder = FrameSharder(render, rank, world, dst=0, chunk=chunk)
 
     def step():
         sharder.run(frames, out, gathered, gather=(world > 1 and not args.no_gather))
@@ -327,7 +328,8 @@ def run_ours(args):
     eng.set_option("profile", 1)
     torch.cuda.synchronize(device)
     for _ in range(args.steps):
-        render(frames, out)
+        for lo in range(0, F, chunk):
+            render(frames[lo:lo + chunk], out[lo:lo + chunk])
     torch.cuda.synchronize(device)
     k1_ns, k2_ns, pf = eng.get_option("profile_k1_ns"), eng.get_option("profile_k2_ns"), eng.get_option("profile_frames")
     eng.set_option("profile", 0)
@@ -454,7 +456,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--events", type=int, default=EVENTS_PER_FRAME)
     ap.add_argument("--frames", type=int, default=64, help="distinct frames per step per GPU")
-    ap.add_argument("--gather-chunk", type=int, default=8)
+    ap.add_argument("--gather-chunk", type=int, default=0, help="frames per render call (one persistent kernel each); 0 = 32 on one GPU, 16 with the NCCL gather")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--cpu-runs", type=int, default=5)
     ap.add_argument("--e2e-frames", type=int, default=16)

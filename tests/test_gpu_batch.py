@@ -1,0 +1,185 @@
+"""The batched persistent kernel (xm_frame_batch -> batch_kernel): every frame of a batch must be
+bit-identical to the oracle, whatever the mix of frame sizes, and unsorted frames inside a batch must be
+re-rendered exactly on the device."""
+import numpy as np
+import pytest
+
+from oracle import xmaps_oracle as orc
+from test_gpu_parity import E, make_engine
+from xm_helpers import golden_frame, load_golden_tables
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def small():
+    tables, z = load_golden_tables("small")
+    eng = make_engine(tables, z)
+    eng.set_option("batch", 1)  # opt-in (the fused per-frame kernels are the default, see EXPERIMENTS_r01.md)
+    assert eng.get_option("batch") == 1 and eng.get_option("batch_occ") >= 1
+    yield tables, z, eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def default():
+    tables, z = load_golden_tables("default")
+    eng = make_engine(tables)
+    eng.set_option("batch", 1)
+    yield tables, z, eng
+    eng.close()
+
+
+def want_frames(tables, frames, view):
+    return [orc.frame_depth(tables, f, view) for f in frames]
+
+
+SIZES = [20_000, 0, 1, 1023, 1024, 1025, 70_001, 5, 0, 33_000, 4097, 64]
+
+
+@pytest.mark.parametrize("view", [0, 1])
+def test_mixed_sizes_match_oracle(small, view):
+    tables, _, eng = small
+    frames = [orc.synth_events(300 + i, n, 160, 120) for i, n in enumerate(SIZES)]
+    launches0 = eng.launch_count()
+    out = eng.frame_batch(frames, view=view).cpu().numpy()
+    assert eng.launch_count() - launches0 == 3  # bounds + batch + redo scan: the batch kernel really ran
+    for i, w in enumerate(want_frames(tables, frames, view)):
+        assert np.array_equal(out[i], w), f"frame {i} ({SIZES[i]} events)"
+    st = eng.status()  # the last frame of the batch
+    ev = frames[-1]
+    assert st["n_valid"] == int((ev["p"] == 1).sum())
+    assert not st["fixup_ran"] and not st["tbounds_violated"]
+
+
+def test_outputs_disparity_and_bgr(small):
+    tables, _, eng = small
+    e = E()
+    frames = [orc.synth_events(2, 20_000, 160, 120), orc.synth_events(9, 3_000, 160, 120)]
+    g = golden_frame("small_20k_proj")
+    bgr = eng.frame_batch(frames, view=0, output=e.OUT_BGR).cpu().numpy()
+    assert np.array_equal(bgr[0], g["bgr"])
+    disp = eng.frame_batch(frames, view=0, output=e.OUT_DISPARITY).cpu().numpy()
+    for i, f in enumerate(frames):
+        assert np.array_equal(disp[i], orc.frame_disparity_map(tables, f, 0))
+    single = eng.frame(frames[1], view=0, output=e.OUT_BGR).cpu().numpy()
+    assert np.array_equal(bgr[1], single)
+
+
+@pytest.mark.parametrize("n_frames", [33, 40, 65])
+def test_more_frames_than_one_launch(small, n_frames):
+    tables, _, eng = small
+    base = [orc.synth_events(500 + i, 2_000 + 37 * i, 160, 120) for i in range(8)]
+    want = want_frames(tables, base, 0)
+    frames = [base[i % 8] for i in range(n_frames)]
+    out = eng.frame_batch(frames, view=0).cpu().numpy()
+    for i in range(n_frames):
+        assert np.array_equal(out[i], want[i % 8]), f"frame {i}"
+
+
+def test_unsorted_frames_inside_a_batch(small):
+    tables, _, eng = small
+    e = E()
+    frames = [orc.synth_events(600 + i, 15_000, 160, 120) for i in range(6)]
+    for i in (1, 4, 5):
+        np.random.default_rng(i).shuffle(frames[i])
+    for view in (0, 1):
+        out = eng.frame_batch(frames, view=view, time_bounds=e.TBOUNDS_SORTED).cpu().numpy()
+        st = eng.status()
+        assert st["fixup_ran"] and st["tbounds_violated"]  # frame 5 is the last one
+        for i, w in enumerate(want_frames(tables, frames, view)):
+            assert np.array_equal(out[i], w), f"view {view} frame {i}"
+        assert st["n_valid"] == int((frames[5]["p"] == 1).sum())
+    # a clean batch right afterwards is unaffected, and reports no fix-up
+    clean = [orc.synth_events(700 + i, 9_000, 160, 120) for i in range(3)]
+    out = eng.frame_batch(clean, view=0).cpu().numpy()
+    assert not eng.status()["fixup_ran"]
+    for i, w in enumerate(want_frames(tables, clean, 0)):
+        assert np.array_equal(out[i], w)
+
+
+def test_given_bounds(small):
+    tables, _, eng = small
+    e = E()
+    frames = [orc.synth_events(800 + i, 12_000, 160, 120) for i in range(4)]
+    good = []
+    for f in frames:
+        t = f["t"][f["p"] == 1]
+        good.append((int(t.min()), int(t.max())))
+    want = want_frames(tables, frames, 1)
+    out = eng.frame_batch(frames, view=1, time_bounds=e.TBOUNDS_GIVEN, t_bounds=good).cpu().numpy()
+    assert not eng.status()["fixup_ran"]
+    for i in range(4):
+        assert np.array_equal(out[i], want[i])
+    bad = list(good)
+    bad[2] = (100, 5000)
+    bad[3] = (good[3][0] + 50, good[3][1])
+    out = eng.frame_batch(frames, view=1, time_bounds=e.TBOUNDS_GIVEN, t_bounds=bad).cpu().numpy()
+    assert eng.status()["fixup_ran"]
+    for i in range(4):
+        assert np.array_equal(out[i], want[i])
+
+
+def test_batch_single_interleaving_and_epoch_wrap(small):
+    tables, _, eng = small
+    a = [orc.synth_events(900 + i, 6_000, 160, 120) for i in range(5)]
+    wa = want_frames(tables, a, 0)
+    eng.set_option("epoch", 0xFFFF - 12)
+    for rep in range(4):  # each batch takes 10 epochs: crosses the 16-bit wrap
+        out = eng.frame_batch(a, view=0).cpu().numpy()
+        for i in range(5):
+            assert np.array_equal(out[i], wa[i]), f"rep {rep} frame {i}"
+        assert np.array_equal(eng.frame(a[rep], view=0).cpu().numpy(), wa[rep])
+    assert eng.get_option("epoch") < 100
+
+
+def test_batch_option_off_is_identical(small):
+    tables, _, eng = small
+    frames = [orc.synth_events(40 + i, 8_000 + 100 * i, 160, 120) for i in range(5)]
+    on = eng.frame_batch(frames, view=0).cpu().numpy()
+    eng.set_option("batch", 0)
+    try:
+        off = eng.frame_batch(frames, view=0).cpu().numpy()
+    finally:
+        eng.set_option("batch", 1)
+    assert np.array_equal(on, off)
+
+
+def test_pixel_oob_is_flagged_per_frame(small):
+    tables, _, eng = small
+    frames = [orc.synth_events(2, 2_000, 160, 120) for _ in range(3)]
+    frames[2] = frames[2].copy()
+    frames[2]["x"][7] = 160
+    eng.frame_batch(frames, view=1)
+    assert eng.status()["pixel_oob"]
+
+
+def test_heavy_collisions_in_a_batch(small):
+    tables, _, eng = small
+    rng = np.random.default_rng(3)
+    frames = []
+    for i in range(3):
+        n = 150_000
+        ev = orc.synth_events(30 + i, n, 160, 120, p_on=1.0)
+        ev["x"] = rng.integers(60, 64, n)
+        ev["y"] = rng.integers(50, 54, n)
+        frames.append(ev)
+    for view in (0, 1):
+        out = eng.frame_batch(frames, view=view).cpu().numpy()
+        for i, w in enumerate(want_frames(tables, frames, view)):
+            assert np.array_equal(out[i], w)
+
+
+def test_default_geometry_1m_events(default):
+    """BASELINE geometry, 6 x 1 M events: the tile items of one frame overlap the chunks of the next."""
+    tables, _, eng = default
+    frames = [orc.synth_events(1000 + i, 1_000_000, 640, 480) for i in range(6)]
+    for view in (0, 1):
+        out = eng.frame_batch(frames, view=view).cpu().numpy()
+        for i in (0, 3, 5):
+            assert np.array_equal(out[i], orc.frame_depth(tables, frames[i], view)), f"view {view} frame {i}"
+        # the other frames against the single-frame kernels
+        for i in (1, 2, 4):
+            assert np.array_equal(out[i], eng.frame(frames[i], view=view).cpu().numpy())

@@ -1,0 +1,661 @@
+// xm_batch_kernel.cuh — ONE persistent kernel for a batch of independent frames.
+//
+// Frames do not depend on each other (python/depth_reprojection_pipe.py:121-167 keeps no state across
+// frames), so a batch of them can be rendered by one grid that never drains between frames:
+//
+//   * All work of the batch is ONE ordered list of items handed out by a global counter.  An item is
+//     either an event chunk (kEvChunk records of one frame) or an epilogue tile (32x32 output pixels of
+//     one frame; camera view: 4096 pixels).  "Slot" s of the list holds the chunks of frame s with the
+//     tiles of frame s-1 interleaved into its middle half, so the epilogue of a frame runs on the same
+//     SMs, at the same time, as the event stream of the next one: HBM streaming, L2 gathers and the
+//     shared-memory dilation overlap instead of alternating, and there is no launch, drain or pipeline
+//     fill per frame.
+//   * Every CTA is the lean warp-specialised pipeline of events_lean_kernel: one producer lane takes
+//     items from the counter and feeds an mbarrier ring (TMA bulk copies of the chunk and of its X-map
+//     window; a tile is just a descriptor in the ring), eight consumer warps work through the ring in
+//     order.  The producer takes its items TWO ahead and reads the first / last timestamp of a chunk
+//     ONE ahead, so neither the atomic's nor the loads' round trip sits on its critical path.
+//   * A tile of frame f may only read the scatter map once every chunk of frame f has been scattered.
+//     Each CTA counts the chunks it finished per frame and publishes the count (after a fence) when its
+//     consumers leave the frame; a tile item spins until the frame's count is complete.  Items are taken
+//     in list order and a tile only ever waits for items earlier in the list, so this cannot deadlock,
+//     and because the tiles of frame f start a quarter of a frame after its last chunk was handed out
+//     the wait is normally already over.
+//   * Frames rotate through kBatchMaps scatter maps (epoch-tagged keys as everywhere else), so the
+//     events of frame f+1 and f+2 never disturb the cells frame f's tiles still have to read; the
+//     first chunk of frame f+3 a CTA sees waits for frame f's tile count (long complete for real frames).
+//   * Time bounds: batch_bounds_kernel (one tiny launch per batch) looks up first / last valid event
+//     of every frame.  Events outside the assumed bounds flag their frame; batch_redo_kernel (one tiny
+//     launch per batch) re-renders flagged frames exactly (device-side tail launches of the two-pass
+//     kernels), so unsorted input stays bit-exact without any host round trip.
+#pragma once
+#include "xm_fused_kernel.cuh"
+
+namespace xm {
+
+constexpr int kBatchMax = 32;    // frames per launch (the frame table travels in the kernel parameters)
+constexpr int kBatchMaps = 3;    // scatter maps in rotation
+constexpr int kBatchHeader = 768;  // mbarriers, ring descriptors, CTA accumulators, per-warp frame constants
+constexpr int kCamTilePx = 4096;  // camera-view epilogue item
+
+struct BatchFrame {
+    const int4* events;
+    void* dst;
+    long long n;
+};
+
+struct BatchParams {
+    // per-event tables / geometry (as EventParams)
+    int polarity;
+    const int* lut_xy;
+    int cam_w, cam_h;
+    const short* xmap_t;
+    int xmap_w, xmap_h, col_stride;
+    int t_px_scale, x_offset;
+    int rect_w, rect_h;
+    int cap_cols, stages, win_stages;
+    unsigned long long* maps[kBatchMaps];
+    unsigned epoch0;        // frame f scatters with epoch0 + f
+    FrameState* states;     // [n_frames + 1]; block n_frames is the control block (next_chunk = item counter)
+    // epilogue (ep.map / ep.dst / ep.state are set per tile)
+    EpilogueParams ep;
+    int tiles_x, tile_items;  // items per frame epilogue
+    int n_frames;
+    int debug;  // timing experiments only (results WRONG): 16 = skip the epilogue work of tile items
+    unsigned total_items;
+    unsigned first_item[kBatchMax + 2];  // first item of slot s (slot n_frames holds the last frame's tiles)
+    BatchFrame frames[kBatchMax];
+};
+
+__host__ __device__ __forceinline__ unsigned batch_chunks(long long n) { return static_cast<unsigned>((n + kEvChunk - 1) / kEvChunk); }
+
+inline int batch_smem_bytes(int stages, int win_stages, int win_bytes, int region_cells) {
+    int lut_tile = region_cells * 4;  // the tile's two u16 regions alias the LUT double buffer (+ extra)
+    if (lut_tile < kEvLutBytes) lut_tile = kEvLutBytes;
+    return kBatchHeader + lut_tile + stages * (kEvChunk * 16) + win_stages * win_bytes;
+}
+
+struct BatchBoundsParams {
+    const int4* events[kBatchMax];
+    long long n[kBatchMax];
+    long long lo[kBatchMax], hi[kBatchMax];
+    unsigned given_mask;  // bit f: bounds of frame f are lo[f] / hi[f] (else first / last valid event)
+    int polarity;
+    int n_frames;
+    FrameState* states;
+};
+
+// grid = n_frames + 1 CTAs of 64 threads: clears the state blocks and sets the bounds of every frame
+__global__ void __launch_bounds__(64) batch_bounds_kernel(const __grid_constant__ BatchBoundsParams p) {
+    const int f = blockIdx.x;
+    FrameState* st = p.states + f;
+    if (threadIdx.x == 0) {
+        st->red_lo = 0;
+        st->red_hi = 0;
+        st->n_valid = 0;
+        st->n_inliers = 0;
+        st->flags = 0;
+        st->redo = 0;
+        st->epoch_used = 0;
+        st->blocks_done = 0;
+        st->any_valid = 0;
+        st->next_chunk = 0;
+        st->next_tile = 0;
+        st->fix_chunk = 0;
+    }
+    if (f >= p.n_frames) {
+        if (threadIdx.x == 0) st->t_lo_bits = st->t_hi_bits = 0;
+        return;
+    }
+    if (p.given_mask & (1u << f)) {
+        if (threadIdx.x == 0) {
+            st->t_lo_bits = p.lo[f];
+            st->t_hi_bits = p.hi[f];
+        }
+        return;
+    }
+    scan_sorted_bounds(p.events[f], p.n[f], p.polarity, threadIdx.x >> 5, threadIdx.x & 31, &st->t_lo_bits);
+}
+
+__device__ __forceinline__ long long ld_time_nc(const int4* ev) {
+    long long t;
+    asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(t) : "l"(reinterpret_cast<const char*>(ev) + 8));
+    return t;
+}
+__device__ __forceinline__ void sts128_a(unsigned addr, const int4& v) {
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ int2 lds64_a(unsigned addr) {
+    int2 r;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+    return r;
+}
+
+// One epilogue item of frame f, executed by the kEvThreads consumer threads (kept out of line so that
+// its registers do not weigh on the per-event loop).
+template <bool CAM>
+static __device__ __noinline__ void batch_tile(const BatchParams& bp, int f, int t, unsigned short* bufA, unsigned short* bufB, int tid) {
+    const unsigned epoch = bp.epoch0 + static_cast<unsigned>(f);
+    if (bp.debug & 16) {
+        // timing experiment: no epilogue work (results WRONG)
+    } else if (CAM) {
+        const unsigned long long* mp = bp.maps[f % kBatchMaps];
+        const int n_px = bp.ep.out_w * bp.ep.out_h;
+        const int end = min(n_px, (t + 1) * kCamTilePx);
+        for (int i = t * kCamTilePx + tid; i < end; i += kEvThreads)
+            emit_pixel_int(bp.ep.out, bp.frames[f].dst, i, key_disparity(__ldcg(mp + i), epoch));
+    } else {
+        EpilogueParams q = bp.ep;
+        q.map = bp.maps[f % kBatchMaps];
+        q.dst = bp.frames[f].dst;
+        const int by = t / bp.tiles_x;
+        proj7_tile<kEvThreads, 3>(q, t - by * bp.tiles_x, by, bp.tiles_x, epoch, bufA, bufB, tid, 1);
+    }
+}
+
+template <bool CAM>
+__global__ void __launch_bounds__(kWsThreads, 3) batch_kernel(const __grid_constant__ BatchParams bp) {
+    extern __shared__ __align__(128) unsigned char ev_smem[];
+    uint64_t* full_ev = reinterpret_cast<uint64_t*>(ev_smem);
+    uint64_t* empty_ev = reinterpret_cast<uint64_t*>(ev_smem + 32);
+    uint64_t* full_win = reinterpret_cast<uint64_t*>(ev_smem + 64);
+    uint64_t* empty_win = reinterpret_cast<uint64_t*>(ev_smem + 96);
+    int2* win_meta = reinterpret_cast<int2*>(ev_smem + 128);  // [4] (first column, count) of a window stage
+    int2* ev_meta = reinterpret_cast<int2*>(ev_smem + 160);   // [4] (kind << 16 | frame, chunk or tile index); x < 0: end
+    unsigned* s_acc = reinterpret_cast<unsigned*>(ev_smem + 192);  // [8][4] per-frame CTA accumulators: valid, inliers, flags, warps
+    const int lut_tile = max(bp.ep.region_cap * 4, kEvLutBytes);
+    unsigned char* ring = ev_smem + kBatchHeader + lut_tile;
+    const int win_bytes = bp.cap_cols * bp.col_stride * 2;
+    unsigned char* win_ring = ring + bp.stages * (kEvChunk * 16);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const bool producer = warp == kEvThreads / 32;
+    const int B = bp.n_frames;
+    unsigned* const item_counter = &bp.states[B].next_chunk;
+
+    if (tid == 0) {
+        for (int s = 0; s < kWsMaxStages; ++s) {
+            mbar_init(full_ev + s, 1);
+            mbar_init(empty_ev + s, kEvThreads / 32);
+            mbar_init(full_win + s, 1);
+            mbar_init(empty_win + s, kEvThreads / 32);
+        }
+    }
+    if (tid < 32) s_acc[tid] = 0u;
+    __syncthreads();
+
+    if (producer) {
+        if (lane != 0) return;
+        // ---- producer lane ------------------------------------------------------------------------
+        int se = 0, sw = 0;
+        unsigned pe = 0, pw = 0;
+        int issued = 0;
+        const uint64_t pol = make_evict_first_policy();
+        // slot decoding state (items arrive in increasing order)
+        int slot = 0;
+        unsigned s_first = bp.first_item[0], s_next = bp.first_item[1];
+        unsigned sC = 0, sP = 0, sA = 0, sR = 0;
+        auto load_slot = [&]() {
+            sC = slot < B ? batch_chunks(bp.frames[slot].n) : 0u;
+            sP = slot >= 1 ? static_cast<unsigned>(bp.tile_items) : 0u;
+            sR = sP ? (sC / 2u) / sP : 0u;
+            sA = sR ? sC / 4u : sC;
+        };
+        load_slot();
+        // item -> (kind << 16 | frame, index); x = -1: past the end
+        auto decode = [&](unsigned it) -> int2 {
+            if (it >= bp.total_items) return make_int2(-1, 0);
+            while (it >= s_next) {
+                ++slot;
+                s_first = s_next;
+                s_next = bp.first_item[slot + 1];
+                load_slot();
+            }
+            unsigned j = it - s_first;
+            if (j < sA) return make_int2(slot, static_cast<int>(j));
+            j -= sA;
+            const unsigned period = sR + 1u;
+            if (j < sP * period) {
+                const unsigned q = j / period, m = j - q * period;
+                if (m == 0u) return make_int2((1 << 16) | (slot - 1), static_cast<int>(q));
+                return make_int2(slot, static_cast<int>(sA + q * sR + m - 1u));
+            }
+            return make_int2(slot, static_cast<int>(sA + sP * sR + (j - sP * period)));
+        };
+        // first / last timestamp of a chunk (loads only; consumed one iteration later)
+        auto fetch_ts = [&](const int2& d, long long& ta, long long& tb) {
+            ta = tb = 0;
+            if (d.x < 0 || (d.x >> 16)) return;
+            const BatchFrame& fr = bp.frames[d.x];
+            const long long first = static_cast<long long>(d.y) * kEvChunk;
+            const long long last = min(fr.n, first + kEvChunk) - 1;
+            ta = ld_time_nc(fr.events + first);
+            tb = ld_time_nc(fr.events + last);
+        };
+
+        int tc_frame = -1;
+        TimeCol<false> tc;
+        tc.init(0, 0, bp.t_px_scale);
+
+        int2 dA = decode(atomicAdd(item_counter, 1u));
+        long long tAa, tAb;
+        fetch_ts(dA, tAa, tAb);
+        unsigned itB = dA.x >= 0 ? atomicAdd(item_counter, 1u) : 0xffffffffu;
+        for (;;) {
+            // look-ahead: decode the next item (its atomic was issued one iteration ago), start its
+            // timestamp loads, and issue the atomic of the one after
+            const int2 dB = dA.x >= 0 ? decode(itB) : make_int2(-1, 0);
+            long long tBa, tBb;
+            fetch_ts(dB, tBa, tBb);
+            const unsigned itC = dB.x >= 0 ? atomicAdd(item_counter, 1u) : 0xffffffffu;
+
+            if (issued >= bp.stages) mbar_wait(empty_ev + se, pe);
+            ev_meta[se] = dA;
+            if (dA.x < 0 || (dA.x >> 16)) {
+                mbar_arrive(full_ev + se);  // descriptor only (tile / end)
+            } else {
+                const BatchFrame& fr = bp.frames[dA.x];
+                const long long first = static_cast<long long>(dA.y) * kEvChunk;
+                const unsigned count = static_cast<unsigned>(min(static_cast<long long>(kEvChunk), fr.n - first));
+                mbar_expect_tx(full_ev + se, count * 16u);
+                tma_load_1d_hint(ring + se * (kEvChunk * 16), fr.events + first, count * 16u, full_ev + se, pol);
+            }
+            ++issued;
+            if (++se == bp.stages) {
+                se = 0;
+                if (issued > bp.stages) pe ^= 1u;
+            }
+            if (dA.x < 0) break;
+            if (!(dA.x >> 16) && bp.cap_cols > 0) {
+                // X-map window: the columns between the chunk's first and last record
+                if (dA.x != tc_frame) {
+                    tc_frame = dA.x;
+                    const FrameState* st = bp.states + tc_frame;
+                    tc.init(__ldcg(&st->t_lo_bits), __ldcg(&st->t_hi_bits), bp.t_px_scale);
+                }
+                bool va, vb;
+                int ca = tc.column(tAa, va), cb = tc.column(tAb, vb);
+                ca = min(max(ca, 0), bp.xmap_w - 1);
+                cb = min(max(cb, 0), bp.xmap_w - 1);
+                const int lo = min(ca, cb);
+                const int n = min(min(max(ca, cb) - lo + 1, bp.cap_cols), bp.xmap_w - lo);
+                mbar_wait(empty_win + sw, pw ^ 1u);  // first round passes immediately
+                win_meta[sw] = make_int2(lo, n);
+                const unsigned bytes = static_cast<unsigned>(n) * bp.col_stride * 2u;
+                mbar_expect_tx(full_win + sw, bytes);
+                tma_load_1d(win_ring + sw * win_bytes, bp.xmap_t + static_cast<long long>(lo) * bp.col_stride, bytes, full_win + sw);
+                if (++sw == bp.win_stages) {
+                    sw = 0;
+                    pw ^= 1u;
+                }
+            }
+            dA = dB;
+            tAa = tBa;
+            tAb = tBb;
+            itB = itC;
+        }
+        return;
+    }
+
+    // ---- consumers (8 warps) ------------------------------------------------------------------------
+    const unsigned sbase = smem_u32(ev_smem);
+    const unsigned a_full_ev = sbase, a_empty_ev = sbase + 32, a_full_win = sbase + 64, a_empty_win = sbase + 96;
+    const unsigned a_wmeta = sbase + 128, a_emeta = sbase + 160;
+    const unsigned a_lut = sbase + kBatchHeader + tid * 4;                   // + parity * 4096 + k * 1024
+    const unsigned a_ring = sbase + kBatchHeader + lut_tile + tid * 16;      // + slot * 16384 + k * 4096
+    const unsigned a_win = sbase + kBatchHeader + lut_tile + bp.stages * (kEvChunk * 16);
+    // geometry is read from the parameter bank where it is used (constant operands, no registers)
+#define XM_B_YLIM (static_cast<unsigned>(bp.xmap_h) - 1u)
+#define XM_B_CAMW (static_cast<unsigned>(bp.cam_w))
+#define XM_B_CAMH (static_cast<unsigned>(bp.cam_h))
+    const unsigned pol_mask = bp.polarity ? 0xffffu : 0u;
+
+    int fe = 0, bw = 0;
+    unsigned fpe = 0, bpw = 0;
+    unsigned fpar = 0, bpar = 0;  // LUT double-buffer halves of the next front / back half
+
+    // per-frame state
+    int cur_f = -1;
+    unsigned my_chunks = 0, n_valid = 0, n_inl = 0, flags = 0;
+    // The constants of the frame a warp is working on live in shared memory (48 B per warp, written by
+    // lane 0 when the warp enters a frame, read back with broadcast loads where they are used): unlike
+    // the single-frame kernels, where they are kernel parameters, they would otherwise occupy ~14
+    // registers across the whole per-event loop and push it into local-memory spills.
+    //   [0] t_min lo, hi, range, 2*scale   [1] d, M, shift, ok   [2] map lo, hi, epoch << 16, n_events
+    const unsigned a_fc = sbase + 320 + warp * 48;
+
+    // leaves frame cur_f: statistics and the count of finished chunks go to the frame's state block
+    // (once per CTA: the last of the eight warps to leave forwards the CTA's totals)
+    auto leave_frame = [&]() {
+        if (cur_f < 0) return;
+        n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+        n_inl = __reduce_add_sync(0xffffffffu, n_inl);
+        flags = __reduce_or_sync(0xffffffffu, flags);
+        __threadfence();  // every lane: its scatter atomics are ordered before the counts below
+        __syncwarp();
+        if (lane == 0) {
+            unsigned* acc = s_acc + (cur_f & 7) * 4;
+            if (n_valid) atomicAdd(acc + 0, n_valid);
+            if (n_inl) atomicAdd(acc + 1, n_inl);
+            if (flags) atomicOr(acc + 2, flags);
+            __threadfence_block();
+            if (atomicAdd(acc + 3, 1u) == kEvThreads / 32 - 1) {
+                __threadfence_block();
+                const unsigned v = atomicExch(acc + 0, 0u), i = atomicExch(acc + 1, 0u), fl = atomicExch(acc + 2, 0u);
+                atomicExch(acc + 3, 0u);
+                FrameState* st = bp.states + cur_f;
+                if (v) atomicAdd(&st->n_valid, static_cast<unsigned long long>(v));
+                if (i) atomicAdd(&st->n_inliers, static_cast<unsigned long long>(i));
+                if (fl) atomicOr(&st->flags, fl);
+                __threadfence();
+                atomicAdd(&st->blocks_done, my_chunks);
+            }
+        }
+        __syncwarp();
+        n_valid = n_inl = flags = 0;
+        my_chunks = 0;
+        cur_f = -1;
+    };
+    auto enter_frame = [&](int f) {
+        leave_frame();
+        cur_f = f;
+        if (f >= kBatchMaps) {
+            // this frame scatters into the map frame f - kBatchMaps used: all of that frame's tiles must have read it
+            if (lane == 0) {
+                const unsigned* done = &bp.states[f - kBatchMaps].next_tile;
+                const unsigned need = static_cast<unsigned>(bp.tile_items);
+                while (ld_acquire_u32(done) < need) __nanosleep(64);
+            }
+            __syncwarp();
+        }
+        const FrameState* st = bp.states + f;
+        if (lane == 0) {
+            IntCol ic;
+            ic.init(__ldcg(&st->t_lo_bits), __ldcg(&st->t_hi_bits), bp.t_px_scale);
+            const unsigned long long mp = reinterpret_cast<unsigned long long>(bp.maps[f % kBatchMaps]);
+            sts128_a(a_fc, make_int4(static_cast<int>(ic.lo), static_cast<int>(ic.lo >> 32), static_cast<int>(ic.range), static_cast<int>(ic.scale2)));
+            sts128_a(a_fc + 16, make_int4(static_cast<int>(ic.d), static_cast<int>(ic.M), ic.sh, ic.ok ? 1 : 0));
+            sts128_a(a_fc + 32, make_int4(static_cast<int>(mp), static_cast<int>(mp >> 32),
+                                          static_cast<int>((bp.epoch0 + static_cast<unsigned>(f)) << 16), static_cast<int>(bp.frames[f].n)));
+        }
+        __syncwarp();
+    };
+
+    auto peek = [&]() -> int2 {
+        mbar_wait_a(a_full_ev + fe * 8, fpe);
+        return lds64_a(a_emeta + fe * 8);
+    };
+    auto release = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(a_empty_ev + fe * 8);
+        if (++fe == bp.stages) {
+            fe = 0;
+            fpe ^= 1u;
+        }
+    };
+
+    // FRONT half of chunk g of the current frame (stage fe): events into registers, LUT gathers started,
+    // time columns computed; releases the stage
+    auto front = [&](int g, int (&col)[kEvPerThread], int (&pix)[kEvPerThread]) {
+        const unsigned a_stage = a_ring + fe * (kEvChunk * 16);
+        const unsigned a_lut_c = a_lut + fpar * (kEvChunk * 4);
+        fpar ^= 1u;
+        IntCol ic;
+        {
+            const int4 c0 = lds128_a(a_fc), c1 = lds128_a(a_fc + 16);
+            ic.lo = (static_cast<unsigned long long>(static_cast<unsigned>(c0.y)) << 32) | static_cast<unsigned>(c0.x);
+            ic.range = static_cast<unsigned>(c0.z);
+            ic.scale2 = static_cast<unsigned>(c0.w);
+            ic.d = static_cast<unsigned>(c1.x);
+            ic.M = static_cast<unsigned>(c1.y);
+            ic.sh = c1.z;
+            ic.ok = c1.w != 0;
+        }
+        const unsigned left = static_cast<unsigned>(lds32_a(a_fc + 44)) - static_cast<unsigned>(g) * kEvChunk;
+        const int limit = left < kEvChunk ? static_cast<int>(left) : kEvChunk;
+        unsigned vmask = 0, bad_mask = 0;
+        // two events at a time: half the registers for the raw records (the per-event loop must not spill)
+#pragma unroll
+        for (int h = 0; h < kEvPerThread; h += 2) {
+            int4 raw[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) raw[j] = lds128_a(a_stage + (h + j) * (kEvThreads * 16));
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int k = h + j;
+                const unsigned ex = static_cast<unsigned>(raw[j].x) & 0xffffu, ey = static_cast<unsigned>(raw[j].x) >> 16;
+                bool valid = ((static_cast<unsigned>(raw[j].y) ^ 1u) & pol_mask) == 0u;  // polarity: p == 1, or everything
+                if (limit < kEvChunk) valid = valid && (k * kEvThreads + tid < limit);
+                const bool ok = valid && ex < XM_B_CAMW && ey < XM_B_CAMH;
+                const int px = static_cast<int>(ey * XM_B_CAMW + ex);
+                if (ok) cp_async_4_a(a_lut_c + k * (kEvThreads * 4), bp.lut_xy + px);
+                const long long t_bits = (static_cast<long long>(raw[j].w) << 32) | static_cast<unsigned>(raw[j].z);
+                bool bad;
+                const unsigned q = ic.column(t_bits, bad);
+                col[k] = ok ? static_cast<int>(q) : -1;
+                if (CAM) pix[k] = px;
+                vmask |= valid ? (1u << k) : 0u;
+                bad_mask |= (valid && (!ok || bad || !ic.ok)) ? (1u << k) : 0u;
+            }
+        }
+        cp_async_commit();
+        n_valid += __popc(vmask);
+        if (bad_mask) {  // slow path: the reference's own float64 expression / error flags
+            TimeCol<false> tc;  // rebuilt here: the float64 constants are not worth registers in the hot loop
+            tc.init(__ldcg(&bp.states[cur_f].t_lo_bits), __ldcg(&bp.states[cur_f].t_hi_bits), bp.t_px_scale);
+#pragma unroll
+            for (int k = 0; k < kEvPerThread; ++k) {
+                if (!(bad_mask & (1u << k))) continue;
+                if (col[k] < 0) {
+                    flags |= kStatusPixelOob;  // the reference raises IndexError here
+                    continue;
+                }
+                const int4 rec = lds128_a(a_stage + k * (kEvThreads * 16));  // the stage is ours until release()
+                const long long t_bits = (static_cast<long long>(rec.w) << 32) | static_cast<unsigned>(rec.z);
+                bool viol;
+                int cc = tc.column(t_bits, viol);
+                if (cc < 0) cc += bp.xmap_w;  // NumPy negative index (only reachable with wrong bounds)
+                viol = viol || cc < 0 || cc >= bp.xmap_w;
+                if (viol) {
+                    flags |= kStatusTBounds;
+                    cc = 0;
+                }
+                col[k] = cc;
+            }
+        }
+        release();
+    };
+
+    // BACK half: X-map lookups (window in shared memory, else through L2), disparity, scatter
+    auto back = [&](int g, const int (&col)[kEvPerThread], const int (&pix)[kEvPerThread]) {
+        int win_lo = 0;
+        unsigned win_n = 0;
+        unsigned a_win_c = a_lut;  // any valid address: without a window every lookup misses
+        if (bp.cap_cols > 0) {
+            mbar_wait_a(a_full_win + bw * 8, bpw);
+            win_lo = lds32_a(a_wmeta + bw * 8);
+            win_n = static_cast<unsigned>(lds32_a(a_wmeta + bw * 8 + 4));
+            a_win_c = a_win + bw * win_bytes;
+        }
+        const unsigned a_lut_c = a_lut + bpar * (kEvChunk * 4);
+        bpar ^= 1u;
+        int lut[kEvPerThread], xp[kEvPerThread];
+#pragma unroll
+        for (int k = 0; k < kEvPerThread; ++k) lut[k] = lds32_a(a_lut_c + k * (kEvThreads * 4));
+        unsigned hit_mask = 0, miss_mask = 0;
+#pragma unroll
+        for (int k = 0; k < kEvPerThread; ++k) {
+            const unsigned ycr = static_cast<unsigned>(lut[k] >> 16);
+            const unsigned rel = static_cast<unsigned>(col[k] - win_lo);  // dropped events (col = -1) wrap to huge
+            const bool y_ok = ycr < XM_B_YLIM;  // x_maps_disparity.py:23: 0 <= y_rect < H - 1 (last row excluded)
+            const bool hit = y_ok && rel < win_n;
+            xp[k] = lds_s16_a(a_win_c + (hit ? (rel * static_cast<unsigned>(bp.col_stride) + ycr) * 2u : 0u));
+            hit_mask |= hit ? (1u << k) : 0u;
+            miss_mask |= (y_ok && !hit && col[k] >= 0) ? (1u << k) : 0u;
+        }
+        if (miss_mask) {  // column outside the staged window: read the transposed table through L2
+#pragma unroll
+            for (int k = 0; k < kEvPerThread; ++k)
+                if (miss_mask & (1u << k)) xp[k] = __ldg(bp.xmap_t + static_cast<long long>(col[k]) * bp.col_stride + (lut[k] >> 16));
+            hit_mask |= miss_mask;
+        }
+        const unsigned idx0 = static_cast<unsigned>(g) * kEvChunk + static_cast<unsigned>(tid);
+        const int4 c2 = lds128_a(a_fc + 32);
+        unsigned long long* const map = reinterpret_cast<unsigned long long*>(
+            (static_cast<unsigned long long>(static_cast<unsigned>(c2.y)) << 32) | static_cast<unsigned>(c2.x));
+        const unsigned epoch16 = static_cast<unsigned>(c2.z);
+        unsigned imask = 0;
+#pragma unroll
+        for (int k = 0; k < kEvPerThread; ++k) {
+            const int xcr = static_cast<short>(lut[k] & 0xffff);
+            const int ycr = lut[k] >> 16;
+            const int disp = static_cast<short>(xp[k] - xcr - bp.x_offset);  // int16 arithmetic wraps
+            const bool inl = ((hit_mask >> k) & 1u) && disp >= 0;
+            // projector view: x_rect + disp = x_map - x_offset, in [0, rect_w) for verified tables
+            const int cell = CAM ? pix[k] : ycr * bp.rect_w + (xp[k] - bp.x_offset);
+            const unsigned idx = idx0 + static_cast<unsigned>(k * kEvThreads);
+            const unsigned long long key =
+                (static_cast<unsigned long long>(epoch16 | (idx >> 16)) << 32) | ((idx << 16) | static_cast<unsigned>(disp));
+            red_max_u64_if(map + cell, key, inl);
+            imask |= inl ? (1u << k) : 0u;
+        }
+        n_inl += __popc(imask);
+        if (bp.cap_cols > 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(a_empty_win + bw * 8);
+            if (++bw == bp.win_stages) {
+                bw = 0;
+                bpw ^= 1u;
+            }
+        }
+        ++my_chunks;
+    };
+
+    int2 m = peek();
+    for (;;) {
+        if (m.x < 0) break;
+        const int f = m.x & 0xffff;
+        if (m.x >> 16) {
+            // ---- epilogue tile m.y of frame f ---------------------------------------------------------
+            const int t = m.y;
+            release();
+            if (cur_f >= 0 && cur_f <= f) leave_frame();
+            // all consumers are done with the LUT buffers (the tile regions alias them) and have left frame f
+            group_sync<kEvThreads>(1);
+            if (tid == 0) {
+                const unsigned need = batch_chunks(bp.frames[f].n);
+                const unsigned* done = &bp.states[f].blocks_done;
+                while (ld_acquire_u32(done) < need) __nanosleep(64);
+            }
+            group_sync<kEvThreads>(1);
+            {
+                unsigned short* bufA = reinterpret_cast<unsigned short*>(ev_smem + kBatchHeader);
+                batch_tile<CAM>(bp, f, t, bufA, bufA + bp.ep.region_cap, tid);
+            }
+            group_sync<kEvThreads>(1);  // the regions are free again before anyone starts LUT gathers
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(&bp.states[f].next_tile, 1u);  // this tile no longer needs the frame's scatter map
+            }
+            m = peek();
+            continue;
+        }
+        // ---- a run of chunks of frame f -------------------------------------------------------------------
+        if (f != cur_f) enter_frame(f);
+        int col_cur[kEvPerThread], pix_cur[kEvPerThread];
+        int g_cur = m.y;
+        front(g_cur, col_cur, pix_cur);
+        for (;;) {
+            m = peek();
+            const bool more = m.x == cur_f;  // kind 0, same frame
+            int col_nxt[kEvPerThread], pix_nxt[kEvPerThread];
+            if (more) {
+                front(m.y, col_nxt, pix_nxt);
+                cp_async_wait<1>();  // the gathers of the current chunk have landed; the next chunk's stay in flight
+            } else {
+                cp_async_wait<0>();
+            }
+            back(g_cur, col_cur, pix_cur);
+            if (!more) break;
+#pragma unroll
+            for (int k = 0; k < kEvPerThread; ++k) {
+                col_cur[k] = col_nxt[k];
+                if (CAM) pix_cur[k] = pix_nxt[k];
+            }
+            g_cur = m.y;
+        }
+    }
+    leave_frame();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Exact re-render of the frames whose optimistic bounds were violated (unsorted input): one thread
+// walks the batch and tail-launches, per flagged frame, the bounds reduction, the lean per-event
+// kernel on the reduced bounds and the epilogue -- the same kernels the single-frame path uses.
+// ---------------------------------------------------------------------------------------------------
+struct BatchRedoParams {
+    EventParams ev;       // shared fields; events / n / epoch / state / map are set per frame
+    EpilogueParams ep;    // shared fields; dst / epoch / state are set per frame
+    unsigned epoch_redo0;  // frame f re-renders with epoch_redo0 + f
+    int n_frames;
+    int sm_count;
+    int k1_grid_max, k1_smem;
+    int tiles_x, tiles_y, k2_smem;
+    int view;
+    FrameState* states;
+    BatchFrame frames[kBatchMax];
+};
+
+__global__ void __launch_bounds__(32) batch_redo_kernel(const __grid_constant__ BatchRedoParams rp) {
+    if (threadIdx.x != 0) return;
+    for (int f = 0; f < rp.n_frames; ++f) {
+        FrameState* st = rp.states + f;
+        const unsigned fl = *reinterpret_cast<volatile unsigned*>(&st->flags);
+        if (!(fl & kStatusTBounds)) continue;
+        st->flags = fl & ~(kStatusPixelOob | kStatusScatterOob);
+        st->redo = 1;
+        st->blocks_done = 0;
+        st->next_chunk = 0;
+        st->red_lo = 0;
+        st->red_hi = 0;
+        const BatchFrame& fr = rp.frames[f];
+        long long b = (fr.n + 2047) / 2048;
+        b = b < 1 ? 1 : (b > rp.sm_count * 8 ? rp.sm_count * 8 : b);
+        bounds_reduce_kernel<false><<<static_cast<int>(b), 256, 0, cudaStreamTailLaunch>>>(fr.events, fr.n, rp.ev.polarity, st);
+        EventParams q = rp.ev;
+        q.events = fr.events;
+        q.n = fr.n;
+        q.epoch = rp.epoch_redo0 + f;
+        q.state = st;
+        q.bounds_mode = 2;
+        q.arm_fixup = 0;
+        q.use_pdl = 0;
+        long long g = (fr.n + kEvChunk - 1) / kEvChunk;
+        g = g < 1 ? 1 : (g > rp.k1_grid_max ? rp.k1_grid_max : g);
+        if (rp.view == 1)
+            events_lean_kernel<true><<<static_cast<int>(g), kWsThreads, rp.k1_smem, cudaStreamTailLaunch>>>(q);
+        else
+            events_lean_kernel<false><<<static_cast<int>(g), kWsThreads, rp.k1_smem, cudaStreamTailLaunch>>>(q);
+        EpilogueParams e = rp.ep;
+        e.dst = fr.dst;
+        e.state = st;
+        e.epoch = q.epoch - 1;  // the epilogue adds state->redo (= 1)
+        e.recycle = nullptr;
+        e.use_pdl = 0;
+        if (rp.view == 1) {
+            long long eb = (static_cast<long long>(e.out_w) * e.out_h + 511) / 512;
+            eb = eb > rp.sm_count * 8 ? rp.sm_count * 8 : eb;
+            epilogue_camera_kernel<<<static_cast<int>(eb), 256, 0, cudaStreamTailLaunch>>>(e);
+        } else {
+            epilogue_projector7_kernel<<<dim3(rp.tiles_x, rp.tiles_y), 256, rp.k2_smem, cudaStreamTailLaunch>>>(e);
+        }
+    }
+}
+
+#undef XM_B_YLIM
+#undef XM_B_CAMW
+#undef XM_B_CAMH
+
+}  // namespace xm

@@ -17,6 +17,7 @@
 #include "../../include/xmaps_b200.h"
 #include "xm_stage_kernels.cuh"
 #include "xm_fused_kernel.cuh"
+#include "xm_batch_kernel.cuh"
 
 namespace {
 
@@ -104,6 +105,13 @@ struct XmCtx {
     int opt_k2_variant = 1;   // 1: sliding-window epilogue (7x7, even rect_w), 0: per-tap epilogue
     int opt_fused = 1;        // 1: one fused kernel per frame where the lean path applies
     int fused_occ = 0;        // resident CTAs per SM of frame_kernel
+    int opt_batch = 0;        // 1: xm_frame_batch renders uniform batches with one persistent kernel per <= 32 frames
+                              //    (bit-exact; measured 8 % slower than the fused per-frame kernels on B200, so opt-in:
+                              //    profiles/EXPERIMENTS_r01.md "batch kernel")
+    int batch_occ = 0, batch_smem = 0, batch_cols = 0;  // launch configuration of batch_kernel
+    unsigned long long* d_map_ring[xm::kBatchMaps] = {nullptr, nullptr, nullptr};  // [0] = d_map
+    xm::FrameState* d_bstate = nullptr;  // [kBatchMax + 1] state blocks of the current batch
+    const xm::FrameState* status_src = nullptr;  // state block xm_frame_status reports (NULL: d_state + last_slot)
     int opt_pdl = 1;          // programmatic dependent launch between K1 / K2 / next K1
     int opt_safe_tables = 1;  // use the check-free scatter when the tables were verified
     int opt_stages = 2;  // depth of the shared-memory event ring of K1
@@ -118,6 +126,7 @@ struct XmCtx {
     size_t prof_used = 0;
     double prof_k1_ms = 0.0, prof_k2_ms = 0.0;
     long long prof_frames = 0;
+    long long prof_batch_extra = 0;  // frames rendered by batch launches beyond one per event triple
     // derived
     int ev_occ_i64 = 0, ev_occ_f64 = 0;
     int ev_smem = 0, cap_cols = 0;
@@ -147,6 +156,7 @@ int acquire_state_slot(XmCtx* c, cudaStream_t s, bool need_clean, cudaError_t* e
 // state block for a stage-by-stage call (cleared here unless the callee resets it itself)
 int staged_state(XmCtx* c, cudaStream_t s, bool need_clean, xm::FrameState** out) {
     cudaError_t err;
+    c->status_src = nullptr;
     const int slot = acquire_state_slot(c, s, need_clean, &err);
     XM_CUDA(err);
     c->slot_dirty[slot] = true;
@@ -160,6 +170,8 @@ unsigned next_epoch(XmCtx* c, unsigned count, cudaStream_t s, cudaError_t* err) 
     *err = cudaSuccess;
     if (c->epoch + count > 0xffffu) {
         *err = cudaMemsetAsync(c->d_map, 0, static_cast<size_t>(c->map_cells) * 8, s);
+        for (int i = 1; i < xm::kBatchMaps && *err == cudaSuccess; ++i)
+            if (c->d_map_ring[i]) *err = cudaMemsetAsync(c->d_map_ring[i], 0, static_cast<size_t>(c->map_cells) * 8, s);
         c->epoch = 0;
     }
     unsigned e = c->epoch + 1;
@@ -242,6 +254,32 @@ int configure_event_kernels(XmCtx* c) {
             occ_min = occ < occ_min ? occ : occ_min;
         }
         c->fused_occ = occ_min;
+    }
+    // batch kernel: same pipeline plus the tile regions; keep 3 CTAs below the 196 KB shared-memory
+    // carve-out (above it the L1 shrinks to 28 KB and the LUT gathers slow down by 1.5x, EXPERIMENTS_r01.md)
+    c->batch_occ = 0;
+    if (variant == 2) {
+        int bcols = cols;
+        auto smem_for = [&](int k) { return xm::batch_smem_bytes(c->opt_stages, c->opt_win_stages, k * c->col_stride * 2, c->opt_region_cells); };
+        while (bcols > 0 && 3 * (smem_for(bcols) + 1024) > 196 * 1024) --bcols;
+        c->batch_cols = bcols;
+        c->batch_smem = smem_for(bcols);
+        int occ_min = 1 << 30;
+        for (int cam = 0; cam < 2; ++cam) {
+            void (*k)(xm::BatchParams) = cam ? xm::batch_kernel<true> : xm::batch_kernel<false>;
+            cudaFuncAttributes fa;
+            XM_CUDA(cudaFuncGetAttributes(&fa, k));
+            const int dyn = optin - static_cast<int>(fa.sharedSizeBytes);
+            if (c->batch_smem > dyn) {
+                occ_min = 0;
+                break;
+            }
+            XM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+            int occ = 0;
+            XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, xm::kWsThreads, c->batch_smem));
+            occ_min = occ < occ_min ? occ : occ_min;
+        }
+        c->batch_occ = occ_min;
     }
     return XM_OK;
 }
@@ -373,6 +411,7 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     XM_CUDA(err);
     const int slot = acquire_state_slot(c, s, true, &err);
     XM_CUDA(err);
+    c->status_src = nullptr;
     xm::FrameState* st = c->d_state + slot;
     int rc = XM_OK;
     const int polarity = (a->flags & XM_FLAG_POLARITY) ? 1 : 0;
@@ -546,6 +585,175 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     return XM_OK;
 }
 
+// true if frames a[0..n) can be rendered by one batch_kernel launch sequence
+bool batch_applies(const XmCtx* c, const XmFrameArgs* a, int n) {
+    if (!c->opt_batch || n < 2 || c->opt_k1_variant != 2 || c->batch_occ < 1) return false;
+    if (!(c->lut_safe && c->xmap_safe && c->opt_safe_tables)) return false;
+    if (static_cast<long long>(c->proj_w) * c->proj_h <= 0 && a[0].view == XM_VIEW_PROJECTOR) return false;
+    if (a[0].view == XM_VIEW_PROJECTOR && !(c->dilate == 7 && !(c->rect_w & 1))) return false;
+    for (int i = 0; i < n; ++i) {
+        if (a[i].view != a[0].view || a[i].output != a[0].output || a[i].flags != a[0].flags) return false;
+        if (a[i].z_near != a[0].z_near || a[i].z_far != a[0].z_far) return false;
+        if ((a[i].flags & XM_FLAG_TIME_F64) || a[i].time_bounds == XM_TBOUNDS_REDUCE || !a[i].d_out) return false;
+    }
+    return true;
+}
+
+int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
+    // lazily: the extra scatter maps and the batch's state blocks
+    if (!c->d_bstate) {
+        XM_CUDA(cudaMalloc(&c->d_bstate, (xm::kBatchMax + 1) * sizeof(xm::FrameState)));
+        XM_CUDA(cudaMemset(c->d_bstate, 0, (xm::kBatchMax + 1) * sizeof(xm::FrameState)));
+    }
+    c->d_map_ring[0] = c->d_map;
+    for (int i = 1; i < xm::kBatchMaps; ++i)
+        if (!c->d_map_ring[i]) {
+            XM_CUDA(cudaMalloc(&c->d_map_ring[i], static_cast<size_t>(c->map_cells) * 8));
+            XM_CUDA(cudaMemset(c->d_map_ring[i], 0, static_cast<size_t>(c->map_cells) * 8));
+        }
+    const bool cam = a[0].view == XM_VIEW_CAMERA;
+    const int polarity = (a[0].flags & XM_FLAG_POLARITY) ? 1 : 0;
+    const bool fixup = c->opt_auto_fixup != 0;
+    cudaError_t err;
+    const unsigned epoch0 = next_epoch(c, static_cast<unsigned>(fixup ? 2 * n : n), s, &err);
+    XM_CUDA(err);
+    c->prev_was_frame = false;
+
+    xm::BatchBoundsParams bb;
+    memset(&bb, 0, sizeof(bb));
+    bb.polarity = polarity;
+    bb.n_frames = n;
+    bb.states = c->d_bstate;
+    for (int f = 0; f < n; ++f) {
+        bb.events[f] = static_cast<const int4*>(a[f].d_events);
+        bb.n[f] = a[f].n_events;
+        if (a[f].time_bounds == XM_TBOUNDS_GIVEN) {
+            bb.given_mask |= 1u << f;
+            bb.lo[f] = a[f].t_min;
+            bb.hi[f] = a[f].t_max;
+        }
+    }
+    xm::batch_bounds_kernel<<<n + 1, 64, 0, s>>>(bb);
+    XM_LAUNCHED();
+
+    xm::BatchParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.polarity = polarity;
+    bp.lut_xy = c->d_lut_xy;
+    bp.cam_w = c->cam_w;
+    bp.cam_h = c->cam_h;
+    bp.xmap_t = c->d_xmap_t;
+    bp.xmap_w = c->xmap_w;
+    bp.xmap_h = c->xmap_h;
+    bp.col_stride = c->col_stride;
+    bp.t_px_scale = c->t_px_scale;
+    bp.x_offset = c->x_offset;
+    bp.rect_w = c->rect_w;
+    bp.rect_h = c->rect_h;
+    bp.cap_cols = c->batch_cols;
+    bp.stages = c->opt_stages;
+    bp.win_stages = c->opt_win_stages;
+    for (int i = 0; i < xm::kBatchMaps; ++i) bp.maps[i] = c->d_map_ring[i];
+    bp.epoch0 = epoch0;
+    bp.states = c->d_bstate;
+    xm::EpilogueParams& q = bp.ep;
+    q.map = nullptr;
+    q.state = nullptr;
+    q.epoch = 0;
+    q.use_pdl = 0;
+    q.recycle = nullptr;
+    q.remap_xy = c->d_remap_xy;
+    q.tile_box = c->d_tile_box;
+    q.rect_w = c->rect_w;
+    q.rect_h = c->rect_h;
+    q.radius = c->dilate / 2;
+    q.region_cap = c->opt_region_cells;
+    q.out = make_output(c, a[0].output, c->depth_scale, a[0].z_near, a[0].z_far);
+    q.dst = nullptr;
+    q.out_w = cam ? c->cam_w : c->proj_w;
+    q.out_h = cam ? c->cam_h : c->proj_h;
+    const int tiles_x = (c->proj_w + xm::kTile - 1) / xm::kTile, tiles_y = (c->proj_h + xm::kTile - 1) / xm::kTile;
+    bp.tiles_x = tiles_x;
+    bp.tile_items = cam ? (c->cam_w * c->cam_h + xm::kCamTilePx - 1) / xm::kCamTilePx : tiles_x * tiles_y;
+    bp.n_frames = n;
+    bp.debug = c->opt_debug;
+    unsigned items = 0;
+    for (int sl = 0; sl <= n; ++sl) {
+        bp.first_item[sl] = items;
+        if (sl < n) items += xm::batch_chunks(a[sl].n_events);
+        if (sl >= 1) items += static_cast<unsigned>(bp.tile_items);
+    }
+    bp.first_item[n + 1] = items;
+    bp.total_items = items;
+    for (int f = 0; f < n; ++f) {
+        bp.frames[f].events = static_cast<const int4*>(a[f].d_events);
+        bp.frames[f].dst = a[f].d_out;
+        bp.frames[f].n = a[f].n_events;
+    }
+    const int occ = c->opt_ctas_per_sm > 0 && c->opt_ctas_per_sm < c->batch_occ ? c->opt_ctas_per_sm : c->batch_occ;
+    long long want = (static_cast<long long>(items) + 1) / 2;  // no more CTAs than (pairs of) items
+    int grid = c->sm_count * occ;
+    if (want < grid) grid = static_cast<int>(want < 1 ? 1 : want);
+    if (c->opt_profile) {
+        int rc = profile_mark(c, s);
+        if (rc) return rc;
+    }
+    if (cam)
+        xm::batch_kernel<true><<<grid, xm::kWsThreads, c->batch_smem, s>>>(bp);
+    else
+        xm::batch_kernel<false><<<grid, xm::kWsThreads, c->batch_smem, s>>>(bp);
+    XM_LAUNCHED();
+    if (c->opt_profile) {
+        int rc = profile_mark(c, s);
+        if (rc) return rc;
+        rc = profile_mark(c, s);
+        if (rc) return rc;
+        c->prof_batch_extra += n - 1;  // one event triple covers n frames
+    }
+
+    if (fixup) {
+        xm::BatchRedoParams rp;
+        memset(&rp, 0, sizeof(rp));
+        xm::EventParams& p = rp.ev;
+        p.polarity = polarity;
+        p.lut_xy = c->d_lut_xy;
+        p.cam_w = c->cam_w;
+        p.cam_h = c->cam_h;
+        p.xmap_t = c->d_xmap_t;
+        p.xmap_w = c->xmap_w;
+        p.xmap_h = c->xmap_h;
+        p.col_stride = c->col_stride;
+        p.t_px_scale = c->t_px_scale;
+        p.x_offset = c->x_offset;
+        p.rect_w = c->rect_w;
+        p.rect_h = c->rect_h;
+        p.view = a[0].view;
+        p.map = c->d_map;
+        p.cap_cols = c->cap_cols;
+        p.lookahead = c->opt_lookahead;
+        p.stages = c->opt_stages;
+        p.win_stages = c->opt_win_stages;
+        p.smem_bytes = c->ev_smem;
+        rp.ep = bp.ep;
+        rp.ep.map = c->d_map;
+        rp.epoch_redo0 = epoch0 + static_cast<unsigned>(n);
+        rp.n_frames = n;
+        rp.sm_count = c->sm_count;
+        rp.k1_grid_max = c->sm_count * c->ev_occ_i64;
+        rp.k1_smem = c->ev_smem;
+        rp.tiles_x = tiles_x;
+        rp.tiles_y = tiles_y;
+        rp.k2_smem = c->opt_region_cells * 4;
+        rp.view = a[0].view;
+        rp.states = c->d_bstate;
+        for (int f = 0; f < n; ++f) rp.frames[f] = bp.frames[f];
+        xm::batch_redo_kernel<<<1, 32, 0, s>>>(rp);
+        XM_LAUNCHED();
+    }
+    c->status_src = c->d_bstate + (n - 1);
+    return XM_OK;
+}
+
 size_t output_bytes(const XmCtx* c, int view, int output) {
     const size_t px = view == XM_VIEW_CAMERA ? static_cast<size_t>(c->cam_w) * c->cam_h : static_cast<size_t>(c->proj_w) * c->proj_h;
     return output == XM_OUT_BGR ? px * 3 : px * 4;
@@ -698,6 +906,8 @@ int xm_ctx_destroy(XmCtx* c) {
     cudaFree(c->d_depth_lut);
     cudaFree(c->d_dbg);
     cudaFree(c->d_map);
+    for (int i = 1; i < xm::kBatchMaps; ++i) cudaFree(c->d_map_ring[i]);
+    cudaFree(c->d_bstate);
     cudaFree(c->d_state);
     cudaFree(c->d_counts);
     cudaFree(c->d_stage_ev);
@@ -762,6 +972,10 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         c->opt_k2_variant = v != 0;
         return XM_OK;
     }
+    if (!strcmp(key, "batch")) {
+        c->opt_batch = v != 0;
+        return XM_OK;
+    }
     if (!strcmp(key, "fused")) {
         c->opt_fused = v != 0;
         return XM_OK;
@@ -794,6 +1008,7 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         if (v < 0) {
             c->prof_k1_ms = c->prof_k2_ms = 0.0;
             c->prof_frames = 0;
+            c->prof_batch_extra = 0;
         } else {
             c->opt_profile = v != 0;
         }
@@ -824,6 +1039,10 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     else if (!strcmp(key, "k1_variant")) *value = c->opt_k1_variant;
     else if (!strcmp(key, "pdl")) *value = c->opt_pdl;
     else if (!strcmp(key, "fused")) *value = c->opt_fused;
+    else if (!strcmp(key, "batch")) *value = c->opt_batch;
+    else if (!strcmp(key, "batch_occ")) *value = c->batch_occ;
+    else if (!strcmp(key, "batch_smem")) *value = c->batch_smem;
+    else if (!strcmp(key, "batch_cols")) *value = c->batch_cols;
     else if (!strcmp(key, "k2_variant")) *value = c->opt_k2_variant;
     else if (!strcmp(key, "safe_tables")) *value = c->opt_safe_tables && c->lut_safe && c->xmap_safe;
     else if (!strcmp(key, "auto_fixup")) *value = c->opt_auto_fixup;
@@ -832,13 +1051,14 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     else if (!strcmp(key, "region_cells")) *value = c->opt_region_cells;
     else if (!strcmp(key, "epoch")) *value = c->epoch;
     else if (!strcmp(key, "profile")) *value = c->opt_profile;
-    else if (!strcmp(key, "profile_k1_ns") || !strcmp(key, "profile_k2_ns") || !strcmp(key, "profile_frames")) {
+    else if (!strcmp(key, "profile_k1_ns") || !strcmp(key, "profile_k2_ns") || !strcmp(key, "profile_frames") || !strcmp(key, "profile_launches")) {
         DeviceGuard guard(c->device);
         int rc = profile_drain(c); /* synchronises on the recorded events */
         if (rc) return rc;
         if (key[9] == '1') *value = static_cast<int64_t>(c->prof_k1_ms * 1e6);
         else if (key[9] == '2') *value = static_cast<int64_t>(c->prof_k2_ms * 1e6);
-        else *value = c->prof_frames;
+        else if (key[8] == 'l') *value = c->prof_frames;  /* timed K1 launches (a batch launch covers many frames) */
+        else *value = c->prof_frames + c->prof_batch_extra;
     }
     else if (!strcmp(key, "cap_cols")) *value = c->cap_cols;          /* read-only, derived */
     else if (!strcmp(key, "occupancy")) *value = c->ev_occ_i64;       /* read-only, derived */
@@ -863,8 +1083,21 @@ int xm_frame_batch(XmCtx* c, const XmFrameArgs* a, int32_t n_frames, void* strea
         if (rc) return rc;
     }
     DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (batch_applies(c, a, n_frames)) {
+        // one persistent kernel per group of <= kBatchMax frames; a trailing single frame joins the last group
+        int i = 0;
+        while (i < n_frames) {
+            int m = n_frames - i;
+            if (m > xm::kBatchMax) m = (m - xm::kBatchMax == 1) ? xm::kBatchMax - 1 : xm::kBatchMax;
+            int rc = batch_impl(c, a + i, m, s);
+            if (rc) return rc;
+            i += m;
+        }
+        return XM_OK;
+    }
     for (int i = 0; i < n_frames; ++i) {
-        int rc = frame_impl(c, a + i, static_cast<cudaStream_t>(stream));
+        int rc = frame_impl(c, a + i, s);
         if (rc) return rc;
     }
     return XM_OK;
@@ -875,7 +1108,7 @@ int xm_frame_status(XmCtx* c, XmFrameStatus* h, void* stream) {
     DeviceGuard guard(c->device);
     xm::FrameState st;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    XM_CUDA(cudaMemcpyAsync(&st, c->d_state + c->last_slot, sizeof(st), cudaMemcpyDeviceToHost, s));
+    XM_CUDA(cudaMemcpyAsync(&st, c->status_src ? c->status_src : c->d_state + c->last_slot, sizeof(st), cudaMemcpyDeviceToHost, s));
     XM_CUDA(cudaStreamSynchronize(s));
     h->n_events = 0;
     h->n_valid = static_cast<int64_t>(st.n_valid);

@@ -1458,7 +1458,7 @@ __device__ __forceinline__ void group_sync(int bar_id) {
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT) : "memory");
 }
 
-template <int NT>
+template <int NT, int UA = 1>
 __device__ __forceinline__ void proj7_tile(const EpilogueParams& p, int bx, int by, int tiles_x, unsigned epoch, unsigned short* bufA,
                                            unsigned short* bufB, int gtid, int bar_id) {
     constexpr int R = 3;
@@ -1493,16 +1493,30 @@ __device__ __forceinline__ void proj7_tile(const EpilogueParams& p, int bx, int 
                 const int pairs = stride >> 1;
                 const unsigned mg = magic_div(pairs);
                 unsigned* dst = reinterpret_cast<unsigned*>(bufA);
-                for (int c = tid; c < pairs * rh; c += NT) {
-                    const int ry = static_cast<int>(__umulhi(static_cast<unsigned>(c), mg));
-                    const int cx = 2 * (c - ry * pairs) - kRowPad;  // data coordinate of the pair's first cell (even)
-                    const int gx = rx0 + cx, gy = ry0 + ry;
-                    unsigned packed = 0;
-                    if (cx >= 0 && cx < rw && gx >= 0 && gx < p.rect_w && gy >= 0 && gy < p.rect_h) {
-                        const ulonglong2 kk = __ldcg(reinterpret_cast<const ulonglong2*>(p.map + gy * p.rect_w + gx));
-                        packed = static_cast<unsigned>(key_disparity(kk.x, epoch)) | (static_cast<unsigned>(key_disparity(kk.y, epoch)) << 16);
+                // UA cell pairs per thread per round, all loads of a round issued before the first decode:
+                // with UA > 1 the region comes out of L2 in one round trip per round instead of one per pair
+                const int total = pairs * rh;
+                for (int c0 = tid; c0 < total; c0 += UA * NT) {
+                    ulonglong2 kk[UA];
+                    bool live[UA];
+#pragma unroll
+                    for (int j = 0; j < UA; ++j) {
+                        const int c = c0 + j * NT;
+                        const int ry = static_cast<int>(__umulhi(static_cast<unsigned>(c), mg));
+                        const int cx = 2 * (c - ry * pairs) - kRowPad;  // data coordinate of the pair's first cell (even)
+                        const int gx = rx0 + cx, gy = ry0 + ry;
+                        live[j] = c < total && cx >= 0 && cx < rw && gx >= 0 && gx < p.rect_w && gy >= 0 && gy < p.rect_h;
+                        kk[j] = make_ulonglong2(0ULL, 0ULL);
+                        if (live[j]) kk[j] = __ldcg(reinterpret_cast<const ulonglong2*>(p.map + gy * p.rect_w + gx));
                     }
-                    dst[c] = packed;
+#pragma unroll
+                    for (int j = 0; j < UA; ++j) {
+                        const int c = c0 + j * NT;
+                        if (c < total)
+                            dst[c] = live[j] ? (static_cast<unsigned>(key_disparity(kk[j].x, epoch)) |
+                                                (static_cast<unsigned>(key_disparity(kk[j].y, epoch)) << 16))
+                                             : 0u;
+                    }
                 }
             }
             group_sync<NT>(bar_id);

@@ -125,6 +125,11 @@ class DepthEngine:
     def set_option(self, key: str, value: int):
         N.check(N.lib.xm_ctx_set_option(self._ctx, key.encode(), int(value)))
 
+    @staticmethod
+    def launch_count() -> int:
+        """Kernels launched by the library in this process so far."""
+        return N.launch_count()
+
     def get_option(self, key: str) -> int:
         v = C.c_int64()
         N.check(N.lib.xm_ctx_get_option(self._ctx, key.encode(), C.byref(v)))
@@ -203,8 +208,12 @@ class DepthEngine:
         z_near: float = 0.1,
         z_far: float = 1.0,
         out: Optional[torch.Tensor] = None,
+        t_bounds: Optional[Sequence] = None,
     ) -> torch.Tensor:
-        """Independent frames back to back on one stream -> ``[n_frames, ...]``."""
+        """Independent frames on one stream -> ``[n_frames, ...]``.  Uniform batches (one view / output,
+        integer timestamps) are rendered by ONE persistent kernel per 32 frames (``xm_frame_batch``): the
+        epilogue of a frame overlaps the event stream of the next one.  ``t_bounds``: per-frame
+        ``(t_min, t_max)`` for ``TBOUNDS_GIVEN``."""
         evs = [self.events(f) for f in frames]
         shape = self.out_shape(view, output)
         dtype = torch.uint8 if output == OUT_BGR else torch.float32
@@ -214,7 +223,8 @@ class DepthEngine:
             raise ValueError("out has the wrong shape / dtype")
         arr = (N.XmFrameArgs * max(1, len(evs)))()
         for i, ev in enumerate(evs):
-            arr[i] = self._args(ev, view, output, time_bounds, polarity, None, None, z_near, z_far, out[i].data_ptr())
+            lo, hi = t_bounds[i] if t_bounds is not None else (None, None)
+            arr[i] = self._args(ev, view, output, time_bounds, polarity, lo, hi, z_near, z_far, out[i].data_ptr())
         N.check(N.lib.xm_frame_batch(self._ctx, arr, len(evs), self._stream()))
         return out
 
