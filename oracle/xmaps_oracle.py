@@ -335,3 +335,204 @@ def synth_events(seed: int, n: int, cam_w: int, cam_h: int, frame_us: int = 1666
     ev = np.zeros(n, dtype=EVENT_DTYPE)
     ev["x"], ev["y"], ev["p"], ev["t"] = x, y, p, t + t0
     return ev
+
+
+# --------------------------------------------------------------------------------------
+# N4 -- per-frame de-duplication filters (python/frame_event_filter.py:19-128)
+#
+# The reference scatters `t` (and for the YT filter `x`) into zero-initialised int32 images indexed
+# by the event's key and reads the images back through a boolean mask, i.e. the survivors come out in
+# row-major key order, `t` wrapped to int32, `p` = 1.  Forward assignment keeps the LAST duplicate.
+# The "First..." filters assign reversed VIEWS (`img[y[::-1], x[::-1]] = t[::-1]`) and are meant to keep
+# the first duplicate, but NumPy's index iterator negates the negative strides of the three views and
+# walks them in memory order again, so the reference AS IT RUNS (NumPy 2.3.5 here; golden vectors in
+# tests/golden/stream_filters.npz) keeps the LAST duplicate in those filters too, and the "mean" filter
+# averages the last timestamp with itself (with the int32 wrap of the sum).  `as_reference=True`
+# (default) reproduces that; `as_reference=False` gives the documented intent (true first event).
+# Restated with one stable argsort of the keys instead of dense images.
+# --------------------------------------------------------------------------------------
+FILTER_NONE, FILTER_FIRST_YT, FILTER_FIRST_XY, FILTER_LAST_XY, FILTER_MEAN_XY = 0, 1, 2, 3, 4
+
+
+def _first_last_per_key(key: np.ndarray):
+    """Unique keys (ascending) with the index of their first and last occurrence."""
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    start = np.flatnonzero(np.concatenate(([True], ks[1:] != ks[:-1]))) if len(ks) else np.zeros(0, np.int64)
+    end = np.concatenate((start[1:], [len(ks)])) - 1 if len(ks) else np.zeros(0, np.int64)
+    return ks[start], order[start], order[end]
+
+
+def _t32(t: np.ndarray) -> np.ndarray:
+    """`int32_image[...] = events["t"]`: the int64 timestamp wraps to int32 (frame_event_filter.py:26,52)."""
+    return t.astype(np.int64).astype(np.int32)
+
+
+def frame_event_filter(events: np.ndarray, mode: int, xp_i16: Optional[np.ndarray] = None, as_reference: bool = True) -> np.ndarray:
+    """`FrameEventFilter.filter_events(events, xp_i16)` of the five filters
+    (frame_event_filter.py:10-128).  Errors of the reference are kept: an empty positive set raises
+    ValueError (`.max()` of an empty array, :24); for the YT filter `xp_i16` must be as long as the
+    positive events (:78 would raise on the shape mismatch) and a negative column wraps like a NumPy
+    index (IndexError if it wraps below 0)."""
+    if mode == FILTER_NONE:
+        return events  # NoFilter :10-16
+    ev = events[events["p"] == 1]  # :21,47,72,104
+    if len(ev) == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")
+    y = ev["y"].astype(np.int64)
+    if mode == FILTER_FIRST_YT:
+        xp = np.asarray(xp_i16)
+        if len(xp) != len(ev):
+            raise IndexError("shape mismatch: indexing arrays could not be broadcast together")
+        width = int(xp.max()) + 1  # :75
+        col = xp.astype(np.int64)
+        col = np.where(col < 0, col + width, col)
+        if width <= 0 or (col < 0).any():
+            raise IndexError("index out of bounds for the (y, x_rect) image")
+        keys, first, last = _first_last_per_key(y * width + col)
+        if as_reference:
+            first = last
+        out = np.zeros(len(keys), dtype=events.dtype)
+        out["t"] = _t32(ev["t"][first])  # :83 (reversed assignment: first event wins)
+        out["x"] = ev["x"][first]        # :79
+        out["y"] = keys // width
+        out["p"] = 1
+        return out
+    width = int(ev["x"].max()) + 1
+    keys, first, last = _first_last_per_key(y * width + ev["x"].astype(np.int64))
+    if as_reference:
+        first = last
+    out = np.zeros(len(keys), dtype=events.dtype)
+    if mode == FILTER_LAST_XY:       # :19-41
+        out["t"] = _t32(ev["t"][last])
+    elif mode == FILTER_FIRST_XY:    # :44-66
+        out["t"] = _t32(ev["t"][first])
+    elif mode == FILTER_MEAN_XY:     # :101-128: int32 add (wraps), floor division
+        out["t"] = (_t32(ev["t"][last]).astype(np.int64) + _t32(ev["t"][first]).astype(np.int64)).astype(np.int32) // 2
+    else:
+        raise ValueError(f"unknown filter mode {mode}")
+    out["x"] = keys % width
+    out["y"] = keys // width
+    out["p"] = 1
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# N2 -- frame segmentation (python/trigger_finder.py:93-189)
+# --------------------------------------------------------------------------------------
+MIN_EVENTS_PER_FRAME = 1000  # trigger_finder.py:8
+
+
+def find_trigger(t: np.ndarray, projector_fps: float, pause_thresh_us: int = 40, min_events: int = MIN_EVENTS_PER_FRAME):
+    """Decision of `RobustTriggerFinder.find_trigger` (:146-189) on the timestamps of the popped
+    buffer.  Returns (status, prev_idx, next_idx, n_pauses):
+      status  1: frame = events[prev_idx + 2 : next_idx - 2], events[next_idx - 2 :] go back to the buffer
+      status  0: candidate rejected, events[next_idx :] go back to the buffer
+      status -1: no candidate, nothing goes back (the reference has already popped the buffer)."""
+    t = np.asarray(t).astype(np.int64)
+    pauses = np.flatnonzero(t[1:] - t[:-1] >= pause_thresh_us) if len(t) > 1 else np.zeros(0, np.int64)  # :155
+    frame_us = 1e6 / projector_fps
+    for k in range(len(pauses) - 1):  # :161 consecutive pauses
+        prev_idx, next_idx = int(pauses[k]), int(pauses[k + 1])
+        gap = int(t[next_idx] - t[prev_idx])
+        if gap > frame_us / 2:  # :168
+            if gap <= frame_us and next_idx - prev_idx > min_events:  # :169
+                return 1, prev_idx, next_idx, len(pauses)
+            return 0, prev_idx, next_idx, len(pauses)  # :184-187
+    return -1, -1, -1, len(pauses)
+
+
+class TriggerFinderOracle:
+    """`RobustTriggerFinder` + `EventBufferList` (:11-145) on plain NumPy chunks: same buffering,
+    frame-drop and span rules; `frame_callback(events)` fires once per accepted frame."""
+
+    def __init__(self, projector_fps, frame_callback, pause_thresh_us: int = 40):
+        self.projector_fps = projector_fps
+        self.frame_callback = frame_callback
+        self.pause_thresh_us = pause_thresh_us
+        self.should_drop = False
+        self.last_frame_start_us = -1
+        self.chunks = []
+        self.log = []  # (status, start_time) per find_trigger call
+
+    # EventBufferList ---------------------------------------------------------------------
+    def _first_t(self):
+        return int(self.chunks[0]["t"][0]) if self.chunks else -1
+
+    def _last_t(self):
+        return int(self.chunks[-1]["t"][-1]) if self.chunks else -1
+
+    def _drop(self, drop_len_ms):  # :63-75
+        until = self._first_t() + drop_len_ms * 1000
+        dropped = False
+        while self.chunks and self._first_t() < until:
+            self.chunks.pop(0)
+            dropped = True
+        return dropped
+
+    # RobustTriggerFinder -----------------------------------------------------------------
+    def reset(self):  # :111-114
+        self.chunks.clear()
+        self.should_drop = False
+        self.last_frame_start_us = -1
+
+    def drop_frame(self):
+        self.should_drop = True
+
+    def process_events(self, evs):  # :119-144
+        if len(evs):
+            self.chunks.append(evs)
+        if self.should_drop:
+            if self._drop(1e3 / self.projector_fps):
+                self.should_drop = False
+            else:
+                return
+        if not self.chunks:
+            return
+        first, last = self._first_t(), self._last_t()
+        span = -1 if first < 0 or last < 0 else last - first  # :52-60
+        if span < 1e6 / self.projector_fps:
+            return
+        evs = np.concatenate(self.chunks)
+        self.chunks.clear()
+        status, prev_idx, next_idx, _ = find_trigger(evs["t"], self.projector_fps, self.pause_thresh_us)
+        start_time = -1
+        if status == 1:
+            self.frame_callback(evs[prev_idx + 2 : next_idx - 2])
+            start_time = int(evs["t"][prev_idx + 2])
+            self.last_frame_start_us = start_time
+            rest = evs[next_idx - 2 :]
+        elif status == 0:
+            rest = evs[next_idx:]
+        else:
+            rest = evs[:0]
+        if len(rest):
+            self.chunks.append(rest)
+        self.log.append((status, start_time))
+
+
+def synth_projector_stream(seed: int, n_frames: int, events_per_frame: int, cam_w: int, cam_h: int, projector_fps: float = 60.2,
+                           duty: float = 0.95, glitch_every: int = 0) -> np.ndarray:
+    """A continuous stream as the laser projector produces it: per frame period a burst of events over
+    `duty` of the period (sorted, gaps well below the 40 us pause threshold), then a pause.  The true
+    rate sits slightly above the nominal 60 fps, as it must for the reference's `gap <= 1e6 / fps` test
+    (:169) to accept frames.  With `glitch_every` > 0 every such frame is cut short (a rejected
+    candidate for the trigger finder)."""
+    rng = np.random.default_rng(seed)
+    period = 1e6 / projector_fps
+    chunks = []
+    for f in range(n_frames):
+        n = events_per_frame
+        active = duty * period
+        if glitch_every and f % glitch_every == glitch_every - 1:
+            active *= 0.45
+            n = max(4, n // 2)
+        t0 = int(round(f * period)) + 100
+        t = t0 + np.floor(np.arange(n, dtype=np.float64) * (active / n)).astype(np.int64) + rng.integers(0, 3, n)
+        ev = np.zeros(n, dtype=EVENT_DTYPE)
+        ev["x"] = rng.integers(0, cam_w, n)
+        ev["y"] = rng.integers(0, cam_h, n)
+        ev["p"] = 1
+        ev["t"] = np.sort(t)
+        chunks.append(ev)
+    return np.concatenate(chunks)
