@@ -69,6 +69,14 @@ enum {
 #define XM_STATUS_TBOUNDS_VIOLATED 0x1u /* an event lies outside the assumed [t_min, t_max]          */
 #define XM_STATUS_PIXEL_OOB 0x2u        /* event pixel outside the camera image (ref: IndexError)   */
 #define XM_STATUS_SCATTER_OOB 0x4u      /* scatter target outside the map       (ref: IndexError)   */
+#define XM_STATUS_FILTER_POLARITY 0x8u  /* xm_filter_events YT: an event with p != 1 (ref: index arrays would not line up) */
+#define XM_STATUS_FILTER_INDEX 0x10u    /* xm_filter_events YT: column outside the (y, x_rect) image (ref: IndexError)     */
+
+/* XmFilterMode: the reference's frame_event_filter.py classes */
+#define XM_FILTER_FIRST_YT 1 /* FirstEventPerYTFilter          :70-98   */
+#define XM_FILTER_FIRST_XY 2 /* FirstEventPerXYFilter          :44-66   */
+#define XM_FILTER_LAST_XY 3  /* LastEventPerXYFilter           :19-41   */
+#define XM_FILTER_MEAN_XY 4  /* MeanFirstLastEventPerXYFilter  :101-128 */
 
 typedef struct XmCtx XmCtx;
 
@@ -209,6 +217,24 @@ int xm_colorize(XmCtx* ctx, const float* d_disp, int64_t n, double depth_scale, 
 /* CamProjMaps.construct_point_cloud (cam_proj_calibration.py:319-331): float32 [n] x3 -> [n, 3]. */
 int xm_point_cloud(XmCtx* ctx, const float* d_x, const float* d_y, const float* d_disp, int64_t n,
                    const double* h_Q /* 4x4 row-major */, float* d_xyz, void* stream);
+
+/* ---- the rows either side of the path ("next" rows N4, N2) -------------------------------- */
+/* FrameEventFilter.filter_events (python/frame_event_filter.py:19-128): one survivor per key -- pixel
+ * (x, y), or (y, rectified x) for XM_FILTER_FIRST_YT, which needs d_x_rect = rectify_cam_coords_i16 of the
+ * frame -- written as EventCD records (p = 1, t wrapped to int32 as the reference's int32 images do) in
+ * row-major key order.  d_out needs room for min(n, cam_h * key-image width) records; *d_count receives
+ * the number written.  as_reference != 0 reproduces the reference as it runs (its "first" filters assign
+ * reversed NumPy views, which NumPy walks in memory order again, so they keep the LAST event per key);
+ * as_reference == 0 keeps the first event, the documented intent.  Only events with p == 1 take part. */
+int xm_filter_events(XmCtx* ctx, const void* d_events, int64_t n, int32_t mode, const int16_t* d_x_rect,
+                     int32_t as_reference, void* d_out, int64_t* d_count, void* stream);
+/* RobustTriggerFinder.find_trigger (python/trigger_finder.py:146-189) on one time-ordered buffer:
+ * pauses = events followed by a gap >= pause_thresh_us; the first two consecutive pauses further apart
+ * than frame_us / 2 decide.  d_result[0..5] (device, int64) = status, prev_idx, next_idx, n_pauses,
+ * t[prev_idx + 2], t[next_idx - 2];  status 1: frame = events[prev_idx + 2 : next_idx - 2], the caller
+ * keeps events[next_idx - 2 :];  0: candidate rejected, keep events[next_idx :];  -1: none, keep nothing. */
+int xm_find_trigger(XmCtx* ctx, const void* d_events, int64_t n, int64_t pause_thresh_us, double frame_us,
+                    int64_t min_events, int64_t* d_result /* [8] */, void* stream);
 
 /* ---- set-up time ("next" row N3) --------------------------------------------------------- */
 /* compute_x_map_from_time_map (python/x_map.py:5-55): float32 time map [h, w] (device) ->

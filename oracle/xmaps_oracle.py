@@ -535,4 +535,9 @@ def synth_projector_stream(seed: int, n_frames: int, events_per_frame: int, cam_
         ev["p"] = 1
         ev["t"] = np.sort(t)
         chunks.append(ev)
-    return np.concatenate(chunks)
+    out = np.zeros(sum(len(c) for c in chunks), dtype=EVENT_DTYPE)  # (np.concatenate would repack the 16-byte records)
+    i = 0
+    for c in chunks:
+        out[i : i + len(c)] = c
+        i += len(c)
+    return out

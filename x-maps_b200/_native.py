@@ -20,6 +20,8 @@ OUT_DEPTH, OUT_DISPARITY, OUT_BGR = 0, 1, 2
 TBOUNDS_REDUCE, TBOUNDS_SORTED, TBOUNDS_GIVEN = 0, 1, 2
 FLAG_POLARITY, FLAG_TIME_F64 = 0x1, 0x2
 STATUS_TBOUNDS_VIOLATED, STATUS_PIXEL_OOB, STATUS_SCATTER_OOB = 0x1, 0x2, 0x4
+STATUS_FILTER_POLARITY, STATUS_FILTER_INDEX = 0x8, 0x10
+FILTER_FIRST_YT, FILTER_FIRST_XY, FILTER_LAST_XY, FILTER_MEAN_XY = 1, 2, 3, 4
 
 
 class XmTables(C.Structure):
@@ -104,6 +106,8 @@ SIGNATURES = {
     "xm_disp_to_depth": (C.c_int, [_P, _P, _I64, C.c_double, _P, _P]),
     "xm_colorize": (C.c_int, [_P, _P, _I64, C.c_double, C.c_float, C.c_float, _P, _P]),
     "xm_point_cloud": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P]),
+    "xm_filter_events": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P, _P, _P]),
+    "xm_find_trigger": (C.c_int, [_P, _P, _I64, _I64, C.c_double, _I64, _P, _P]),
     "xm_build_xmap": (C.c_int, [C.c_int, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
 }
 

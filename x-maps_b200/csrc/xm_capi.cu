@@ -18,6 +18,7 @@
 #include "xm_stage_kernels.cuh"
 #include "xm_fused_kernel.cuh"
 #include "xm_batch_kernel.cuh"
+#include "xm_stream_kernels.cuh"
 
 namespace {
 
@@ -91,6 +92,13 @@ struct XmCtx {
     // compaction scratch
     unsigned* d_counts = nullptr;
     long long counts_cap = 0;
+    // filters / trigger finder scratch
+    int lut_x_max = 0;                 // largest rectified x of the LUT: bounds the YT filter's key image
+    unsigned* d_filter_first = nullptr;  // [cam_h * max(cam_w, lut_x_max + 1)]
+    unsigned* d_filter_last = nullptr;
+    unsigned* d_pause_idx = nullptr;
+    long long pause_cap = 0;
+    void* d_stream_scratch = nullptr;  // TriggerScratch + xp_max
     // staging for xm_frame_host
     void* d_stage_ev = nullptr;
     long long stage_ev_cap = 0;
@@ -809,8 +817,12 @@ int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
     const size_t cam_px = static_cast<size_t>(t->cam_w) * t->cam_h;
     {
         std::vector<int> packed(cam_px);
-        int min_x = 32767;
-        for (size_t i = 0; i < cam_px; ++i) min_x = t->lut_x[i] < min_x ? t->lut_x[i] : min_x;
+        int min_x = 32767, max_x = -32768;
+        for (size_t i = 0; i < cam_px; ++i) {
+            min_x = t->lut_x[i] < min_x ? t->lut_x[i] : min_x;
+            max_x = t->lut_x[i] > max_x ? t->lut_x[i] : max_x;
+        }
+        c->lut_x_max = max_x;
         c->lut_safe = min_x > -t->x_offset && t->x_offset > 0;
         for (size_t i = 0; i < cam_px; ++i)
             packed[i] = static_cast<int>((static_cast<unsigned>(static_cast<unsigned short>(t->lut_y[i])) << 16) |
@@ -910,6 +922,10 @@ int xm_ctx_destroy(XmCtx* c) {
     cudaFree(c->d_bstate);
     cudaFree(c->d_state);
     cudaFree(c->d_counts);
+    cudaFree(c->d_filter_first);
+    cudaFree(c->d_filter_last);
+    cudaFree(c->d_pause_idx);
+    cudaFree(c->d_stream_scratch);
     cudaFree(c->d_stage_ev);
     cudaFree(c->d_stage_out);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
@@ -1344,6 +1360,125 @@ int xm_point_cloud(XmCtx* c, const float* d_x, const float* d_y, const float* d_
     xm::Mat4f q;
     for (int i = 0; i < 16; ++i) q.m[i] = static_cast<float>(h_Q[i]);
     xm::point_cloud_kernel<<<grid_for(n, 256, 4, c->sm_count * 8), 256, 0, s>>>(d_x, d_y, d_disp, n, q, d_xyz);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
+namespace {
+int ensure_counts(XmCtx* c, long long blocks, cudaStream_t s) {
+    if (blocks > c->counts_cap) {
+        XM_CUDA(cudaStreamSynchronize(s));
+        cudaFree(c->d_counts);
+        c->d_counts = nullptr;
+        c->counts_cap = 0;
+        XM_CUDA(cudaMalloc(&c->d_counts, static_cast<size_t>(blocks) * 4));
+        c->counts_cap = blocks;
+    }
+    return XM_OK;
+}
+int ensure_stream_scratch(XmCtx* c) {
+    if (!c->d_stream_scratch) XM_CUDA(cudaMalloc(&c->d_stream_scratch, 64));
+    return XM_OK;
+}
+}  // namespace
+
+int xm_filter_events(XmCtx* c, const void* d_events, int64_t n, int32_t mode, const int16_t* d_x_rect, int32_t as_reference,
+                     void* d_out, int64_t* d_count, void* stream) {
+    if (!c || n < 0 || !d_count || (n > 0 && (!d_events || !d_out))) return fail(XM_ERR_INVALID_ARG, "filter: bad arguments");
+    if (mode < XM_FILTER_FIRST_YT || mode > XM_FILTER_MEAN_XY) return fail(XM_ERR_INVALID_ARG, "filter: unknown mode %d", mode);
+    if (mode == XM_FILTER_FIRST_YT && n > 0 && !d_x_rect) return fail(XM_ERR_INVALID_ARG, "XM_FILTER_FIRST_YT needs d_x_rect");
+    if (n > 0xfffffffeLL) return fail(XM_ERR_UNSUPPORTED, "more than 2^32 - 2 events");
+    if (reinterpret_cast<uintptr_t>(d_events) & 15 || reinterpret_cast<uintptr_t>(d_out) & 15)
+        return fail(XM_ERR_INVALID_ARG, "event buffers must be 16-byte aligned");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    xm::FrameState* st;
+    int rc = staged_state(c, s, true, &st);
+    if (rc) return rc;
+    if (n == 0) {
+        XM_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
+        return XM_OK;
+    }
+    const int yt_stride = c->lut_x_max + 1 > 1 ? c->lut_x_max + 1 : 1;
+    const int max_stride = yt_stride > c->cam_w ? yt_stride : c->cam_w;
+    if (!c->d_filter_first) {
+        const size_t bytes = static_cast<size_t>(c->cam_h) * max_stride * 4;
+        XM_CUDA(cudaMalloc(&c->d_filter_first, bytes));
+        XM_CUDA(cudaMalloc(&c->d_filter_last, bytes));
+    }
+    rc = ensure_stream_scratch(c);
+    if (rc) return rc;
+    xm::FilterParams p;
+    p.events = static_cast<const int4*>(d_events);
+    p.n = n;
+    p.xp = d_x_rect;
+    p.mode = mode;
+    p.rows = c->cam_h;
+    p.cols = c->cam_w;
+    p.stride = mode == XM_FILTER_FIRST_YT ? yt_stride : c->cam_w;
+    p.as_reference = as_reference ? 1 : 0;
+    p.first = c->d_filter_first;
+    p.last = c->d_filter_last;
+    p.xp_max = reinterpret_cast<int*>(static_cast<char*>(c->d_stream_scratch) + 32);
+    p.state = st;
+    const long long cells = static_cast<long long>(p.rows) * p.stride;
+    const long long blocks = (cells + xm::kCompactBlock - 1) / xm::kCompactBlock;
+    rc = ensure_counts(c, blocks, s);
+    if (rc) return rc;
+    xm::filter_prepare_kernel<<<grid_for(cells, 256, 4, c->sm_count * 8), 256, 0, s>>>(p);
+    XM_LAUNCHED();
+    if (mode == XM_FILTER_FIRST_YT) {
+        xm::filter_xpmax_kernel<<<grid_for(n, 256, 8, c->sm_count * 8), 256, 0, s>>>(p);
+        XM_LAUNCHED();
+    }
+    xm::filter_mark_kernel<<<grid_for(n, 256, 4, c->sm_count * 8), 256, 0, s>>>(p);
+    XM_LAUNCHED();
+    const xm::FilterPred pred{c->d_filter_last};
+    const xm::FilterEmit emit{p, static_cast<int4*>(d_out)};
+    xm::flag_count_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(pred, cells, c->d_counts);
+    XM_LAUNCHED();
+    xm::compact_scan_kernel<<<1, 1024, 0, s>>>(c->d_counts, blocks, reinterpret_cast<long long*>(d_count));
+    XM_LAUNCHED();
+    xm::flag_write_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(pred, emit, cells, c->d_counts);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
+int xm_find_trigger(XmCtx* c, const void* d_events, int64_t n, int64_t pause_thresh_us, double frame_us, int64_t min_events,
+                    int64_t* d_result, void* stream) {
+    if (!c || n < 0 || !d_result || (n > 0 && !d_events)) return fail(XM_ERR_INVALID_ARG, "find_trigger: bad arguments");
+    if (n > 0xfffffffeLL) return fail(XM_ERR_UNSUPPORTED, "more than 2^32 - 2 events");
+    if (reinterpret_cast<uintptr_t>(d_events) & 15) return fail(XM_ERR_INVALID_ARG, "d_events must be 16-byte aligned");
+    if (!(frame_us > 0.0)) return fail(XM_ERR_INVALID_ARG, "frame_us must be positive");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = ensure_stream_scratch(c);
+    if (rc) return rc;
+    xm::TriggerScratch* sc = static_cast<xm::TriggerScratch*>(c->d_stream_scratch);
+    const long long blocks = n > 0 ? (n + xm::kCompactBlock - 1) / xm::kCompactBlock : 1;
+    rc = ensure_counts(c, blocks, s);
+    if (rc) return rc;
+    if (n > c->pause_cap) {
+        XM_CUDA(cudaStreamSynchronize(s));
+        cudaFree(c->d_pause_idx);
+        c->d_pause_idx = nullptr;
+        c->pause_cap = 0;
+        XM_CUDA(cudaMalloc(&c->d_pause_idx, static_cast<size_t>(n) * 4));
+        c->pause_cap = n;
+    }
+    XM_CUDA(cudaMemsetAsync(sc, 0xff, sizeof(xm::TriggerScratch), s));  // first_pair = none
+    const int4* ev = static_cast<const int4*>(d_events);
+    const xm::PausePred pred{ev, n, pause_thresh_us};
+    const xm::PauseEmit emit{c->d_pause_idx};
+    xm::flag_count_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(pred, n, c->d_counts);
+    XM_LAUNCHED();
+    xm::compact_scan_kernel<<<1, 1024, 0, s>>>(c->d_counts, blocks, &sc->n_pauses);
+    XM_LAUNCHED();
+    xm::flag_write_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(pred, emit, n, c->d_counts);
+    XM_LAUNCHED();
+    xm::trigger_pairs_kernel<<<c->sm_count * 2, 256, 0, s>>>(ev, c->d_pause_idx, sc, frame_us / 2.0);
+    XM_LAUNCHED();
+    xm::trigger_decide_kernel<<<1, 32, 0, s>>>(ev, c->d_pause_idx, sc, frame_us, min_events, reinterpret_cast<long long*>(d_result));
     XM_LAUNCHED();
     return XM_OK;
 }

@@ -242,7 +242,45 @@ class DepthEngine:
             "tbounds_violated": bool(st.flags & N.STATUS_TBOUNDS_VIOLATED),
             "pixel_oob": bool(st.flags & N.STATUS_PIXEL_OOB),
             "scatter_oob": bool(st.flags & N.STATUS_SCATTER_OOB),
+            "filter_polarity": bool(st.flags & N.STATUS_FILTER_POLARITY),
+            "filter_index": bool(st.flags & N.STATUS_FILTER_INDEX),
         }
+
+    # ------------------------------------------------------------------ the rows next to the path
+    def filter_events(self, events, mode: int, x_rect: Optional[torch.Tensor] = None, as_reference: bool = True) -> DeviceEvents:
+        """One survivor per key (``frame_event_filter.py``'s filters, ``N.FILTER_*``) as a new device
+        event buffer in row-major key order; see ``xm_filter_events`` in the header."""
+        ev = self.events(events)
+        n = len(ev)
+        if ev.time_f64:
+            raise ValueError("the frame filters work on integer timestamps")
+        if mode == N.FILTER_FIRST_YT:
+            if x_rect is None or x_rect.dtype != torch.int16 or not x_rect.is_contiguous() or x_rect.numel() != n:
+                raise ValueError("FILTER_FIRST_YT needs x_rect: contiguous int16, one entry per event")
+        out = torch.empty((max(n, 1), 4), dtype=torch.int32, device=self.device)
+        count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        N.check(
+            N.lib.xm_filter_events(
+                self._ctx, ev.raw.data_ptr() if n else None, n, int(mode), x_rect.data_ptr() if (x_rect is not None and n) else None,
+                1 if as_reference else 0, out.data_ptr(), count.data_ptr(), self._stream(),
+            )
+        )
+        k = int(count.item())
+        return DeviceEvents(out[:k], False)
+
+    def find_trigger(self, events, projector_fps: float, pause_thresh_us: int = 40, min_events: int = 1000):
+        """``RobustTriggerFinder.find_trigger``'s decision on one device buffer ->
+        ``(status, prev_idx, next_idx, n_pauses, start_time, end_time)`` (one 64-byte read-back)."""
+        ev = self.events(events)
+        n = len(ev)
+        res = torch.empty(8, dtype=torch.int64, device=self.device)
+        N.check(
+            N.lib.xm_find_trigger(
+                self._ctx, ev.raw.data_ptr() if n else None, n, int(pause_thresh_us), 1e6 / float(projector_fps), int(min_events),
+                res.data_ptr(), self._stream(),
+            )
+        )
+        return tuple(int(v) for v in res.cpu().tolist()[:6])
 
     def frame_host(
         self,
