@@ -219,6 +219,10 @@ int xm_point_cloud(XmCtx* ctx, const float* d_x, const float* d_y, const float* 
                    const double* h_Q /* 4x4 row-major */, float* d_xyz, void* stream);
 
 /* ---- the rows either side of the path ("next" rows N4, N2) -------------------------------- */
+/* PolarityFilterAlgorithm(1).process_events (Metavision; call site depth_reprojection_pipe.py:43,114) ==
+ * events[events["p"] == 1] (frame_event_filter.py:21), order preserved; d_out needs room for n records.
+ * (xm_frame fuses this mask; this entry point materialises it for the stream in front of the trigger finder.) */
+int xm_polarity_filter(XmCtx* ctx, const void* d_events, int64_t n, void* d_out, int64_t* d_count, void* stream);
 /* FrameEventFilter.filter_events (python/frame_event_filter.py:19-128): one survivor per key -- pixel
  * (x, y), or (y, rectified x) for XM_FILTER_FIRST_YT, which needs d_x_rect = rectify_cam_coords_i16 of the
  * frame -- written as EventCD records (p = 1, t wrapped to int32 as the reference's int32 images do) in

@@ -111,3 +111,51 @@ def test_evaluation_script_call_sequence(pipes):
     ref[:, 1:] = -ref[:, 1:]
     ok = np.isfinite(ref).all(axis=1) & (d > 0)
     np.testing.assert_allclose(np.asarray(pc)[ok], ref[ok], rtol=2e-5, atol=1e-6)
+
+
+def test_frame_event_filter_in_the_pipe(pipes):
+    """Key `E` of the reference rotates the per-frame filter (depth_reprojection_pipe.py:169-171): the
+    filtered frame must equal the oracle's filter + depth chain."""
+    proj, _ = pipes
+    tables, _ = load_golden_tables("default")
+    evs = orc.polarity_mask(orc.synth_events(3, 300_000, 640, 480))
+    want_plain = orc.colorize(orc.frame_disparity_map(tables, evs, 0), tables.depth_scale, 0.1, 1.0)
+    assert str(proj.ev_filter_proc.selected_filter()) == "NoFilter"
+    assert np.array_equal(proj.process_ev_frame(evs), want_plain)
+    try:
+        assert str(proj.select_next_frame_event_filter()) == "FirstEventPerYTFilter"
+        assert str(proj.select_next_frame_event_filter()) == "FirstEventPerXYFilter"
+        for mode in (orc.FILTER_FIRST_XY, orc.FILTER_LAST_XY, orc.FILTER_MEAN_XY):
+            flt = orc.frame_event_filter(evs, mode)
+            want = orc.colorize(orc.frame_disparity_map(tables, flt, 0), tables.depth_scale, 0.1, 1.0)
+            assert np.array_equal(proj.process_ev_frame(evs), want), mode
+            proj.select_next_frame_event_filter()
+        assert str(proj.ev_filter_proc.selected_filter()) == "NoFilter"
+    finally:
+        while str(proj.ev_filter_proc.selected_filter()) != "NoFilter":
+            proj.select_next_frame_event_filter()
+
+
+def test_stream_through_the_pipe(pipes):
+    """process_events: raw stream slices (both polarities) -> polarity filter -> trigger finder ->
+    process_ev_frame per projector frame; frames equal the oracle's segmentation + depth chain."""
+    proj, _ = pipes
+    tables, _ = load_golden_tables("default")
+    rng = np.random.default_rng(5)
+    stream = orc.synth_projector_stream(4, 14, 20_000, 640, 480)
+    stream["p"] = rng.random(len(stream)) < 0.8
+    want_frames = []
+    otf = orc.TriggerFinderOracle(60, lambda e: want_frames.append(e.copy()))
+    got = []
+    proj.frame_callback = got.append
+    proj.reset()
+    try:
+        for i in range(0, len(stream), 23_000):
+            part = stream[i : i + 23_000]
+            otf.process_events(part[part["p"] == 1])
+            proj.process_events(part)
+    finally:
+        proj.frame_callback = None
+    assert len(got) == len(want_frames) >= 5
+    for bgr, f in zip(got, want_frames):
+        assert np.array_equal(bgr, orc.colorize(orc.frame_disparity_map(tables, f, 0), tables.depth_scale, 0.1, 1.0))

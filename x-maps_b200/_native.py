@@ -106,6 +106,7 @@ SIGNATURES = {
     "xm_disp_to_depth": (C.c_int, [_P, _P, _I64, C.c_double, _P, _P]),
     "xm_colorize": (C.c_int, [_P, _P, _I64, C.c_double, C.c_float, C.c_float, _P, _P]),
     "xm_point_cloud": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P]),
+    "xm_polarity_filter": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "xm_filter_events": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P, _P, _P]),
     "xm_find_trigger": (C.c_int, [_P, _P, _I64, _I64, C.c_double, _I64, _P, _P]),
     "xm_build_xmap": (C.c_int, [C.c_int, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),

@@ -1382,6 +1382,30 @@ int ensure_stream_scratch(XmCtx* c) {
 }
 }  // namespace
 
+int xm_polarity_filter(XmCtx* c, const void* d_events, int64_t n, void* d_out, int64_t* d_count, void* stream) {
+    if (!c || n < 0 || !d_count || (n > 0 && (!d_events || !d_out))) return fail(XM_ERR_INVALID_ARG, "polarity_filter: bad arguments");
+    if (reinterpret_cast<uintptr_t>(d_events) & 15 || reinterpret_cast<uintptr_t>(d_out) & 15)
+        return fail(XM_ERR_INVALID_ARG, "event buffers must be 16-byte aligned");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n == 0) {
+        XM_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
+        return XM_OK;
+    }
+    const long long blocks = (n + xm::kCompactBlock - 1) / xm::kCompactBlock;
+    int rc = ensure_counts(c, blocks, s);
+    if (rc) return rc;
+    const xm::PolarityPred pred{static_cast<const int4*>(d_events)};
+    const xm::CopyEventEmit emit{static_cast<const int4*>(d_events), static_cast<int4*>(d_out)};
+    xm::flag_count_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(pred, n, c->d_counts);
+    XM_LAUNCHED();
+    xm::compact_scan_kernel<<<1, 1024, 0, s>>>(c->d_counts, blocks, reinterpret_cast<long long*>(d_count));
+    XM_LAUNCHED();
+    xm::flag_write_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(pred, emit, n, c->d_counts);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
 int xm_filter_events(XmCtx* c, const void* d_events, int64_t n, int32_t mode, const int16_t* d_x_rect, int32_t as_reference,
                      void* d_out, int64_t* d_count, void* stream) {
     if (!c || n < 0 || !d_count || (n > 0 && (!d_events || !d_out))) return fail(XM_ERR_INVALID_ARG, "filter: bad arguments");

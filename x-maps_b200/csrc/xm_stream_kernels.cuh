@@ -67,6 +67,20 @@ __global__ void __launch_bounds__(256) flag_write_kernel(const Pred pred, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// A0 materialised: PolarityFilterAlgorithm(1).process_events = events[events["p"] == 1], order kept
+// (python/depth_reprojection_pipe.py:43,114; restated in frame_event_filter.py:21)
+// ---------------------------------------------------------------------------------------------
+struct PolarityPred {
+    const int4* events;
+    __device__ __forceinline__ bool operator()(long long i) const { return unpack_event(ld_event_plain(events + i)).p == 1; }
+};
+struct CopyEventEmit {
+    const int4* events;
+    int4* out;
+    __device__ __forceinline__ void operator()(long long i, unsigned pos) const { out[pos] = ld_event_plain(events + i); }
+};
+
+// ---------------------------------------------------------------------------------------------
 // N4: de-duplication filters.  Key image of `rows` x `stride` cells; per cell the index of the first
 // and of the last event that hit it (atomicMin / atomicMax).  Modes as XM_FILTER_*.
 // ---------------------------------------------------------------------------------------------

@@ -247,6 +247,16 @@ class DepthEngine:
         }
 
     # ------------------------------------------------------------------ the rows next to the path
+    def polarity_filter(self, events) -> DeviceEvents:
+        """``events[events["p"] == 1]`` on the device, order preserved (the reference's Metavision
+        ``PolarityFilterAlgorithm(1)``, depth_reprojection_pipe.py:43,114)."""
+        ev = self.events(events)
+        n = len(ev)
+        out = torch.empty((max(n, 1), 4), dtype=torch.int32, device=self.device)
+        count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        N.check(N.lib.xm_polarity_filter(self._ctx, ev.raw.data_ptr() if n else None, n, out.data_ptr(), count.data_ptr(), self._stream()))
+        return DeviceEvents(out[: int(count.item())], ev.time_f64)
+
     def filter_events(self, events, mode: int, x_rect: Optional[torch.Tensor] = None, as_reference: bool = True) -> DeviceEvents:
         """One survivor per key (``frame_event_filter.py``'s filters, ``N.FILTER_*``) as a new device
         event buffer in row-major key order; see ``xm_filter_events`` in the header."""

@@ -16,7 +16,9 @@ from typing import Callable, Optional
 from .calibration import CamProjCalibrationParams, CamProjMaps
 from .depth import DisparityToDepth
 from .disparity import XMapsDisparity
+from .frame_event_filter import FrameEventFilterProcessor
 from .time_map import ProjectorTimeMap
+from .trigger_finder import RobustTriggerFinder
 
 
 @dataclass
@@ -73,13 +75,40 @@ class DepthFramePipeline:
             stats=self.stats_printer, calib_params=calib_params, calib_maps=self.calib_maps,
             z_near=params.z_near, z_far=params.z_far, return_host=return_host,
         )
+        # the rows either side of the path (depth_reprojection_pipe.py:97-105): per-frame de-duplication
+        # filter (NoFilter until select_next_frame_event_filter) and the frame segmentation of the stream
+        eng = self.calib_maps.engine()
+        self.ev_filter_proc = FrameEventFilterProcessor(engine=eng)
+        self.trigger_finder = RobustTriggerFinder(
+            projector_fps=params.projector_fps, stats=self.stats_printer, pool=None, frame_callback=self.process_ev_frame, engine=eng,
+        )
+
+    def process_events(self, evs):
+        """A slice of the continuous stream (depth_reprojection_pipe.py:108-119): polarity filter, then
+        the trigger finder, which calls process_ev_frame once per projector frame it finds.  (The
+        Metavision activity-noise filter of :116-117 is a closed binary and is not applied.)"""
+        pos = self.calib_maps.engine().polarity_filter(evs)
+        self.trigger_finder.process_events(pos)
+
+    def select_next_frame_event_filter(self):
+        return self.ev_filter_proc.select_next_filter()
+
+    def reset(self):
+        self.trigger_finder.reset()
 
     def process_ev_frame(self, evs):
         """One frame of (already polarity-filtered) events -> colourised depth frame; the call
-        sequence of depth_reprojection_pipe.py:121-167 (frame event filter = NoFilter)."""
+        sequence of depth_reprojection_pipe.py:121-167."""
         sp = self.stats_printer
         with sp.measure_time("ev rect"):
             ev_x_rect_i16, ev_y_rect_i16 = self.calib_maps.rectify_cam_coords_i16(evs)
+        with sp.measure_time("frame ev filter"):
+            filtered_evs = self.ev_filter_proc.filter_events(evs, ev_x_rect_i16)
+            if len(evs):
+                sp.add_metric("frame evs filtered out [%]", 100 - len(filtered_evs) / len(evs) * 100)
+            if len(filtered_evs) < len(evs):  # :137-139: the survivors are rectified again
+                ev_x_rect_i16, ev_y_rect_i16 = self.calib_maps.rectify_cam_coords_i16(filtered_evs)
+            evs = filtered_evs
         with sp.measure_time("x-maps disp"):
             ev_disparity_f32, inlier_mask = self.x_maps_disp.compute_event_disparity(
                 events=evs, ev_x_rect_i16=ev_x_rect_i16, ev_y_rect_i16=ev_y_rect_i16
