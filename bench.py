@@ -349,11 +349,18 @@ def run_ours(args):
     xmap_bytes = tables.x_map.size * 2
     k1_bytes = 16 * n + lut_bytes + xmap_bytes
     kernel_name = "xm::events_lean_kernel (K1: polarity + rectify LUT + X-map lookup + disparity + scatter)"
-    fused = bool(eng.get_option("fused")) and eng.get_option("k1_variant") == 2 and k2_us < 0.5
+    # one kernel per frame (fused frame kernel, or the batch kernel: one launch per chunk of frames)
+    fused = launches <= 1.5 * F * args.steps
     if fused:
         # one kernel per frame: K1's bytes + the remap table read + the depth frame written (B(N_in))
         k1_bytes += PROJ_W * PROJ_H * 4 * 2
         kernel_name = "xm::frame_kernel (whole frame: per-event phase + grid barrier + dilate/remap/depth epilogue)"
+        if eng.get_option("batch"):
+            kernel_name = "xm::batch_kernel (persistent: event chunks and epilogue tiles of up to 32 frames in one work list)"
+        # Consecutive frame kernels overlap (programmatic dependent launch), so the duration of a launch
+        # inside the step is the timed region divided by its launches; the CUDA-event bracket of region B
+        # breaks that overlap and is reported as the isolated figure.
+        k1_isolated_us, k1_us = k1_us, ms * 1e3 / (F * args.steps)
     achieved = k1_bytes / (k1_us * 1e-6) / 1e9 if k1_us > 0 else 0.0
     roofline = {
         "bound": "hbm",
@@ -366,6 +373,7 @@ def run_ours(args):
         "traffic": None,
         "bytes_per_launch": k1_bytes,
         "us_per_launch": k1_us,
+        "us_per_launch_isolated": k1_isolated_us if fused else k1_us,
         "k2_us_per_launch": k2_us,
         "frame_us": ms * 1e3 / (F * args.steps),
     }

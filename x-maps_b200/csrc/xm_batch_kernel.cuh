@@ -3,27 +3,27 @@
 // Frames do not depend on each other (python/depth_reprojection_pipe.py:121-167 keeps no state across
 // frames), so a batch of them can be rendered by one grid that never drains between frames:
 //
-//   * All work of the batch is ONE ordered list of items handed out by a global counter.  An item is
-//     either an event chunk (kEvChunk records of one frame) or an epilogue tile (32x32 output pixels of
-//     one frame; camera view: 4096 pixels).  "Slot" s of the list holds the chunks of frame s with the
-//     tiles of frame s-1 interleaved into its middle half, so the epilogue of a frame runs on the same
-//     SMs, at the same time, as the event stream of the next one: HBM streaming, L2 gathers and the
-//     shared-memory dilation overlap instead of alternating, and there is no launch, drain or pipeline
-//     fill per frame.
-//   * Every CTA is the lean warp-specialised pipeline of events_lean_kernel: one producer lane takes
-//     items from the counter and feeds an mbarrier ring (TMA bulk copies of the chunk and of its X-map
-//     window; a tile is just a descriptor in the ring), eight consumer warps work through the ring in
-//     order.  The producer takes its items TWO ahead and reads the first / last timestamp of a chunk
-//     ONE ahead, so neither the atomic's nor the loads' round trip sits on its critical path.
+//   * Every CTA has two kinds of warps that never wait for each other inside a frame:
+//       - the lean warp-specialised event pipeline of events_lean_kernel (one producer lane, eight
+//         consumer warps, mbarrier ring fed by TMA bulk copies of the chunks and of their X-map windows).
+//         All chunks of the batch form ONE ordered list handed out by a global counter; the producer takes
+//         its chunks TWO ahead and reads a chunk's first / last timestamp ONE ahead;
+//       - kTileWarps epilogue warps in groups of kTileGroupThreads threads.  A group takes 32x32 output
+//         tiles (camera view: 4096 pixels) of frame f from that frame's ticket counter as soon as every
+//         chunk of frame f has been scattered, then moves on to frame f+1.
+//     So the epilogue of a frame runs on the same SMs, at the same time, as the event stream of the next
+//     frames: HBM streaming, L2 gathers and the shared-memory dilation overlap instead of alternating, and
+//     there is no launch, drain or pipeline fill per frame.  (A first version let the eight consumer warps
+//     execute the tiles in line: a tile is a chain of four barrier-separated phases, ~8 us during which
+//     the CTA's event stream stood still -- slower than separate kernels, see EXPERIMENTS_r01.md.)
 //   * A tile of frame f may only read the scatter map once every chunk of frame f has been scattered.
 //     Each CTA counts the chunks it finished per frame and publishes the count (after a fence) when its
-//     consumers leave the frame; a tile item spins until the frame's count is complete.  Items are taken
-//     in list order and a tile only ever waits for items earlier in the list, so this cannot deadlock,
-//     and because the tiles of frame f start a quarter of a frame after its last chunk was handed out
-//     the wait is normally already over.
+//     consumers leave the frame; the tile groups spin on the frame's count.  A chunk only ever waits for
+//     tiles of an earlier frame and a tile only for chunks of its own frame, and chunks are handed out in
+//     frame order, so this cannot deadlock.
 //   * Frames rotate through kBatchMaps scatter maps (epoch-tagged keys as everywhere else), so the
 //     events of frame f+1 and f+2 never disturb the cells frame f's tiles still have to read; the
-//     first chunk of frame f+3 a CTA sees waits for frame f's tile count (long complete for real frames).
+//     first chunk of frame f+3 a warp sees waits for frame f's finished-tile count.
 //   * Time bounds: batch_bounds_kernel (one tiny launch per batch) looks up first / last valid event
 //     of every frame.  Events outside the assumed bounds flag their frame; batch_redo_kernel (one tiny
 //     launch per batch) re-renders flagged frames exactly (device-side tail launches of the two-pass
@@ -37,6 +37,10 @@ constexpr int kBatchMax = 32;    // frames per launch (the frame table travels i
 constexpr int kBatchMaps = 3;    // scatter maps in rotation
 constexpr int kBatchHeader = 768;  // mbarriers, ring descriptors, CTA accumulators, per-warp frame constants
 constexpr int kCamTilePx = 4096;  // camera-view epilogue item
+constexpr int kTileWarps = 4;             // epilogue warps per CTA
+constexpr int kTileGroupThreads = 64;     // threads that share one tile
+constexpr int kTileGroups = kTileWarps * 32 / kTileGroupThreads;
+constexpr int kBatchThreads = kWsThreads + kTileWarps * 32;
 
 struct BatchFrame {
     const int4* events;
@@ -63,16 +67,15 @@ struct BatchParams {
     int n_frames;
     int debug;  // timing experiments only (results WRONG): 16 = skip the epilogue work of tile items
     unsigned total_items;
-    unsigned first_item[kBatchMax + 2];  // first item of slot s (slot n_frames holds the last frame's tiles)
+    unsigned first_item[kBatchMax + 2];  // first chunk of frame f in the batch-wide chunk list; [n_frames] = total
     BatchFrame frames[kBatchMax];
 };
 
 __host__ __device__ __forceinline__ unsigned batch_chunks(long long n) { return static_cast<unsigned>((n + kEvChunk - 1) / kEvChunk); }
 
 inline int batch_smem_bytes(int stages, int win_stages, int win_bytes, int region_cells) {
-    int lut_tile = region_cells * 4;  // the tile's two u16 regions alias the LUT double buffer (+ extra)
-    if (lut_tile < kEvLutBytes) lut_tile = kEvLutBytes;
-    return kBatchHeader + lut_tile + stages * (kEvChunk * 16) + win_stages * win_bytes;
+    // header | LUT double buffer | event ring | X-map window ring | two u16 regions per tile group
+    return kBatchHeader + kEvLutBytes + stages * (kEvChunk * 16) + win_stages * win_bytes + kTileGroups * region_cells * 4;
 }
 
 struct BatchBoundsParams {
@@ -117,6 +120,9 @@ __global__ void __launch_bounds__(64) batch_bounds_kernel(const __grid_constant_
     scan_sorted_bounds(p.events[f], p.n[f], p.polarity, threadIdx.x >> 5, threadIdx.x & 31, &st->t_lo_bits);
 }
 
+// release fence for the "data, then counter" hand-offs below (lighter than __threadfence(), which is fence.sc)
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 __device__ __forceinline__ long long ld_time_nc(const int4* ev) {
     long long t;
     asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(t) : "l"(reinterpret_cast<const char*>(ev) + 8));
@@ -131,10 +137,11 @@ __device__ __forceinline__ int2 lds64_a(unsigned addr) {
     return r;
 }
 
-// One epilogue item of frame f, executed by the kEvThreads consumer threads (kept out of line so that
-// its registers do not weigh on the per-event loop).
+// One epilogue item of frame f, executed by one group of kTileGroupThreads threads (`tid` inside the
+// group, named barrier `bar_id`).
 template <bool CAM>
-static __device__ __noinline__ void batch_tile(const BatchParams& bp, int f, int t, unsigned short* bufA, unsigned short* bufB, int tid) {
+static __device__ __noinline__ void batch_tile(const BatchParams& bp, int f, int t, unsigned short* bufA, unsigned short* bufB, int tid,
+                                               int bar_id) {
     const unsigned epoch = bp.epoch0 + static_cast<unsigned>(f);
     if (bp.debug & 16) {
         // timing experiment: no epilogue work (results WRONG)
@@ -142,19 +149,19 @@ static __device__ __noinline__ void batch_tile(const BatchParams& bp, int f, int
         const unsigned long long* mp = bp.maps[f % kBatchMaps];
         const int n_px = bp.ep.out_w * bp.ep.out_h;
         const int end = min(n_px, (t + 1) * kCamTilePx);
-        for (int i = t * kCamTilePx + tid; i < end; i += kEvThreads)
+        for (int i = t * kCamTilePx + tid; i < end; i += kTileGroupThreads)
             emit_pixel_int(bp.ep.out, bp.frames[f].dst, i, key_disparity(__ldcg(mp + i), epoch));
     } else {
         EpilogueParams q = bp.ep;
         q.map = bp.maps[f % kBatchMaps];
         q.dst = bp.frames[f].dst;
         const int by = t / bp.tiles_x;
-        proj7_tile<kEvThreads, 3>(q, t - by * bp.tiles_x, by, bp.tiles_x, epoch, bufA, bufB, tid, 1);
+        proj7_tile<kTileGroupThreads, 3>(q, t - by * bp.tiles_x, by, bp.tiles_x, epoch, bufA, bufB, tid, bar_id);
     }
 }
 
 template <bool CAM>
-__global__ void __launch_bounds__(kWsThreads, 3) batch_kernel(const __grid_constant__ BatchParams bp) {
+__global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_constant__ BatchParams bp) {
     extern __shared__ __align__(128) unsigned char ev_smem[];
     uint64_t* full_ev = reinterpret_cast<uint64_t*>(ev_smem);
     uint64_t* empty_ev = reinterpret_cast<uint64_t*>(ev_smem + 32);
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) batch_kernel(const __grid_const
     int2* win_meta = reinterpret_cast<int2*>(ev_smem + 128);  // [4] (first column, count) of a window stage
     int2* ev_meta = reinterpret_cast<int2*>(ev_smem + 160);   // [4] (kind << 16 | frame, chunk or tile index); x < 0: end
     unsigned* s_acc = reinterpret_cast<unsigned*>(ev_smem + 192);  // [8][4] per-frame CTA accumulators: valid, inliers, flags, warps
-    const int lut_tile = max(bp.ep.region_cap * 4, kEvLutBytes);
+    constexpr int lut_tile = kEvLutBytes;
     unsigned char* ring = ev_smem + kBatchHeader + lut_tile;
     const int win_bytes = bp.cap_cols * bp.col_stride * 2;
     unsigned char* win_ring = ring + bp.stages * (kEvChunk * 16);
@@ -186,6 +193,37 @@ __global__ void __launch_bounds__(kWsThreads, 3) batch_kernel(const __grid_const
     if (tid < 32) s_acc[tid] = 0u;
     __syncthreads();
 
+    if (warp > kEvThreads / 32) {
+        // ---- epilogue groups ----------------------------------------------------------------------
+        const int grp = (tid - kWsThreads) / kTileGroupThreads, gtid = (tid - kWsThreads) % kTileGroupThreads;
+        unsigned short* bufA = reinterpret_cast<unsigned short*>(win_ring + bp.win_stages * win_bytes) + grp * (2 * bp.ep.region_cap);
+        unsigned short* bufB = bufA + bp.ep.region_cap;
+        volatile int* s_ticket = reinterpret_cast<volatile int*>(ev_smem + 704) + grp;
+        const int bar_id = 1 + grp;
+        const int n_tiles = bp.tile_items;
+        for (int f = 0; f < B; ++f) {
+            FrameState* st = bp.states + f;
+            if (gtid == 0) {
+                const unsigned need = batch_chunks(bp.frames[f].n);
+                while (ld_acquire_u32(&st->blocks_done) < need) __nanosleep(200);
+            }
+            for (;;) {
+                group_sync<kTileGroupThreads>(bar_id);  // the previous tile is done with the buffers / the frame is complete
+                if (gtid == 0) *s_ticket = static_cast<int>(atomicAdd(&st->fix_chunk, 1u));
+                group_sync<kTileGroupThreads>(bar_id);
+                const int t = *s_ticket;
+                if (t >= n_tiles) break;
+                batch_tile<CAM>(bp, f, t, bufA, bufB, gtid, bar_id);
+                group_sync<kTileGroupThreads>(bar_id);
+                if (gtid == 0) {
+                    __threadfence();
+                    atomicAdd(&st->next_tile, 1u);  // this tile no longer needs the frame's scatter map
+                }
+            }
+        }
+        return;
+    }
+
     if (producer) {
         if (lane != 0) return;
         // ---- producer lane ------------------------------------------------------------------------
@@ -193,41 +231,22 @@ __global__ void __launch_bounds__(kWsThreads, 3) batch_kernel(const __grid_const
         unsigned pe = 0, pw = 0;
         int issued = 0;
         const uint64_t pol = make_evict_first_policy();
-        // slot decoding state (items arrive in increasing order)
+        // chunk -> (frame, chunk index inside the frame); x = -1: past the end (chunks arrive in increasing order)
         int slot = 0;
         unsigned s_first = bp.first_item[0], s_next = bp.first_item[1];
-        unsigned sC = 0, sP = 0, sA = 0, sR = 0;
-        auto load_slot = [&]() {
-            sC = slot < B ? batch_chunks(bp.frames[slot].n) : 0u;
-            sP = slot >= 1 ? static_cast<unsigned>(bp.tile_items) : 0u;
-            sR = sP ? (sC / 2u) / sP : 0u;
-            sA = sR ? sC / 4u : sC;
-        };
-        load_slot();
-        // item -> (kind << 16 | frame, index); x = -1: past the end
         auto decode = [&](unsigned it) -> int2 {
             if (it >= bp.total_items) return make_int2(-1, 0);
             while (it >= s_next) {
                 ++slot;
                 s_first = s_next;
                 s_next = bp.first_item[slot + 1];
-                load_slot();
             }
-            unsigned j = it - s_first;
-            if (j < sA) return make_int2(slot, static_cast<int>(j));
-            j -= sA;
-            const unsigned period = sR + 1u;
-            if (j < sP * period) {
-                const unsigned q = j / period, m = j - q * period;
-                if (m == 0u) return make_int2((1 << 16) | (slot - 1), static_cast<int>(q));
-                return make_int2(slot, static_cast<int>(sA + q * sR + m - 1u));
-            }
-            return make_int2(slot, static_cast<int>(sA + sP * sR + (j - sP * period)));
+            return make_int2(slot, static_cast<int>(it - s_first));
         };
         // first / last timestamp of a chunk (loads only; consumed one iteration later)
         auto fetch_ts = [&](const int2& d, long long& ta, long long& tb) {
             ta = tb = 0;
-            if (d.x < 0 || (d.x >> 16)) return;
+            if (d.x < 0) return;
             const BatchFrame& fr = bp.frames[d.x];
             const long long first = static_cast<long long>(d.y) * kEvChunk;
             const long long last = min(fr.n, first + kEvChunk) - 1;
@@ -253,8 +272,8 @@ __global__ void __launch_bounds__(kWsThreads, 3) batch_kernel(const __grid_const
 
             if (issued >= bp.stages) mbar_wait(empty_ev + se, pe);
             ev_meta[se] = dA;
-            if (dA.x < 0 || (dA.x >> 16)) {
-                mbar_arrive(full_ev + se);  // descriptor only (tile / end)
+            if (dA.x < 0) {
+                mbar_arrive(full_ev + se);  // descriptor only (end of the batch)
             } else {
                 const BatchFrame& fr = bp.frames[dA.x];
                 const long long first = static_cast<long long>(dA.y) * kEvChunk;
@@ -268,7 +287,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) batch_kernel(const __grid_const
                 if (issued > bp.stages) pe ^= 1u;
             }
             if (dA.x < 0) break;
-            if (!(dA.x >> 16) && bp.cap_cols > 0) {
+            if (bp.cap_cols > 0) {
                 // X-map window: the columns between the chunk's first and last record
                 if (dA.x != tc_frame) {
                     tc_frame = dA.x;
@@ -333,7 +352,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) batch_kernel(const __grid_const
         n_valid = __reduce_add_sync(0xffffffffu, n_valid);
         n_inl = __reduce_add_sync(0xffffffffu, n_inl);
         flags = __reduce_or_sync(0xffffffffu, flags);
-        __threadfence();  // every lane: its scatter atomics are ordered before the counts below
+        fence_acq_rel_gpu();  // every lane: its scatter atomics are ordered before the counts below
         __syncwarp();
         if (lane == 0) {
             unsigned* acc = s_acc + (cur_f & 7) * 4;
@@ -349,7 +368,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) batch_kernel(const __grid_const
                 if (v) atomicAdd(&st->n_valid, static_cast<unsigned long long>(v));
                 if (i) atomicAdd(&st->n_inliers, static_cast<unsigned long long>(i));
                 if (fl) atomicOr(&st->flags, fl);
-                __threadfence();
+                fence_acq_rel_gpu();
                 atomicAdd(&st->blocks_done, my_chunks);
             }
         }
@@ -536,32 +555,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) batch_kernel(const __grid_const
     int2 m = peek();
     for (;;) {
         if (m.x < 0) break;
-        const int f = m.x & 0xffff;
-        if (m.x >> 16) {
-            // ---- epilogue tile m.y of frame f ---------------------------------------------------------
-            const int t = m.y;
-            release();
-            if (cur_f >= 0 && cur_f <= f) leave_frame();
-            // all consumers are done with the LUT buffers (the tile regions alias them) and have left frame f
-            group_sync<kEvThreads>(1);
-            if (tid == 0) {
-                const unsigned need = batch_chunks(bp.frames[f].n);
-                const unsigned* done = &bp.states[f].blocks_done;
-                while (ld_acquire_u32(done) < need) __nanosleep(64);
-            }
-            group_sync<kEvThreads>(1);
-            {
-                unsigned short* bufA = reinterpret_cast<unsigned short*>(ev_smem + kBatchHeader);
-                batch_tile<CAM>(bp, f, t, bufA, bufA + bp.ep.region_cap, tid);
-            }
-            group_sync<kEvThreads>(1);  // the regions are free again before anyone starts LUT gathers
-            if (tid == 0) {
-                __threadfence();
-                atomicAdd(&bp.states[f].next_tile, 1u);  // this tile no longer needs the frame's scatter map
-            }
-            m = peek();
-            continue;
-        }
+        const int f = m.x;
         // ---- a run of chunks of frame f -------------------------------------------------------------------
         if (f != cur_f) enter_frame(f);
         int col_cur[kEvPerThread], pix_cur[kEvPerThread];

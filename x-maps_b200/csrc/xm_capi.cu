@@ -113,9 +113,8 @@ struct XmCtx {
     int opt_k2_variant = 1;   // 1: sliding-window epilogue (7x7, even rect_w), 0: per-tap epilogue
     int opt_fused = 1;        // 1: one fused kernel per frame where the lean path applies
     int fused_occ = 0;        // resident CTAs per SM of frame_kernel
-    int opt_batch = 0;        // 1: xm_frame_batch renders uniform batches with one persistent kernel per <= 32 frames
-                              //    (bit-exact; measured 8 % slower than the fused per-frame kernels on B200, so opt-in:
-                              //    profiles/EXPERIMENTS_r01.md "batch kernel")
+    int opt_batch = 1;        // 1: xm_frame_batch renders uniform batches with one persistent kernel per <= 32 frames
+                              //    (event warps + dedicated epilogue warps; 47 vs 57 us per 5 M-event frame, EXPERIMENTS_r01.md)
     int batch_occ = 0, batch_smem = 0, batch_cols = 0;  // launch configuration of batch_kernel
     unsigned long long* d_map_ring[xm::kBatchMaps] = {nullptr, nullptr, nullptr};  // [0] = d_map
     xm::FrameState* d_bstate = nullptr;  // [kBatchMax + 1] state blocks of the current batch
@@ -263,13 +262,14 @@ int configure_event_kernels(XmCtx* c) {
         }
         c->fused_occ = occ_min;
     }
-    // batch kernel: same pipeline plus the tile regions; keep 3 CTAs below the 196 KB shared-memory
-    // carve-out (above it the L1 shrinks to 28 KB and the LUT gathers slow down by 1.5x, EXPERIMENTS_r01.md)
+    // batch kernel: the same pipeline plus epilogue warp groups with their own tile regions, 2 CTAs per SM
+    // (416 threads x 72 registers); keep them below the 196 KB shared-memory carve-out (above it the L1
+    // shrinks to 28 KB and the LUT gathers slow down by 1.5x, EXPERIMENTS_r01.md)
     c->batch_occ = 0;
     if (variant == 2) {
         int bcols = cols;
         auto smem_for = [&](int k) { return xm::batch_smem_bytes(c->opt_stages, c->opt_win_stages, k * c->col_stride * 2, c->opt_region_cells); };
-        while (bcols > 0 && 3 * (smem_for(bcols) + 1024) > 196 * 1024) --bcols;
+        while (bcols > 0 && 2 * (smem_for(bcols) + 1024) > 196 * 1024) --bcols;
         c->batch_cols = bcols;
         c->batch_smem = smem_for(bcols);
         int occ_min = 1 << 30;
@@ -284,7 +284,7 @@ int configure_event_kernels(XmCtx* c) {
             }
             XM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
             int occ = 0;
-            XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, xm::kWsThreads, c->batch_smem));
+            XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, xm::kBatchThreads, c->batch_smem));
             occ_min = occ < occ_min ? occ : occ_min;
         }
         c->batch_occ = occ_min;
@@ -686,12 +686,11 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     bp.n_frames = n;
     bp.debug = c->opt_debug;
     unsigned items = 0;
-    for (int sl = 0; sl <= n; ++sl) {
-        bp.first_item[sl] = items;
-        if (sl < n) items += xm::batch_chunks(a[sl].n_events);
-        if (sl >= 1) items += static_cast<unsigned>(bp.tile_items);
+    for (int f = 0; f < n; ++f) {
+        bp.first_item[f] = items;
+        items += xm::batch_chunks(a[f].n_events);
     }
-    bp.first_item[n + 1] = items;
+    bp.first_item[n] = bp.first_item[n + 1] = items;
     bp.total_items = items;
     for (int f = 0; f < n; ++f) {
         bp.frames[f].events = static_cast<const int4*>(a[f].d_events);
@@ -699,7 +698,10 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
         bp.frames[f].n = a[f].n_events;
     }
     const int occ = c->opt_ctas_per_sm > 0 && c->opt_ctas_per_sm < c->batch_occ ? c->opt_ctas_per_sm : c->batch_occ;
-    long long want = (static_cast<long long>(items) + 1) / 2;  // no more CTAs than (pairs of) items
+    // no more CTAs than there is work: a CTA takes chunks in pairs and runs kTileGroups tiles at a time
+    long long want = (static_cast<long long>(items) + 1) / 2;
+    const long long want_tiles = (static_cast<long long>(bp.tile_items) + xm::kTileGroups - 1) / xm::kTileGroups;
+    if (want_tiles > want) want = want_tiles;
     int grid = c->sm_count * occ;
     if (want < grid) grid = static_cast<int>(want < 1 ? 1 : want);
     if (c->opt_profile) {
@@ -707,9 +709,9 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
         if (rc) return rc;
     }
     if (cam)
-        xm::batch_kernel<true><<<grid, xm::kWsThreads, c->batch_smem, s>>>(bp);
+        xm::batch_kernel<true><<<grid, xm::kBatchThreads, c->batch_smem, s>>>(bp);
     else
-        xm::batch_kernel<false><<<grid, xm::kWsThreads, c->batch_smem, s>>>(bp);
+        xm::batch_kernel<false><<<grid, xm::kBatchThreads, c->batch_smem, s>>>(bp);
     XM_LAUNCHED();
     if (c->opt_profile) {
         int rc = profile_mark(c, s);
