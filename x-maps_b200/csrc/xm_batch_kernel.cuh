@@ -156,7 +156,7 @@ static __device__ __noinline__ void batch_tile(const BatchParams& bp, int f, int
         q.map = bp.maps[f % kBatchMaps];
         q.dst = bp.frames[f].dst;
         const int by = t / bp.tiles_x;
-        proj7_tile<kTileGroupThreads, 3>(q, t - by * bp.tiles_x, by, bp.tiles_x, epoch, bufA, bufB, tid, bar_id);
+        proj7_tile_late<kTileGroupThreads, 6, 8>(q, t - by * bp.tiles_x, by, bp.tiles_x, epoch, bufA, bufB, tid, bar_id);
     }
 }
 
@@ -203,20 +203,26 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
         const int n_tiles = bp.tile_items;
         for (int f = 0; f < B; ++f) {
             FrameState* st = bp.states + f;
+            int next_ticket = 0;
             if (gtid == 0) {
                 const unsigned need = batch_chunks(bp.frames[f].n);
                 while (ld_acquire_u32(&st->blocks_done) < need) __nanosleep(200);
+                next_ticket = static_cast<int>(atomicAdd(&st->fix_chunk, 1u));
             }
             for (;;) {
                 group_sync<kTileGroupThreads>(bar_id);  // the previous tile is done with the buffers / the frame is complete
-                if (gtid == 0) *s_ticket = static_cast<int>(atomicAdd(&st->fix_chunk, 1u));
+                if (gtid == 0) {
+                    *s_ticket = next_ticket;
+                    // the ticket after this one is requested now and read after the tile: its round trip is hidden
+                    if (next_ticket < n_tiles) next_ticket = static_cast<int>(atomicAdd(&st->fix_chunk, 1u));
+                }
                 group_sync<kTileGroupThreads>(bar_id);
                 const int t = *s_ticket;
                 if (t >= n_tiles) break;
                 batch_tile<CAM>(bp, f, t, bufA, bufB, gtid, bar_id);
                 group_sync<kTileGroupThreads>(bar_id);
                 if (gtid == 0) {
-                    __threadfence();
+                    fence_acq_rel_gpu();
                     atomicAdd(&st->next_tile, 1u);  // this tile no longer needs the frame's scatter map
                 }
             }

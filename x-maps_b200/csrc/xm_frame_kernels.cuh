@@ -1458,36 +1458,36 @@ __device__ __forceinline__ void group_sync(int bar_id) {
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT) : "memory");
 }
 
-template <int NT, int UA = 1>
-__device__ __forceinline__ void proj7_tile(const EpilogueParams& p, int bx, int by, int tiles_x, unsigned epoch, unsigned short* bufA,
-                                           unsigned short* bufB, int gtid, int bar_id) {
+// Geometry of a tile's source region in shared memory.
+struct TileRegion {
+    int rx0, ry0, rw, rh, stride;
+    bool any;   // the tile maps into the rectified image at all
+    bool fits;  // the region fits the shared-memory buffers (else: direct 49-tap reads)
+};
+
+__device__ __forceinline__ TileRegion tile_region(const EpilogueParams& p, const short4& box) {
     constexpr int R = 3;
-    constexpr int PX = kTile * kTile / NT;  // output pixels per thread
-    constexpr int ROWS = NT / 32;           // tile rows covered by one pass of the group
-    const int tid = gtid;
-    const int lane = gtid & 31, warp = gtid >> 5;
-    const int u0 = bx * kTile, v0 = by * kTile;
-
-    const short4 box = __ldg(p.tile_box + by * tiles_x + bx);
+    TileRegion g;
     const int x0 = box.x, y0 = box.y, x1 = box.z, y1 = box.w;
+    g.any = x1 >= 0;
+    g.rx0 = (x0 - R) & ~1;               // even
+    g.rw = (x1 + R - g.rx0 + 2) & ~1;    // even number of data cells
+    g.ry0 = y0 - R;
+    g.rh = y1 - y0 + 1 + 2 * R;
+    g.stride = g.rw + kRowExtra;         // cells per shared-memory row
+    g.fits = g.any && g.stride * g.rh <= p.region_cap;
+    return g;
+}
 
-    short2 m[PX];
-#pragma unroll
-    for (int k = 0; k < PX; ++k) {
-        const int u = u0 + lane, v = v0 + warp + k * ROWS;
-        m[k] = make_short2(-1, -1);
-        if (u < p.out_w && v < p.out_h) m[k] = __ldg(p.remap_xy + v * p.out_w + u);
-    }
-
-    int val[PX];
-#pragma unroll
-    for (int k = 0; k < PX; ++k) val[k] = 0;
-    if (x1 >= 0) {
-        const int rx0 = (x0 - R) & ~1;                 // even
-        const int rw = (x1 + R - rx0 + 2) & ~1;        // even number of data cells
-        const int ry0 = y0 - R, rh = y1 - y0 + 1 + 2 * R;
-        const int stride = rw + kRowExtra;             // cells per shared-memory row
-        if (stride * rh <= p.region_cap) {
+// Phases A-C for a region that fits: afterwards bufA holds the 7x7-dilated disparities of the region
+// (row stride g.stride, kRowPad zero cells left of the data); ends with a group barrier.
+template <int NT, int UA>
+__device__ __forceinline__ void proj7_dilate_region(const EpilogueParams& p, const TileRegion& g, unsigned epoch, unsigned short* bufA,
+                                                    unsigned short* bufB, int tid, int bar_id) {
+    constexpr int R = 3;
+    const int rx0 = g.rx0, ry0 = g.ry0, rw = g.rw, rh = g.rh, stride = g.stride;
+    {
+        {
             // ---- A: decode the region (pads included, written as zeros) -------------------------
             {
                 const int pairs = stride >> 1;
@@ -1581,33 +1581,84 @@ __device__ __forceinline__ void proj7_tile(const EpilogueParams& p, int bx, int 
                 }
             }
             group_sync<NT>(bar_id);
-            // ---- D: gather ----------------------------------------------------------------------------
-#pragma unroll
-            for (int k = 0; k < PX; ++k)
-                if (m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h)
-                    val[k] = bufA[(m[k].y - ry0) * stride + (m[k].x - rx0) + kRowPad];
-        } else {
-#pragma unroll
-            for (int k = 0; k < PX; ++k) {
-                if (!(m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h)) continue;
-                int best = 0;
-                for (int dy = -R; dy <= R; ++dy) {
-                    const int gy = m[k].y + dy;
-                    if (gy < 0 || gy >= p.rect_h) continue;
-                    for (int dx = -R; dx <= R; ++dx) {
-                        const int gx = m[k].x + dx;
-                        if (gx < 0 || gx >= p.rect_w) continue;
-                        best = max(best, key_disparity(p.map[gy * p.rect_w + gx], epoch));
-                    }
-                }
-                val[k] = best;
-            }
         }
     }
+}
+
+// 49-tap fallback for one pixel (regions that do not fit the buffers)
+__device__ __forceinline__ int proj7_direct(const EpilogueParams& p, const short2 m, unsigned epoch) {
+    constexpr int R = 3;
+    int best = 0;
+    for (int dy = -R; dy <= R; ++dy) {
+        const int gy = m.y + dy;
+        if (gy < 0 || gy >= p.rect_h) continue;
+        for (int dx = -R; dx <= R; ++dx) {
+            const int gx = m.x + dx;
+            if (gx < 0 || gx >= p.rect_w) continue;
+            best = max(best, key_disparity(p.map[gy * p.rect_w + gx], epoch));
+        }
+    }
+    return best;
+}
+
+template <int NT, int UA = 1>
+__device__ __forceinline__ void proj7_tile(const EpilogueParams& p, int bx, int by, int tiles_x, unsigned epoch, unsigned short* bufA,
+                                           unsigned short* bufB, int gtid, int bar_id) {
+    constexpr int PX = kTile * kTile / NT;  // output pixels per thread
+    constexpr int ROWS = NT / 32;           // tile rows covered by one pass of the group
+    const int lane = gtid & 31, warp = gtid >> 5;
+    const int u0 = bx * kTile, v0 = by * kTile;
+    const TileRegion g = tile_region(p, __ldg(p.tile_box + by * tiles_x + bx));
+
+    // the remap coordinates are requested before the region work and used after it
+    short2 m[PX];
 #pragma unroll
     for (int k = 0; k < PX; ++k) {
         const int u = u0 + lane, v = v0 + warp + k * ROWS;
-        if (u < p.out_w && v < p.out_h) emit_pixel_int(p.out, p.dst, v * p.out_w + u, val[k]);
+        m[k] = make_short2(-1, -1);
+        if (u < p.out_w && v < p.out_h) m[k] = __ldg(p.remap_xy + v * p.out_w + u);
+    }
+    if (g.fits) proj7_dilate_region<NT, UA>(p, g, epoch, bufA, bufB, gtid, bar_id);
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+        int val = 0;
+        if (g.any && m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h)
+            val = g.fits ? bufA[(m[k].y - g.ry0) * g.stride + (m[k].x - g.rx0) + kRowPad] : proj7_direct(p, m[k], epoch);
+        const int u = u0 + lane, v = v0 + warp + k * ROWS;
+        if (u < p.out_w && v < p.out_h) emit_pixel_int(p.out, p.dst, v * p.out_w + u, val);
+    }
+}
+
+// Same tile for a small group inside a register-tight kernel (batch_kernel's epilogue warps): the remap
+// coordinates are loaded AFTER the region work, PXB pixels at a time, so nothing but the region geometry
+// is live across phases A-C and the region loads can be issued UA at a time without spilling.
+template <int NT, int UA, int PXB>
+__device__ __forceinline__ void proj7_tile_late(const EpilogueParams& p, int bx, int by, int tiles_x, unsigned epoch, unsigned short* bufA,
+                                                unsigned short* bufB, int gtid, int bar_id) {
+    constexpr int PX = kTile * kTile / NT;
+    constexpr int ROWS = NT / 32;
+    static_assert(PX % PXB == 0, "pixel batch must divide the pixels per thread");
+    const int lane = gtid & 31, warp = gtid >> 5;
+    const int u0 = bx * kTile, v0 = by * kTile;
+    const TileRegion g = tile_region(p, __ldg(p.tile_box + by * tiles_x + bx));
+    if (g.fits) proj7_dilate_region<NT, UA>(p, g, epoch, bufA, bufB, gtid, bar_id);
+    const int u = u0 + lane;
+    for (int k0 = 0; k0 < PX; k0 += PXB) {
+        short2 m[PXB];
+#pragma unroll
+        for (int j = 0; j < PXB; ++j) {
+            const int v = v0 + warp + (k0 + j) * ROWS;
+            m[j] = make_short2(-1, -1);
+            if (u < p.out_w && v < p.out_h) m[j] = __ldg(p.remap_xy + v * p.out_w + u);
+        }
+#pragma unroll
+        for (int j = 0; j < PXB; ++j) {
+            int val = 0;
+            if (g.any && m[j].x >= 0 && m[j].x < p.rect_w && m[j].y >= 0 && m[j].y < p.rect_h)
+                val = g.fits ? bufA[(m[j].y - g.ry0) * g.stride + (m[j].x - g.rx0) + kRowPad] : proj7_direct(p, m[j], epoch);
+            const int v = v0 + warp + (k0 + j) * ROWS;
+            if (u < p.out_w && v < p.out_h) emit_pixel_int(p.out, p.dst, v * p.out_w + u, val);
+        }
     }
 }
 
