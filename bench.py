@@ -349,19 +349,27 @@ def run_ours(args):
     xmap_bytes = tables.x_map.size * 2
     k1_bytes = 16 * n + lut_bytes + xmap_bytes
     kernel_name = "xm::events_lean_kernel (K1: polarity + rectify LUT + X-map lookup + disparity + scatter)"
-    # one kernel per frame (fused frame kernel, or the batch kernel: one launch per chunk of frames)
+    prof_launches = max(1, eng.get_option("profile_launches"))
+    frames_per_launch = max(1, round(pf / prof_launches))
+    # one kernel per frame (fused frame kernel) or per chunk of frames (batch kernel)?
     fused = launches <= 1.5 * F * args.steps
+    batch = fused and frames_per_launch > 1
+    traffic_file = "k1_dram_bytes.json"
     if fused:
-        # one kernel per frame: K1's bytes + the remap table read + the depth frame written (B(N_in))
+        # whole-frame kernels: K1's bytes + the remap table read + the depth frame written (B(N_in))
         k1_bytes += PROJ_W * PROJ_H * 4 * 2
-        kernel_name = "xm::frame_kernel (whole frame: per-event phase + grid barrier + dilate/remap/depth epilogue)"
-        if eng.get_option("batch"):
-            kernel_name = "xm::batch_kernel (persistent: event chunks and epilogue tiles of up to 32 frames in one work list)"
-        # Consecutive frame kernels overlap (programmatic dependent launch), so the duration of a launch
-        # inside the step is the timed region divided by its launches; the CUDA-event bracket of region B
-        # breaks that overlap and is reported as the isolated figure.
-        k1_isolated_us, k1_us = k1_us, ms * 1e3 / (F * args.steps)
-    achieved = k1_bytes / (k1_us * 1e-6) / 1e9 if k1_us > 0 else 0.0
+        traffic_file = "frame_dram_bytes.json"
+        if batch:
+            kernel_name = "xm::batch_kernel (persistent: event warps + epilogue warp groups, %d frames per launch)" % frames_per_launch
+        else:
+            kernel_name = "xm::frame_kernel (whole frame: per-event phase + grid barrier + dilate/remap/depth epilogue)"
+    # duration of one launch of the dominant kernel: CUDA events around every launch (region B).  Consecutive
+    # frame_kernel launches overlap through programmatic dependent launch, which the event records break,
+    # so for that kernel the timed region divided by its launches is the in-step figure.
+    bytes_per_launch = k1_bytes * frames_per_launch
+    us_isolated = k1_us * frames_per_launch
+    us_per_launch = ms * 1e3 / (F * args.steps) if (fused and not batch) else us_isolated
+    achieved = bytes_per_launch / (us_per_launch * 1e-6) / 1e9 if us_per_launch > 0 else 0.0
     roofline = {
         "bound": "hbm",
         "kernel": kernel_name,
@@ -371,23 +379,28 @@ def run_ours(args):
         "unit": "GB/s",
         "frac": achieved / peak,
         "traffic": None,
-        "bytes_per_launch": k1_bytes,
-        "us_per_launch": k1_us,
-        "us_per_launch_isolated": k1_isolated_us if fused else k1_us,
+        "bytes_per_launch": bytes_per_launch,
+        "us_per_launch": us_per_launch,
+        "us_per_launch_isolated": us_isolated,
+        "frames_per_launch": frames_per_launch,
+        "algorithmic_bytes_per_frame": k1_bytes,
         "k2_us_per_launch": k2_us,
         "frame_us": ms * 1e3 / (F * args.steps),
     }
-    traffic_file = os.path.join(ROOT, "profiles", "frame_dram_bytes.json" if fused else "k1_dram_bytes.json")
-    if os.path.exists(traffic_file):
+    tf = os.path.join(ROOT, "profiles", traffic_file)
+    if os.path.exists(tf):
         try:
-            with open(traffic_file) as fh:
-                roofline["traffic"] = json.load(fh).get("dram_bytes_per_launch")
+            with open(tf) as fh:
+                tj = json.load(fh)
+            per_frame = tj.get("dram_bytes_per_frame")
+            roofline["traffic"] = per_frame * frames_per_launch if (batch and per_frame) else tj.get("dram_bytes_per_launch")
+            roofline["traffic_source"] = tj.get("source")
         except Exception:
             pass
 
     if args.quick:  # parameter sweeps: kernel numbers only
         print(json.dumps({"quick": True, "options": args.opt, "value": value, "frame_us": roofline["frame_us"],
-                          "k1_us": k1_us, "k2_us": k2_us, "k1_frac": roofline["frac"], "events": n, "frames": F}), flush=True)
+                          "k1_us": k1_us, "k2_us": k2_us, "k1_frac": roofline["frac"], "frames_per_launch": frames_per_launch, "events": n, "frames": F}), flush=True)
         return
 
     # ---- parity spot check + CPU baseline on one frame of the same workload -------------------

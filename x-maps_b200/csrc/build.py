@@ -37,7 +37,8 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES + LINK_LIBS
+    extra = os.environ.get("XM_NVCC_EXTRA", "").split()  # e.g. -DXM_ROW_PHASE_A=0 for A/B builds
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES + LINK_LIBS
     proc = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
     if verbose or proc.returncode:
         sys.stderr.write(proc.stdout + proc.stderr)

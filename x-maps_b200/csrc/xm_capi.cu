@@ -787,6 +787,8 @@ int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
     if (t->remap_xy && (t->proj_w <= 0 || t->proj_h <= 0)) return fail(XM_ERR_INVALID_ARG, "projector size must be positive");
     if (t->dilate < 1 || (t->dilate & 1) == 0 || t->dilate > 31) return fail(XM_ERR_INVALID_ARG, "dilate must be odd, 1..31");
     if (t->rect_w > 32767 || t->rect_h > 32767) return fail(XM_ERR_TABLE_RANGE, "rectified image exceeds int16 coordinates");
+    if (static_cast<long long>(t->proj_w) * t->proj_h > (1LL << 30) || static_cast<long long>(t->cam_w) * t->cam_h > (1LL << 30))
+        return fail(XM_ERR_UNSUPPORTED, "frames are limited to 2^30 pixels");
     int n_dev = 0;
     XM_CUDA(cudaGetDeviceCount(&n_dev));
     if (device < 0 || device >= n_dev) return fail(XM_ERR_INVALID_ARG, "device %d of %d", device, n_dev);

@@ -331,6 +331,24 @@ __device__ __forceinline__ void emit_pixel_int(const OutputSpec& o, void* out, l
     }
 }
 
+// N pixels at once: all depth-table look-ups are issued before the first store, so their latencies overlap
+// (`live` masks pixels that do not exist; idx[j] is only used when live[j]).
+template <int N>
+__device__ __forceinline__ void emit_pixels_int(const OutputSpec& o, void* out, const int (&idx)[N], const int (&disp)[N], const bool (&live)[N]) {
+    if (o.kind == 0 && o.depth_lut) {
+        float z[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) z[j] = (live[j] && disp[j] != 0) ? __ldg(o.depth_lut + disp[j]) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if (live[j]) static_cast<float*>(out)[idx[j]] = z[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if (live[j]) emit_pixel_int(o, out, idx[j], disp[j]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier + 1-D bulk async copy (TMA) helpers
 // ---------------------------------------------------------------------------------------------

@@ -1445,6 +1445,9 @@ __global__ void __launch_bounds__(256, 7) epilogue_projector_kernel(const Epilog
 //      outputs, same ladder
 //   D  every output pixel reads its dilated value at its own (x_rect, y_rect) and converts.
 // ---------------------------------------------------------------------------------------------
+#ifndef XM_ROW_PHASE_A
+#define XM_ROW_PHASE_A 1
+#endif
 constexpr int kRowPad = 4;    // zero cells left of the data in every shared-memory row
 constexpr int kRowExtra = 16;  // total padding per row (4 left + 12 right)
 
@@ -1491,31 +1494,61 @@ __device__ __forceinline__ void proj7_dilate_region(const EpilogueParams& p, con
             // ---- A: decode the region (pads included, written as zeros) -------------------------
             {
                 const int pairs = stride >> 1;
-                const unsigned mg = magic_div(pairs);
                 unsigned* dst = reinterpret_cast<unsigned*>(bufA);
-                // UA cell pairs per thread per round, all loads of a round issued before the first decode:
-                // with UA > 1 the region comes out of L2 in one round trip per round instead of one per pair
-                const int total = pairs * rh;
-                for (int c0 = tid; c0 < total; c0 += UA * NT) {
-                    ulonglong2 kk[UA];
-                    bool live[UA];
+                const unsigned ep16 = epoch & 0xffffu;
+                if (XM_ROW_PHASE_A && pairs <= 32) {
+                    // one warp per region row, one lane per cell pair: everything that depends on x is a per-lane
+                    // constant and a row costs one 128-bit load, two epoch tests and one shared store per lane;
+                    // UA rows are in flight per warp
+                    constexpr int NW = NT / 32;
+                    const int lane = tid & 31, wrp = tid >> 5;
+                    const int cx = 2 * lane - kRowPad;  // data coordinate of the pair's first cell (even)
+                    const int gx = rx0 + cx;
+                    const bool slot = lane < pairs;
+                    const bool live_x = slot && cx >= 0 && cx < rw && gx >= 0 && gx < p.rect_w;
+                    for (int r0 = wrp; r0 < rh; r0 += UA * NW) {
+                        uint4 kk[UA];
 #pragma unroll
-                    for (int j = 0; j < UA; ++j) {
-                        const int c = c0 + j * NT;
-                        const int ry = static_cast<int>(__umulhi(static_cast<unsigned>(c), mg));
-                        const int cx = 2 * (c - ry * pairs) - kRowPad;  // data coordinate of the pair's first cell (even)
-                        const int gx = rx0 + cx, gy = ry0 + ry;
-                        live[j] = c < total && cx >= 0 && cx < rw && gx >= 0 && gx < p.rect_w && gy >= 0 && gy < p.rect_h;
-                        kk[j] = make_ulonglong2(0ULL, 0ULL);
-                        if (live[j]) kk[j] = __ldcg(reinterpret_cast<const ulonglong2*>(p.map + gy * p.rect_w + gx));
+                        for (int j = 0; j < UA; ++j) {
+                            const int gy = ry0 + r0 + j * NW;
+                            kk[j] = make_uint4(0u, 0u, 0u, 0u);
+                            if (live_x && r0 + j * NW < rh && gy >= 0 && gy < p.rect_h)
+                                kk[j] = __ldcg(reinterpret_cast<const uint4*>(p.map + gy * p.rect_w + gx));
+                        }
+#pragma unroll
+                        for (int j = 0; j < UA; ++j) {
+                            const int row = r0 + j * NW;
+                            // key = epoch:16 | index:32 | disparity:16 -> the epoch is the top half of the high word
+                            const unsigned d0 = (kk[j].y >> 16) == ep16 ? (kk[j].x & 0xffffu) : 0u;
+                            const unsigned d1 = (kk[j].w >> 16) == ep16 ? (kk[j].z << 16) : 0u;
+                            if (slot && row < rh) dst[row * pairs + lane] = d0 | d1;
+                        }
                     }
+                } else {
+                    // UA cell pairs per thread per round, all loads of a round issued before the first decode
+                    const unsigned mg = magic_div(pairs);
+                    const int total = pairs * rh;
+                    for (int c0 = tid; c0 < total; c0 += UA * NT) {
+                        ulonglong2 kk[UA];
+                        bool live[UA];
 #pragma unroll
-                    for (int j = 0; j < UA; ++j) {
-                        const int c = c0 + j * NT;
-                        if (c < total)
-                            dst[c] = live[j] ? (static_cast<unsigned>(key_disparity(kk[j].x, epoch)) |
-                                                (static_cast<unsigned>(key_disparity(kk[j].y, epoch)) << 16))
-                                             : 0u;
+                        for (int j = 0; j < UA; ++j) {
+                            const int c = c0 + j * NT;
+                            const int ry = static_cast<int>(__umulhi(static_cast<unsigned>(c), mg));
+                            const int cx = 2 * (c - ry * pairs) - kRowPad;  // data coordinate of the pair's first cell (even)
+                            const int gx = rx0 + cx, gy = ry0 + ry;
+                            live[j] = c < total && cx >= 0 && cx < rw && gx >= 0 && gx < p.rect_w && gy >= 0 && gy < p.rect_h;
+                            kk[j] = make_ulonglong2(0ULL, 0ULL);
+                            if (live[j]) kk[j] = __ldcg(reinterpret_cast<const ulonglong2*>(p.map + gy * p.rect_w + gx));
+                        }
+#pragma unroll
+                        for (int j = 0; j < UA; ++j) {
+                            const int c = c0 + j * NT;
+                            if (c < total)
+                                dst[c] = live[j] ? (static_cast<unsigned>(key_disparity(kk[j].x, epoch)) |
+                                                    (static_cast<unsigned>(key_disparity(kk[j].y, epoch)) << 16))
+                                                 : 0u;
+                        }
                     }
                 }
             }
@@ -1619,14 +1652,21 @@ __device__ __forceinline__ void proj7_tile(const EpilogueParams& p, int bx, int 
         if (u < p.out_w && v < p.out_h) m[k] = __ldg(p.remap_xy + v * p.out_w + u);
     }
     if (g.fits) proj7_dilate_region<NT, UA>(p, g, epoch, bufA, bufB, gtid, bar_id);
+    int val[PX];
+    int idx[PX];
+    bool live[PX];
 #pragma unroll
     for (int k = 0; k < PX; ++k) {
-        int val = 0;
-        if (g.any && m[k].x >= 0 && m[k].x < p.rect_w && m[k].y >= 0 && m[k].y < p.rect_h)
-            val = g.fits ? bufA[(m[k].y - g.ry0) * g.stride + (m[k].x - g.rx0) + kRowPad] : proj7_direct(p, m[k], epoch);
+        val[k] = 0;
+        const bool inside = g.any && static_cast<unsigned>(m[k].x) < static_cast<unsigned>(p.rect_w) &&
+                            static_cast<unsigned>(m[k].y) < static_cast<unsigned>(p.rect_h);  // negative coordinates wrap to large values
+        if (inside && g.fits) val[k] = bufA[(m[k].y - g.ry0) * g.stride + (m[k].x - g.rx0) + kRowPad];
+        if (inside && !g.fits) val[k] = proj7_direct(p, m[k], epoch);
         const int u = u0 + lane, v = v0 + warp + k * ROWS;
-        if (u < p.out_w && v < p.out_h) emit_pixel_int(p.out, p.dst, v * p.out_w + u, val);
+        live[k] = u < p.out_w && v < p.out_h;
+        idx[k] = v * p.out_w + u;
     }
+    emit_pixels_int<PX>(p.out, p.dst, idx, val, live);
 }
 
 // Same tile for a small group inside a register-tight kernel (batch_kernel's epilogue warps): the remap
@@ -1643,22 +1683,33 @@ __device__ __forceinline__ void proj7_tile_late(const EpilogueParams& p, int bx,
     const TileRegion g = tile_region(p, __ldg(p.tile_box + by * tiles_x + bx));
     if (g.fits) proj7_dilate_region<NT, UA>(p, g, epoch, bufA, bufB, gtid, bar_id);
     const int u = u0 + lane;
+    if (u >= p.out_w) return;  // (after the last group barrier)
+    const bool full = v0 + kTile <= p.out_h;  // every row of the tile exists: no per-pixel row test
+    const short2* rp = p.remap_xy + static_cast<long long>(v0 + warp) * p.out_w + u;
+    const int pix0 = (v0 + warp) * p.out_w + u;  // (frames are limited to 2^30 pixels at context creation)
+    const int step = ROWS * p.out_w;
     for (int k0 = 0; k0 < PX; k0 += PXB) {
         short2 m[PXB];
+        bool live[PXB];
 #pragma unroll
         for (int j = 0; j < PXB; ++j) {
-            const int v = v0 + warp + (k0 + j) * ROWS;
+            live[j] = full || v0 + warp + (k0 + j) * ROWS < p.out_h;
             m[j] = make_short2(-1, -1);
-            if (u < p.out_w && v < p.out_h) m[j] = __ldg(p.remap_xy + v * p.out_w + u);
+            if (live[j]) m[j] = __ldg(rp + (k0 + j) * step);
         }
+        int val[PXB];
+        int idx[PXB];
 #pragma unroll
         for (int j = 0; j < PXB; ++j) {
-            int val = 0;
-            if (g.any && m[j].x >= 0 && m[j].x < p.rect_w && m[j].y >= 0 && m[j].y < p.rect_h)
-                val = g.fits ? bufA[(m[j].y - g.ry0) * g.stride + (m[j].x - g.rx0) + kRowPad] : proj7_direct(p, m[j], epoch);
-            const int v = v0 + warp + (k0 + j) * ROWS;
-            if (u < p.out_w && v < p.out_h) emit_pixel_int(p.out, p.dst, v * p.out_w + u, val);
+            val[j] = 0;
+            // unsigned compares: negative coordinates wrap to large values
+            const bool inside = g.any && static_cast<unsigned>(m[j].x) < static_cast<unsigned>(p.rect_w) &&
+                                static_cast<unsigned>(m[j].y) < static_cast<unsigned>(p.rect_h);
+            if (inside && g.fits) val[j] = bufA[(m[j].y - g.ry0) * g.stride + (m[j].x - g.rx0) + kRowPad];
+            if (inside && !g.fits) val[j] = proj7_direct(p, m[j], epoch);
+            idx[j] = pix0 + (k0 + j) * step;
         }
+        emit_pixels_int<PXB>(p.out, p.dst, idx, val, live);
     }
 }
 
