@@ -436,3 +436,10 @@ def test_hd_config_tables_and_frames(manifest):
     assert sha(eng.frame(ev, view=0).cpu().numpy()) == cfg["hash"]["depth_proj_seed3_1m"]
     assert sha(eng.frame(ev, view=1).cpu().numpy()) == cfg["hash"]["depth_cam_seed3_1m"]
     assert eng.status()["n_inliers"] == cfg["n_inliers"]
+    # the persistent batch kernel on this geometry (wider tile regions than the default one)
+    assert eng.get_option("batch") == 1
+    ev2 = orc.synth_events(4, 700_000, 1280, 720)
+    for view, key in ((0, "depth_proj_seed3_1m"), (1, "depth_cam_seed3_1m")):
+        out = eng.frame_batch([ev, ev2, ev], view=view).cpu().numpy()
+        assert sha(out[0]) == cfg["hash"][key] and sha(out[2]) == cfg["hash"][key]
+        assert np.array_equal(out[1], eng.frame(ev2, view=view).cpu().numpy())

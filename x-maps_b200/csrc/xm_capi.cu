@@ -1044,7 +1044,7 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
     if (!strcmp(key, "region_cells")) {
         if (v < 0 || v > 48 * 1024 / 4) return fail(XM_ERR_INVALID_ARG, "region_cells out of range");
         c->opt_region_cells = v;
-        return XM_OK;
+        return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;  // the batch kernel's shared memory depends on it
     }
     return fail(XM_ERR_INVALID_ARG, "unknown option '%s'", key);
 }
