@@ -35,7 +35,7 @@ namespace xm {
 
 constexpr int kBatchMax = 32;    // frames per launch (the frame table travels in the kernel parameters)
 constexpr int kBatchMaps = 3;    // scatter maps in rotation
-constexpr int kBatchHeader = 768;  // mbarriers, ring descriptors, CTA accumulators, per-warp frame constants
+constexpr int kBatchHeader = 1152;  // mbarriers, ring descriptors, CTA accumulators, per-warp frame constants (2 slots)
 constexpr int kCamTilePx = 4096;  // camera-view epilogue item
 constexpr int kTileWarps = 4;             // epilogue warps per CTA
 constexpr int kTileGroupThreads = 64;     // threads that share one tile
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
         const int grp = (tid - kWsThreads) / kTileGroupThreads, gtid = (tid - kWsThreads) % kTileGroupThreads;
         unsigned short* bufA = reinterpret_cast<unsigned short*>(win_ring + bp.win_stages * win_bytes) + grp * (2 * bp.ep.region_cap);
         unsigned short* bufB = bufA + bp.ep.region_cap;
-        volatile int* s_ticket = reinterpret_cast<volatile int*>(ev_smem + 704) + grp;
+        volatile int* s_ticket = reinterpret_cast<volatile int*>(ev_smem + 1088) + grp;
         const int bar_id = 1 + grp;
         const int n_tiles = bp.tile_items;
         for (int f = 0; f < B; ++f) {
@@ -341,15 +341,18 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
     unsigned fpe = 0, bpw = 0;
     unsigned fpar = 0, bpar = 0;  // LUT double-buffer halves of the next front / back half
 
-    // per-frame state
-    int cur_f = -1;
+    // per-frame state: all statistics are taken in the BACK half, so they belong to exactly one frame
+    int cur_f = -1;    // frame of the back half (the one whose statistics are being accumulated)
+    int front_f = -1;  // frame whose constants the front half prepared last
+    unsigned fslot = 0;  // constant slot of front_f (toggles with every new frame; a chunk carries its slot to the back half)
     unsigned my_chunks = 0, n_valid = 0, n_inl = 0, flags = 0;
-    // The constants of the frame a warp is working on live in shared memory (48 B per warp, written by
-    // lane 0 when the warp enters a frame, read back with broadcast loads where they are used): unlike
+    // The constants of the frames a warp is working on live in shared memory (two slots of 48 B per warp,
+    // alternating per new frame, written by lane 0 when the warp's FRONT half enters the frame, read back with
+    // broadcast loads where they are used; the BACK half is at most one chunk -- hence one frame -- behind): unlike
     // the single-frame kernels, where they are kernel parameters, they would otherwise occupy ~14
     // registers across the whole per-event loop and push it into local-memory spills.
     //   [0] t_min lo, hi, range, 2*scale   [1] d, M, shift, ok   [2] map lo, hi, epoch << 16, n_events
-    const unsigned a_fc = sbase + 320 + warp * 48;
+    const unsigned a_fc = sbase + 320 + warp * 96;  // + slot * 48
 
     // leaves frame cur_f: statistics and the count of finished chunks go to the frame's state block
     // (once per CTA: the last of the eight warps to leave forwards the CTA's totals)
@@ -383,9 +386,10 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
         my_chunks = 0;
         cur_f = -1;
     };
-    auto enter_frame = [&](int f) {
-        leave_frame();
-        cur_f = f;
+    // FRONT side: constants of frame f into the warp's other slot
+    auto prepare_frame = [&](int f) {
+        front_f = f;
+        fslot ^= 1u;
         if (f >= kBatchMaps) {
             // this frame scatters into the map frame f - kBatchMaps used: all of that frame's tiles must have read it
             if (lane == 0) {
@@ -397,13 +401,14 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
         }
         const FrameState* st = bp.states + f;
         if (lane == 0) {
+            const unsigned a = a_fc + fslot * 48;
             IntCol ic;
             ic.init(__ldcg(&st->t_lo_bits), __ldcg(&st->t_hi_bits), bp.t_px_scale);
             const unsigned long long mp = reinterpret_cast<unsigned long long>(bp.maps[f % kBatchMaps]);
-            sts128_a(a_fc, make_int4(static_cast<int>(ic.lo), static_cast<int>(ic.lo >> 32), static_cast<int>(ic.range), static_cast<int>(ic.scale2)));
-            sts128_a(a_fc + 16, make_int4(static_cast<int>(ic.d), static_cast<int>(ic.M), ic.sh, ic.ok ? 1 : 0));
-            sts128_a(a_fc + 32, make_int4(static_cast<int>(mp), static_cast<int>(mp >> 32),
-                                          static_cast<int>((bp.epoch0 + static_cast<unsigned>(f)) << 16), static_cast<int>(bp.frames[f].n)));
+            sts128_a(a, make_int4(static_cast<int>(ic.lo), static_cast<int>(ic.lo >> 32), static_cast<int>(ic.range), static_cast<int>(ic.scale2)));
+            sts128_a(a + 16, make_int4(static_cast<int>(ic.d), static_cast<int>(ic.M), ic.sh, ic.ok ? 1 : 0));
+            sts128_a(a + 32, make_int4(static_cast<int>(mp), static_cast<int>(mp >> 32),
+                                       static_cast<int>((bp.epoch0 + static_cast<unsigned>(f)) << 16), static_cast<int>(bp.frames[f].n)));
         }
         __syncwarp();
     };
@@ -421,15 +426,18 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
         }
     };
 
-    // FRONT half of chunk g of the current frame (stage fe): events into registers, LUT gathers started,
-    // time columns computed; releases the stage
-    auto front = [&](int g, int (&col)[kEvPerThread], int (&pix)[kEvPerThread]) {
+    // FRONT half of chunk g of frame f (stage fe): events into registers, LUT gathers started, time columns
+    // computed; releases the stage.  col[k]: time column, or -1 event not kept (polarity / past the end),
+    // -2 pixel outside the camera image, -3 timestamp outside the assumed bounds.
+    auto front = [&](int f, int g, int (&col)[kEvPerThread], int (&pix)[kEvPerThread]) -> unsigned {
+        if (f != front_f) prepare_frame(f);
+        const unsigned a_fcf = a_fc + fslot * 48;
         const unsigned a_stage = a_ring + fe * (kEvChunk * 16);
         const unsigned a_lut_c = a_lut + fpar * (kEvChunk * 4);
         fpar ^= 1u;
         IntCol ic;
         {
-            const int4 c0 = lds128_a(a_fc), c1 = lds128_a(a_fc + 16);
+            const int4 c0 = lds128_a(a_fcf), c1 = lds128_a(a_fcf + 16);
             ic.lo = (static_cast<unsigned long long>(static_cast<unsigned>(c0.y)) << 32) | static_cast<unsigned>(c0.x);
             ic.range = static_cast<unsigned>(c0.z);
             ic.scale2 = static_cast<unsigned>(c0.w);
@@ -438,9 +446,9 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
             ic.sh = c1.z;
             ic.ok = c1.w != 0;
         }
-        const unsigned left = static_cast<unsigned>(lds32_a(a_fc + 44)) - static_cast<unsigned>(g) * kEvChunk;
+        const unsigned left = static_cast<unsigned>(lds32_a(a_fcf + 44)) - static_cast<unsigned>(g) * kEvChunk;
         const int limit = left < kEvChunk ? static_cast<int>(left) : kEvChunk;
-        unsigned vmask = 0, bad_mask = 0;
+        unsigned bad_mask = 0;
         // two events at a time: half the registers for the raw records (the per-event loop must not spill)
 #pragma unroll
         for (int h = 0; h < kEvPerThread; h += 2) {
@@ -459,42 +467,40 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
                 const long long t_bits = (static_cast<long long>(raw[j].w) << 32) | static_cast<unsigned>(raw[j].z);
                 bool bad;
                 const unsigned q = ic.column(t_bits, bad);
-                col[k] = ok ? static_cast<int>(q) : -1;
+                col[k] = ok ? static_cast<int>(q) : (valid ? -2 : -1);
                 if (CAM) pix[k] = px;
-                vmask |= valid ? (1u << k) : 0u;
-                bad_mask |= (valid && (!ok || bad || !ic.ok)) ? (1u << k) : 0u;
+                bad_mask |= (ok && (bad || !ic.ok)) ? (1u << k) : 0u;
             }
         }
         cp_async_commit();
-        n_valid += __popc(vmask);
-        if (bad_mask) {  // slow path: the reference's own float64 expression / error flags
+        if (bad_mask) {  // slow path: the reference's own float64 expression
             TimeCol<false> tc;  // rebuilt here: the float64 constants are not worth registers in the hot loop
-            tc.init(__ldcg(&bp.states[cur_f].t_lo_bits), __ldcg(&bp.states[cur_f].t_hi_bits), bp.t_px_scale);
+            tc.init(__ldcg(&bp.states[f].t_lo_bits), __ldcg(&bp.states[f].t_hi_bits), bp.t_px_scale);
 #pragma unroll
             for (int k = 0; k < kEvPerThread; ++k) {
                 if (!(bad_mask & (1u << k))) continue;
-                if (col[k] < 0) {
-                    flags |= kStatusPixelOob;  // the reference raises IndexError here
-                    continue;
-                }
                 const int4 rec = lds128_a(a_stage + k * (kEvThreads * 16));  // the stage is ours until release()
                 const long long t_bits = (static_cast<long long>(rec.w) << 32) | static_cast<unsigned>(rec.z);
                 bool viol;
                 int cc = tc.column(t_bits, viol);
                 if (cc < 0) cc += bp.xmap_w;  // NumPy negative index (only reachable with wrong bounds)
                 viol = viol || cc < 0 || cc >= bp.xmap_w;
-                if (viol) {
-                    flags |= kStatusTBounds;
-                    cc = 0;
-                }
-                col[k] = cc;
+                col[k] = viol ? -3 : cc;
             }
         }
         release();
+        return fslot;
     };
 
     // BACK half: X-map lookups (window in shared memory, else through L2), disparity, scatter
-    auto back = [&](int g, const int (&col)[kEvPerThread], const int (&pix)[kEvPerThread]) {
+    auto back = [&](int f, unsigned slot, int g, const int (&col)[kEvPerThread], const int (&pix)[kEvPerThread]) {
+        if (f != cur_f) {
+            // first chunk of a new frame: the previous frame's scatter is complete for this warp.  Its fence
+            // and counters run while the gathers of the next chunk (issued by the front half) are in flight.
+            leave_frame();
+            cur_f = f;
+        }
+        const unsigned a_fcb = a_fc + slot * 48;
         int win_lo = 0;
         unsigned win_n = 0;
         unsigned a_win_c = a_lut;  // any valid address: without a window every lookup misses
@@ -510,10 +516,27 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
 #pragma unroll
         for (int k = 0; k < kEvPerThread; ++k) lut[k] = lds32_a(a_lut_c + k * (kEvThreads * 4));
         unsigned hit_mask = 0, miss_mask = 0;
+        {   // statistics of the chunk (col < 0: see front)
+            unsigned kept = 0;
+            int special = 0;
+#pragma unroll
+            for (int k = 0; k < kEvPerThread; ++k) {
+                kept += col[k] != -1;
+                special |= col[k] + 1;  // negative only for -2 / -3
+            }
+            n_valid += kept;
+            if (special < 0) {
+#pragma unroll
+                for (int k = 0; k < kEvPerThread; ++k) {
+                    if (col[k] == -2) flags |= kStatusPixelOob;  // the reference raises IndexError here
+                    if (col[k] == -3) flags |= kStatusTBounds;
+                }
+            }
+        }
 #pragma unroll
         for (int k = 0; k < kEvPerThread; ++k) {
             const unsigned ycr = static_cast<unsigned>(lut[k] >> 16);
-            const unsigned rel = static_cast<unsigned>(col[k] - win_lo);  // dropped events (col = -1) wrap to huge
+            const unsigned rel = static_cast<unsigned>(col[k] - win_lo);  // dropped events (col < 0) wrap to huge
             const bool y_ok = ycr < XM_B_YLIM;  // x_maps_disparity.py:23: 0 <= y_rect < H - 1 (last row excluded)
             const bool hit = y_ok && rel < win_n;
             xp[k] = lds_s16_a(a_win_c + (hit ? (rel * static_cast<unsigned>(bp.col_stride) + ycr) * 2u : 0u));
@@ -527,7 +550,7 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
             hit_mask |= miss_mask;
         }
         const unsigned idx0 = static_cast<unsigned>(g) * kEvChunk + static_cast<unsigned>(tid);
-        const int4 c2 = lds128_a(a_fc + 32);
+        const int4 c2 = lds128_a(a_fcb + 32);
         unsigned long long* const map = reinterpret_cast<unsigned long long*>(
             (static_cast<unsigned long long>(static_cast<unsigned>(c2.y)) << 32) | static_cast<unsigned>(c2.x));
         const unsigned epoch16 = static_cast<unsigned>(c2.z);
@@ -558,33 +581,48 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
         ++my_chunks;
     };
 
+    // The software pipeline runs across frame boundaries: FRONT half of chunk c+1 (possibly the first chunk
+    // of the next frame), then BACK half of chunk c.
     int2 m = peek();
-    for (;;) {
-        if (m.x < 0) break;
-        const int f = m.x;
-        // ---- a run of chunks of frame f -------------------------------------------------------------------
-        if (f != cur_f) enter_frame(f);
+    if (m.x >= 0) {
         int col_cur[kEvPerThread], pix_cur[kEvPerThread];
-        int g_cur = m.y;
-        front(g_cur, col_cur, pix_cur);
+        int f_cur = m.x, g_cur = m.y;
+        unsigned s_cur = front(f_cur, g_cur, col_cur, pix_cur);
         for (;;) {
             m = peek();
-            const bool more = m.x == cur_f;  // kind 0, same frame
+            const bool more = m.x >= 0;
+            // Entering frame F waits for the tiles of frame F - kBatchMaps, which wait for every warp's count
+            // of that frame's chunks.  This warp publishes a frame's count only in the BACK half of a later
+            // frame's chunk, so if one of its two unpublished frames (cur_f: back half, f_cur: front half done)
+            // is that old, the pipeline is drained first (tiny frames / many more CTAs than chunks per frame).
+            bool drain = false;
+            if (more && m.x != front_f && m.x >= kBatchMaps) {
+                const int must_be_out = m.x - kBatchMaps;
+                drain = f_cur <= must_be_out || (cur_f >= 0 && cur_f <= must_be_out);
+            }
             int col_nxt[kEvPerThread], pix_nxt[kEvPerThread];
-            if (more) {
-                front(m.y, col_nxt, pix_nxt);
+            unsigned s_nxt = 0;
+            if (more && !drain) {
+                s_nxt = front(m.x, m.y, col_nxt, pix_nxt);
                 cp_async_wait<1>();  // the gathers of the current chunk have landed; the next chunk's stay in flight
             } else {
                 cp_async_wait<0>();
             }
-            back(g_cur, col_cur, pix_cur);
+            back(f_cur, s_cur, g_cur, col_cur, pix_cur);
             if (!more) break;
+            if (drain) {
+                leave_frame();
+                s_nxt = front(m.x, m.y, col_cur, pix_cur);
+            } else {
 #pragma unroll
-            for (int k = 0; k < kEvPerThread; ++k) {
-                col_cur[k] = col_nxt[k];
-                if (CAM) pix_cur[k] = pix_nxt[k];
+                for (int k = 0; k < kEvPerThread; ++k) {
+                    col_cur[k] = col_nxt[k];
+                    if (CAM) pix_cur[k] = pix_nxt[k];
+                }
             }
+            f_cur = m.x;
             g_cur = m.y;
+            s_cur = s_nxt;
         }
     }
     leave_frame();
