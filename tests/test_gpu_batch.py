@@ -13,21 +13,24 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-@pytest.fixture(scope="module")
-def small():
+BATCH_KERNELS = [1, 2]  # 1: batch_kernel (staged event pipeline), 2: batch2_kernel (plain-load event warps)
+
+
+@pytest.fixture(scope="module", params=BATCH_KERNELS, ids=["staged", "plain"])
+def small(request):
     tables, z = load_golden_tables("small")
     eng = make_engine(tables, z)
-    eng.set_option("batch", 1)  # opt-in (the fused per-frame kernels are the default, see EXPERIMENTS_r01.md)
-    assert eng.get_option("batch") == 1 and eng.get_option("batch_occ") >= 1
+    eng.set_option("batch", request.param)
+    assert eng.get_option("batch") == request.param and eng.get_option("batch_occ") >= 1
     yield tables, z, eng
     eng.close()
 
 
-@pytest.fixture(scope="module")
-def default():
+@pytest.fixture(scope="module", params=BATCH_KERNELS, ids=["staged", "plain"])
+def default(request):
     tables, z = load_golden_tables("default")
     eng = make_engine(tables)
-    eng.set_option("batch", 1)
+    eng.set_option("batch", request.param)
     yield tables, z, eng
     eng.close()
 
@@ -139,11 +142,12 @@ def test_batch_option_off_is_identical(small):
     tables, _, eng = small
     frames = [orc.synth_events(40 + i, 8_000 + 100 * i, 160, 120) for i in range(5)]
     on = eng.frame_batch(frames, view=0).cpu().numpy()
+    mode = eng.get_option("batch")
     eng.set_option("batch", 0)
     try:
         off = eng.frame_batch(frames, view=0).cpu().numpy()
     finally:
-        eng.set_option("batch", 1)
+        eng.set_option("batch", mode)
     assert np.array_equal(on, off)
 
 

@@ -160,6 +160,42 @@ static __device__ __noinline__ void batch_tile(const BatchParams& bp, int f, int
     }
 }
 
+// The loop of one epilogue group (kTileGroupThreads threads, named barrier 1 + grp): for every frame of the
+// batch, wait until all of its chunks (CHUNK events each) have been scattered, then take tiles from the frame's
+// ticket counter until they run out.
+template <bool CAM, int CHUNK>
+__device__ __forceinline__ void batch_tile_groups(const BatchParams& bp, int grp, int gtid, unsigned short* bufA, unsigned short* bufB,
+                                                  volatile int* s_ticket) {
+    const int bar_id = 1 + grp;
+    const int n_tiles = bp.tile_items;
+    for (int f = 0; f < bp.n_frames; ++f) {
+        FrameState* st = bp.states + f;
+        int next_ticket = 0;
+        if (gtid == 0) {
+            const unsigned need = static_cast<unsigned>((bp.frames[f].n + CHUNK - 1) / CHUNK);
+            while (ld_acquire_u32(&st->blocks_done) < need) __nanosleep(200);
+            next_ticket = static_cast<int>(atomicAdd(&st->fix_chunk, 1u));
+        }
+        for (;;) {
+            group_sync<kTileGroupThreads>(bar_id);  // the previous tile is done with the buffers / the frame is complete
+            if (gtid == 0) {
+                *s_ticket = next_ticket;
+                // the ticket after this one is requested now and read after the tile: its round trip is hidden
+                if (next_ticket < n_tiles) next_ticket = static_cast<int>(atomicAdd(&st->fix_chunk, 1u));
+            }
+            group_sync<kTileGroupThreads>(bar_id);
+            const int t = *s_ticket;
+            if (t >= n_tiles) break;
+            batch_tile<CAM>(bp, f, t, bufA, bufB, gtid, bar_id);
+            group_sync<kTileGroupThreads>(bar_id);
+            if (gtid == 0) {
+                fence_acq_rel_gpu();
+                atomicAdd(&st->next_tile, 1u);  // this tile no longer needs the frame's scatter map
+            }
+        }
+    }
+}
+
 template <bool CAM>
 __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_constant__ BatchParams bp) {
     extern __shared__ __align__(128) unsigned char ev_smem[];
@@ -199,34 +235,7 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
         unsigned short* bufA = reinterpret_cast<unsigned short*>(win_ring + bp.win_stages * win_bytes) + grp * (2 * bp.ep.region_cap);
         unsigned short* bufB = bufA + bp.ep.region_cap;
         volatile int* s_ticket = reinterpret_cast<volatile int*>(ev_smem + 1088) + grp;
-        const int bar_id = 1 + grp;
-        const int n_tiles = bp.tile_items;
-        for (int f = 0; f < B; ++f) {
-            FrameState* st = bp.states + f;
-            int next_ticket = 0;
-            if (gtid == 0) {
-                const unsigned need = batch_chunks(bp.frames[f].n);
-                while (ld_acquire_u32(&st->blocks_done) < need) __nanosleep(200);
-                next_ticket = static_cast<int>(atomicAdd(&st->fix_chunk, 1u));
-            }
-            for (;;) {
-                group_sync<kTileGroupThreads>(bar_id);  // the previous tile is done with the buffers / the frame is complete
-                if (gtid == 0) {
-                    *s_ticket = next_ticket;
-                    // the ticket after this one is requested now and read after the tile: its round trip is hidden
-                    if (next_ticket < n_tiles) next_ticket = static_cast<int>(atomicAdd(&st->fix_chunk, 1u));
-                }
-                group_sync<kTileGroupThreads>(bar_id);
-                const int t = *s_ticket;
-                if (t >= n_tiles) break;
-                batch_tile<CAM>(bp, f, t, bufA, bufB, gtid, bar_id);
-                group_sync<kTileGroupThreads>(bar_id);
-                if (gtid == 0) {
-                    fence_acq_rel_gpu();
-                    atomicAdd(&st->next_tile, 1u);  // this tile no longer needs the frame's scatter map
-                }
-            }
-        }
+        batch_tile_groups<CAM, kEvChunk>(bp, grp, gtid, bufA, bufB, s_ticket);
         return;
     }
 

@@ -18,6 +18,7 @@
 #include "xm_stage_kernels.cuh"
 #include "xm_fused_kernel.cuh"
 #include "xm_batch_kernel.cuh"
+#include "xm_batch2_kernel.cuh"
 #include "xm_stream_kernels.cuh"
 
 namespace {
@@ -116,6 +117,7 @@ struct XmCtx {
     int opt_batch = 1;        // 1: xm_frame_batch renders uniform batches with one persistent kernel per <= 32 frames
                               //    (event warps + dedicated epilogue warps; 47 vs 57 us per 5 M-event frame, EXPERIMENTS_r01.md)
     int batch_occ = 0, batch_smem = 0, batch_cols = 0;  // launch configuration of batch_kernel
+    int batch2_occ = 0, batch2_smem = 0;                // launch configuration of batch2_kernel (option batch = 2)
     unsigned long long* d_map_ring[xm::kBatchMaps] = {nullptr, nullptr, nullptr};  // [0] = d_map
     xm::FrameState* d_bstate = nullptr;  // [kBatchMax + 1] state blocks of the current batch
     const xm::FrameState* status_src = nullptr;  // state block xm_frame_status reports (NULL: d_state + last_slot)
@@ -288,6 +290,24 @@ int configure_event_kernels(XmCtx* c) {
             occ_min = occ < occ_min ? occ : occ_min;
         }
         c->batch_occ = occ_min;
+        // batch2_kernel: plain-load event warps, shared memory only for the tile regions
+        c->batch2_smem = xm::batch2_smem_bytes(c->opt_region_cells);
+        occ_min = 1 << 30;
+        for (int cam = 0; cam < 2; ++cam) {
+            void (*k)(xm::BatchParams) = cam ? xm::batch2_kernel<true> : xm::batch2_kernel<false>;
+            cudaFuncAttributes fa;
+            XM_CUDA(cudaFuncGetAttributes(&fa, k));
+            const int dyn = optin - static_cast<int>(fa.sharedSizeBytes);
+            if (c->batch2_smem > dyn) {
+                occ_min = 0;
+                break;
+            }
+            XM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+            int occ = 0;
+            XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, xm::kB2Threads, c->batch2_smem));
+            occ_min = occ < occ_min ? occ : occ_min;
+        }
+        c->batch2_occ = occ_min;
     }
     return XM_OK;
 }
@@ -685,11 +705,14 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     bp.tile_items = cam ? (c->cam_w * c->cam_h + xm::kCamTilePx - 1) / xm::kCamTilePx : tiles_x * tiles_y;
     bp.n_frames = n;
     bp.debug = c->opt_debug;
-    unsigned items = 0;
+    const bool v2 = c->opt_batch == 2 && c->batch2_occ > 0;
+    unsigned long long items64 = 0;
     for (int f = 0; f < n; ++f) {
-        bp.first_item[f] = items;
-        items += xm::batch_chunks(a[f].n_events);
+        bp.first_item[f] = static_cast<unsigned>(items64);
+        items64 += v2 ? xm::batch2_chunks(a[f].n_events) : xm::batch_chunks(a[f].n_events);
     }
+    if (items64 > 0xfffffff0ULL) return fail(XM_ERR_UNSUPPORTED, "batch too large");
+    unsigned items = static_cast<unsigned>(items64);
     bp.first_item[n] = bp.first_item[n + 1] = items;
     bp.total_items = items;
     for (int f = 0; f < n; ++f) {
@@ -697,9 +720,10 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
         bp.frames[f].dst = a[f].d_out;
         bp.frames[f].n = a[f].n_events;
     }
-    const int occ = c->opt_ctas_per_sm > 0 && c->opt_ctas_per_sm < c->batch_occ ? c->opt_ctas_per_sm : c->batch_occ;
+    const int kocc = v2 ? c->batch2_occ : c->batch_occ;
+    const int occ = c->opt_ctas_per_sm > 0 && c->opt_ctas_per_sm < kocc ? c->opt_ctas_per_sm : kocc;
     // no more CTAs than there is work: a CTA takes chunks in pairs and runs kTileGroups tiles at a time
-    long long want = (static_cast<long long>(items) + 1) / 2;
+    long long want = v2 ? (static_cast<long long>(items) + xm::kB2EventWarps - 1) / xm::kB2EventWarps : (static_cast<long long>(items) + 1) / 2;
     const long long want_tiles = (static_cast<long long>(bp.tile_items) + xm::kTileGroups - 1) / xm::kTileGroups;
     if (want_tiles > want) want = want_tiles;
     int grid = c->sm_count * occ;
@@ -708,7 +732,12 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
         int rc = profile_mark(c, s);
         if (rc) return rc;
     }
-    if (cam)
+    if (v2) {
+        if (cam)
+            xm::batch2_kernel<true><<<grid, xm::kB2Threads, c->batch2_smem, s>>>(bp);
+        else
+            xm::batch2_kernel<false><<<grid, xm::kB2Threads, c->batch2_smem, s>>>(bp);
+    } else if (cam)
         xm::batch_kernel<true><<<grid, xm::kBatchThreads, c->batch_smem, s>>>(bp);
     else
         xm::batch_kernel<false><<<grid, xm::kBatchThreads, c->batch_smem, s>>>(bp);
@@ -992,8 +1021,9 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         c->opt_k2_variant = v != 0;
         return XM_OK;
     }
-    if (!strcmp(key, "batch")) {
-        c->opt_batch = v != 0;
+    if (!strcmp(key, "batch")) { /* 0: per-frame kernels, 1: batch_kernel (staged event pipeline), 2: batch2_kernel (plain-load event warps) */
+        if (v < 0 || v > 2) return fail(XM_ERR_INVALID_ARG, "batch must be 0, 1 or 2");
+        c->opt_batch = v;
         return XM_OK;
     }
     if (!strcmp(key, "fused")) {
@@ -1060,7 +1090,7 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     else if (!strcmp(key, "pdl")) *value = c->opt_pdl;
     else if (!strcmp(key, "fused")) *value = c->opt_fused;
     else if (!strcmp(key, "batch")) *value = c->opt_batch;
-    else if (!strcmp(key, "batch_occ")) *value = c->batch_occ;
+    else if (!strcmp(key, "batch_occ")) *value = c->opt_batch == 2 ? c->batch2_occ : c->batch_occ;
     else if (!strcmp(key, "batch_smem")) *value = c->batch_smem;
     else if (!strcmp(key, "batch_cols")) *value = c->batch_cols;
     else if (!strcmp(key, "k2_variant")) *value = c->opt_k2_variant;
