@@ -66,6 +66,8 @@ struct BatchParams {
     int tiles_x, tile_items;  // items per frame epilogue
     int n_frames;
     int debug;  // timing experiments only (results WRONG): 16 = skip the epilogue work of tile items
+    int hard_frames;  // 1: publish a frame's chunk count before touching the next frame (few chunks per CTA and frame:
+                      //    the tiles would otherwise wait for every CTA's NEXT chunk)
     unsigned total_items;
     unsigned first_item[kBatchMax + 2];  // first chunk of frame f in the batch-wide chunk list; [n_frames] = total
     BatchFrame frames[kBatchMax];
@@ -604,8 +606,8 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
             // of that frame's chunks.  This warp publishes a frame's count only in the BACK half of a later
             // frame's chunk, so if one of its two unpublished frames (cur_f: back half, f_cur: front half done)
             // is that old, the pipeline is drained first (tiny frames / many more CTAs than chunks per frame).
-            bool drain = false;
-            if (more && m.x != front_f && m.x >= kBatchMaps) {
+            bool drain = more && bp.hard_frames && m.x != f_cur;
+            if (!drain && more && m.x != front_f && m.x >= kBatchMaps) {
                 const int must_be_out = m.x - kBatchMaps;
                 drain = f_cur <= must_be_out || (cur_f >= 0 && cur_f <= must_be_out);
             }
@@ -656,6 +658,11 @@ struct BatchRedoParams {
 };
 
 __global__ void __launch_bounds__(32) batch_redo_kernel(const __grid_constant__ BatchRedoParams rp) {
+    // one lane per frame looks at its flags; normally nothing is flagged and the kernel ends here
+    static_assert(kBatchMax <= 32, "one lane per frame");
+    const int lf = threadIdx.x;
+    const bool mine = lf < rp.n_frames && (*reinterpret_cast<volatile unsigned*>(&rp.states[lf].flags) & kStatusTBounds);
+    if (!__any_sync(0xffffffffu, mine)) return;
     if (threadIdx.x != 0) return;
     for (int f = 0; f < rp.n_frames; ++f) {
         FrameState* st = rp.states + f;

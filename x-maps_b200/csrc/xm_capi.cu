@@ -728,6 +728,9 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     if (want_tiles > want) want = want_tiles;
     int grid = c->sm_count * occ;
     if (want < grid) grid = static_cast<int>(want < 1 ? 1 : want);
+    // pipelining across frame boundaries pays when a CTA has many chunks per frame; with few, the late
+    // publication of a frame's count (in the back half of the NEXT frame's first chunk) delays its tiles
+    bp.hard_frames = static_cast<long long>(items) < 8LL * n * grid ? 1 : 0;
     if (c->opt_profile) {
         int rc = profile_mark(c, s);
         if (rc) return rc;
