@@ -273,6 +273,10 @@ def run_ours(args):
         ),
         device=device,
     )
+    if world > 1 and not args.no_gather:
+        # the persistent batch kernel would otherwise own every SM until it ends and NCCL's copy kernels
+        # (the gather of the previous chunk) could not run beside it
+        eng.set_option("reserve_sms", args.reserve_sms)
     for kv in args.opt:
         k, v = kv.split("=")
         eng.set_option(k, int(v))
@@ -288,8 +292,23 @@ def run_ours(args):
     def render(fr, dst):
         eng.frame_batch(fr, view=VIEW_PROJECTOR, output=OUT_DEPTH, out=dst)
 
-    chunk = args.gather_chunk if args.gather_chunk > 0 else (32 if world == 1 or args.no_gather else 16)
-    sharder = FrameSharder(render, rank, world, dst=0, chunk=chunk)
+    # frames per render call = per batch-kernel launch.  With the NCCL gather: 16 (measured on 2 GPUs: 219-226 G
+    # events/s; a tapering schedule with 4 SMs left to NCCL measured 217 G, so both stay options)
+    if args.gather_chunk > 0:
+        chunk, schedule = args.gather_chunk, [args.gather_chunk]
+    elif world == 1 or args.no_gather:
+        chunk, schedule = 32, [32]
+    else:
+        chunk, schedule = 16, [16]
+        if args.taper:  # 16, 16, 16, 8, 4, 4 for 64 frames
+            schedule, left = [], F
+            while left > 32:
+                schedule.append(16)
+                left -= 16
+            schedule += [s for s in (16, 8, 4, 4) if s <= left] if left == 32 else [left]
+            if sum(schedule) != F:
+                schedule = [16]
+    sharder = FrameSharder(render, rank, world, dst=0, chunk=schedule)
 
     def step():
         sharder.run(frames, out, gathered, gather=(world > 1 and not args.no_gather))
@@ -328,8 +347,8 @@ def run_ours(args):
     eng.set_option("profile", 1)
     torch.cuda.synchronize(device)
     for _ in range(args.steps):
-        for lo in range(0, F, chunk):
-            render(frames[lo:lo + chunk], out[lo:lo + chunk])
+        for lo, hi in sharder._spans(F):
+            render(frames[lo:hi], out[lo:hi])
     torch.cuda.synchronize(device)
     k1_ns, k2_ns, pf = eng.get_option("profile_k1_ns"), eng.get_option("profile_k2_ns"), eng.get_option("profile_frames")
     eng.set_option("profile", 0)
@@ -399,6 +418,9 @@ def run_ours(args):
             pass
 
     if args.quick:  # parameter sweeps: kernel numbers only
+        if world > 1:
+            dist.barrier()  # (the other ranks wait here before they leave)
+            dist.destroy_process_group()
         print(json.dumps({"quick": True, "options": args.opt, "value": value, "frame_us": roofline["frame_us"],
                           "k1_us": k1_us, "k2_us": k2_us, "k1_frac": roofline["frac"], "frames_per_launch": frames_per_launch, "events": n, "frames": F}), flush=True)
         return
@@ -479,6 +501,8 @@ def main():
     ap.add_argument("--frames", type=int, default=64, help="distinct frames per step per GPU")
     ap.add_argument("--gather-chunk", type=int, default=0, help="frames per render call (one persistent kernel each); 0 = 32 on one GPU, 16 with the NCCL gather")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="SMs left to NCCL while the batch kernel runs (N > 1 with the gather)")
+    ap.add_argument("--taper", action="store_true", help="tapering render schedule (16, 16, 16, 8, 4, 4) with the NCCL gather")
     ap.add_argument("--cpu-runs", type=int, default=5)
     ap.add_argument("--e2e-frames", type=int, default=16)
     ap.add_argument("--e2e-reps", type=int, default=3)

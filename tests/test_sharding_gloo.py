@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n_frames, q):
+def _worker(rank, world, port, n_frames, q, chunk=2):
     from oracle import xmaps_oracle as orc
     from xmaps_b200.sharding import FrameSharder, global_order, local_frame_indices
 
@@ -34,21 +34,25 @@ def _worker(rank, world, port, n_frames, q):
 
     out = torch.zeros((len(mine), 120, 160), dtype=torch.float32)
     gathered = [torch.zeros_like(out) for _ in range(world)] if rank == 0 else None
-    FrameSharder(render, rank, world, dst=0, chunk=2).run(frames, out, gathered)
+    FrameSharder(render, rank, world, dst=0, chunk=chunk).run(frames, out, gathered)
     if rank == 0:
         q.put(global_order(gathered, n_frames).numpy())
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_round_robin_gather_world2():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("n_frames,chunk", [(6, 2), (14, (3, 2, 1))])  # fixed chunks / tapering schedule (last size repeats)
+def test_round_robin_gather_world2(n_frames, chunk):
     from oracle import xmaps_oracle as orc
 
-    world, n_frames = 2, 6
+    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_frames, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_frames, q, chunk)) for r in range(world)]
     for p in procs:
         p.start()
     got = q.get(timeout=120)
@@ -68,3 +72,9 @@ def test_index_helpers():
     assert local_frame_indices(10, 1, 4) == [1, 5, 9]
     stacks = [torch.arange(3).reshape(3, 1) * 4 + r for r in range(4)]
     assert global_order(stacks, 10).flatten().tolist() == list(range(10))
+    from xmaps_b200.sharding import FrameSharder
+
+    sh = FrameSharder(lambda fr, dst: None, 0, 1, chunk=(16, 16, 16, 8, 4, 4))
+    assert list(sh._spans(64)) == [(0, 16), (16, 32), (32, 48), (48, 56), (56, 60), (60, 64)]
+    assert list(sh._spans(70)) == [(0, 16), (16, 32), (32, 48), (48, 56), (56, 60), (60, 64), (64, 68), (68, 70)]
+    assert list(FrameSharder(lambda fr, dst: None, 0, 1, chunk=32)._spans(64)) == [(0, 32), (32, 64)]

@@ -112,6 +112,7 @@ struct XmCtx {
     int opt_ctas_per_sm = 0;  // 0 = occupancy query
     int opt_smem_cols_bytes = 12 * 1024;
     int opt_k2_variant = 1;   // 1: sliding-window epilogue (7x7, even rect_w), 0: per-tap epilogue
+    int opt_reserve_sms = 0;  // SMs the persistent batch kernel leaves free (room for NCCL's copy kernels next to it)
     int opt_fused = 1;        // 1: one fused kernel per frame where the lean path applies
     int fused_occ = 0;        // resident CTAs per SM of frame_kernel
     int opt_batch = 1;        // 1: xm_frame_batch renders uniform batches with one persistent kernel per <= 32 frames
@@ -726,7 +727,7 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     long long want = v2 ? (static_cast<long long>(items) + xm::kB2EventWarps - 1) / xm::kB2EventWarps : (static_cast<long long>(items) + 1) / 2;
     const long long want_tiles = (static_cast<long long>(bp.tile_items) + xm::kTileGroups - 1) / xm::kTileGroups;
     if (want_tiles > want) want = want_tiles;
-    int grid = c->sm_count * occ;
+    int grid = (c->sm_count - c->opt_reserve_sms) * occ;
     if (want < grid) grid = static_cast<int>(want < 1 ? 1 : want);
     // pipelining across frame boundaries pays when a CTA has many chunks per frame; with few, the late
     // publication of a frame's count (in the back half of the NEXT frame's first chunk) delays its tiles
@@ -1024,6 +1025,11 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         c->opt_k2_variant = v != 0;
         return XM_OK;
     }
+    if (!strcmp(key, "reserve_sms")) {
+        if (v < 0 || v >= c->sm_count) return fail(XM_ERR_INVALID_ARG, "reserve_sms out of range");
+        c->opt_reserve_sms = v;
+        return XM_OK;
+    }
     if (!strcmp(key, "batch")) { /* 0: per-frame kernels, 1: batch_kernel (staged event pipeline), 2: batch2_kernel (plain-load event warps) */
         if (v < 0 || v > 2) return fail(XM_ERR_INVALID_ARG, "batch must be 0, 1 or 2");
         c->opt_batch = v;
@@ -1093,6 +1099,7 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     else if (!strcmp(key, "pdl")) *value = c->opt_pdl;
     else if (!strcmp(key, "fused")) *value = c->opt_fused;
     else if (!strcmp(key, "batch")) *value = c->opt_batch;
+    else if (!strcmp(key, "reserve_sms")) *value = c->opt_reserve_sms;
     else if (!strcmp(key, "batch_occ")) *value = c->opt_batch == 2 ? c->batch2_occ : c->batch_occ;
     else if (!strcmp(key, "batch_smem")) *value = c->batch_smem;
     else if (!strcmp(key, "batch_cols")) *value = c->batch_cols;

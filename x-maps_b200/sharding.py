@@ -43,12 +43,25 @@ class FrameSharder:
     sharding / gather logic is backend-agnostic, which is how the gloo tests exercise it on CPU.
     """
 
-    def __init__(self, render: Callable, rank: int, world: int, dst: int = 0, group=None, chunk: int = 8):
+    def __init__(self, render: Callable, rank: int, world: int, dst: int = 0, group=None, chunk=8):
+        """``chunk``: frames per render call, or a sequence of chunk sizes (the last one repeats).  A tapering
+        sequence such as ``(16, 16, 16, 8, 4, 4)`` keeps the render calls large (one persistent kernel each)
+        while the only gather that cannot overlap a later render -- the last one -- stays small."""
         self.render = render
         self.rank, self.world, self.dst = rank, world, dst
         self.group = group
-        self.chunk = max(1, int(chunk))
+        sizes = [chunk] if isinstance(chunk, int) else list(chunk)
+        self.chunks = [max(1, int(c)) for c in sizes] or [8]
+        self.chunk = self.chunks[0]
         self._comm_stream = None
+
+    def _spans(self, n):
+        lo, k = 0, 0
+        while lo < n:
+            size = self.chunks[min(k, len(self.chunks) - 1)]
+            hi = min(n, lo + size)
+            yield lo, hi
+            lo, k = hi, k + 1
 
     def _gather_chunk(self, send: torch.Tensor, recv: Optional[List[torch.Tensor]], async_op: bool):
         if self.world == 1:
@@ -67,8 +80,7 @@ class FrameSharder:
         if on_cuda and gather and self.world > 1 and self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(out_local.device)
         works = []
-        for lo in range(0, n, self.chunk):
-            hi = min(n, lo + self.chunk)
+        for lo, hi in self._spans(n):
             self.render(local_frames[lo:hi], out_local[lo:hi])
             if not gather:
                 continue
