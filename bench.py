@@ -309,6 +309,9 @@ def run_ours(args):
             if sum(schedule) != F:
                 schedule = [16]
     sharder = FrameSharder(render, rank, world, dst=0, chunk=schedule)
+    gather_mode = "none" if (world == 1 or args.no_gather) else "nccl"
+    if gather_mode == "nccl" and args.gather_mode == "p2p":
+        gather_mode = "p2p" if sharder.enable_peer_copies(gathered) else "nccl (p2p mapping failed)"
 
     def step():
         sharder.run(frames, out, gathered, gather=(world > 1 and not args.no_gather))
@@ -421,7 +424,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()  # (the other ranks wait here before they leave)
             dist.destroy_process_group()
-        print(json.dumps({"quick": True, "options": args.opt, "value": value, "frame_us": roofline["frame_us"],
+        print(json.dumps({"quick": True, "gather": gather_mode, "options": args.opt, "value": value, "frame_us": roofline["frame_us"],
                           "k1_us": k1_us, "k2_us": k2_us, "k1_frac": roofline["frac"], "frames_per_launch": frames_per_launch, "events": n, "frames": F}), flush=True)
         return
 
@@ -473,7 +476,7 @@ def run_ours(args):
             "events_per_frame": n,
             "frames_per_step_per_gpu": F,
             "l2": "inputs larger than L2 (%.1f GB of events per step per GPU)" % (F * n * 16 / 1e9),
-            "parallelism": "frames round-robin over %d GPU(s)%s" % (world, "" if world == 1 or args.no_gather else ", NCCL gather of depth frames to rank 0 inside the step"),
+            "parallelism": "frames round-robin over %d GPU(s)%s" % (world, "" if world == 1 or args.no_gather else ", gather of depth frames to rank 0 inside the step (%s)" % gather_mode),
             "time_bounds": "sorted + device-side verification and fix-up",
             "options": args.opt,
         },
@@ -502,6 +505,7 @@ def main():
     ap.add_argument("--gather-chunk", type=int, default=0, help="frames per render call (one persistent kernel each); 0 = 32 on one GPU, 16 with the NCCL gather")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--reserve-sms", type=int, default=0, help="SMs left to NCCL while the batch kernel runs (N > 1 with the gather)")
+    ap.add_argument("--gather-mode", default="nccl", choices=["nccl", "p2p"], help="p2p: copy-engine peer copies into rank 0's buffer (CUDA IPC)")
     ap.add_argument("--taper", action="store_true", help="tapering render schedule (16, 16, 16, 8, 4, 4) with the NCCL gather")
     ap.add_argument("--cpu-runs", type=int, default=5)
     ap.add_argument("--e2e-frames", type=int, default=16)

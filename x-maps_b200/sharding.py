@@ -54,6 +54,35 @@ class FrameSharder:
         self.chunks = [max(1, int(c)) for c in sizes] or [8]
         self.chunk = self.chunks[0]
         self._comm_stream = None
+        self._remote = None  # peer-copy mode: this rank's slab of the destination's gather buffer (CUDA IPC mapping)
+
+    def enable_peer_copies(self, gathered: Optional[List[torch.Tensor]]) -> bool:
+        """Gather with copy-engine peer copies instead of NCCL kernels: rank ``dst`` exports its per-rank gather
+        slabs through CUDA IPC, every other rank maps its own slab and writes finished frames straight into it
+        (``cudaMemcpyPeerAsync`` over NVLink).  No SM is involved, so the copies overlap the persistent render
+        kernel, which NCCL's copy kernels cannot (they find no free SM resources next to it).  All ranks of one
+        node only.  Returns False (and stays on ``dist.gather``) if any rank could not map its slab."""
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        ok = 1
+        payload = [None]
+        try:
+            if self.rank == self.dst:
+                payload = [[reduce_tensor(g) for g in gathered]]
+            dist.broadcast_object_list(payload, src=self.dst, group=self.group)
+            if self.rank != self.dst:
+                fn, args = payload[0][self.rank]
+                self._remote = fn(*args)
+        except Exception:  # noqa: BLE001 - any failure means: fall back to NCCL on every rank
+            ok = 0
+        dev = torch.device("cuda", torch.cuda.current_device())
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) != 1:
+            self._remote = None
+            return False
+        self._peer = True
+        return True
 
     def _spans(self, n):
         lo, k = 0, 0
@@ -62,6 +91,8 @@ class FrameSharder:
             hi = min(n, lo + size)
             yield lo, hi
             lo, k = hi, k + 1
+
+    _peer = False
 
     def _gather_chunk(self, send: torch.Tensor, recv: Optional[List[torch.Tensor]], async_op: bool):
         if self.world == 1:
@@ -90,7 +121,11 @@ class FrameSharder:
                 done.record(torch.cuda.current_stream(out_local.device))
                 with torch.cuda.stream(self._comm_stream):
                     self._comm_stream.wait_event(done)
-                    works.append(self._gather_chunk(out_local[lo:hi], recv, async_op=True))
+                    if self._peer:
+                        if self._remote is not None:  # (the destination's own frames are already in place)
+                            self._remote[lo:hi].copy_(out_local[lo:hi], non_blocking=True)
+                    else:
+                        works.append(self._gather_chunk(out_local[lo:hi], recv, async_op=True))
             else:
                 self._gather_chunk(out_local[lo:hi], recv, async_op=False)
         if on_cuda and self._comm_stream is not None:
