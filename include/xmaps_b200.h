@@ -155,13 +155,20 @@ int xm_ctx_set_colormap(XmCtx* ctx, const uint8_t* h_bgr256);
  *   "lookahead"       extra columns fetched ahead of a time-sorted stream                       [1]
  *   "auto_fixup"      0/1  with XM_TBOUNDS_SORTED / _GIVEN: when an event lies outside the assumed
  *                     bounds, redo the frame on the device with exact (reduced) bounds         [1]
+ *   "batch"           xm_frame_batch on uniform batches: 1 = batch_kernel (one persistent kernel per <= 32
+ *                     frames: staged event pipeline + epilogue warp groups), 2 = batch2_kernel (same batch
+ *                     structure, plain-load event warps), 0 = the per-frame kernels back to back   [1]
+ *   "reserve_sms"     SMs the persistent batch kernel leaves free (e.g. for NCCL's copy kernels)  [0]
  *   "ctas_per_sm"     resident CTAs per SM for the event kernel, 0 = occupancy query            [0]
  *   "region_cells"    shared-memory cells per buffer of the projector-view epilogue             [3072]
  *   "profile"         1 / 0: record CUDA events around K1 (per-event kernel) and K2 (per-pixel
  *                     epilogue) of every frame; -1 resets the accumulators.  Read back with
- *                     "profile_k1_ns", "profile_k2_ns", "profile_frames" (these synchronise)
+ *                     "profile_k1_ns", "profile_k2_ns", "profile_frames", "profile_launches" (these
+ *                     synchronise; a batch launch counts once in profile_launches, its frames in profile_frames)
  *   "epoch"           test hook: clear the scatter map and set its 16-bit frame counter
- * read-only (xm_ctx_get_option): "cap_cols", "occupancy", "sm_count", "event_smem_bytes". */
+ * read-only (xm_ctx_get_option): "cap_cols", "occupancy", "sm_count", "event_smem_bytes", "batch_occ",
+ * "batch_smem", "batch_cols".  The environment variable XMAPS_B200_OPTS="key=value,key=value" applies options to
+ * every context at creation (A/B runs without code changes). */
 int xm_ctx_set_option(XmCtx* ctx, const char* key, int64_t value);
 int xm_ctx_get_option(XmCtx* ctx, const char* key, int64_t* value);
 
@@ -175,7 +182,12 @@ int xm_ctx_get_option(XmCtx* ctx, const char* key, int64_t* value);
  * (disp_to_depth.py:76-97) and disparity_to_depth_rectified (disp_to_depth.py:46-63);
  * with XM_OUT_BGR also colorize_depth_from_disp (disp_to_depth.py:99-115). */
 int xm_frame(XmCtx* ctx, const XmFrameArgs* args, void* stream);
-/* Same for `n_frames` independent frames back to back on one stream. */
+/* Same for `n_frames` independent frames on one stream (process_ev_frame keeps no state across frames).
+ * Batches that are uniform -- one view / output / flag set / z range, integer timestamps, bounds SORTED or
+ * GIVEN, verified tables -- are rendered by ONE persistent kernel per <= 32 frames (option "batch"): the
+ * epilogue of a frame overlaps the event stream of the next ones, and frames whose assumed bounds turn out
+ * wrong are re-rendered exactly on the device.  Anything else falls back to xm_frame per frame.  Results are
+ * identical either way.  xm_frame_status afterwards reports the LAST frame of the batch. */
 int xm_frame_batch(XmCtx* ctx, const XmFrameArgs* args, int32_t n_frames, void* stream);
 /* Copies the status block of the most recent frame to the host; synchronises `stream`. */
 int xm_frame_status(XmCtx* ctx, XmFrameStatus* h_status, void* stream);
