@@ -106,11 +106,11 @@ def time_to_xmap_column(t: np.ndarray, t_px_scale: int, t_min=None, t_max=None) 
     t = np.asarray(t)
     lo = t.min() if t_min is None else t_min
     hi = t.max() if t_max is None else t_max
-    with np.errstate(invalid="ignore", divide="ignore"):
-        norm = (t - lo) / (hi - lo)
-        col = np.rint(norm * t_px_scale)
-        col = np.where(np.isnan(col), 0.0, col)
-        return col.astype(np.int16)
+    if hi == lo:
+        # every quotient is 0/0 = NaN (NumPy warns and casts NaN -> int16 as 0 on x86-64)
+        return np.zeros(t.shape, dtype=np.int16)
+    norm = (t - lo) / (hi - lo)
+    return np.rint(norm * t_px_scale).astype(np.int16)
 
 
 def event_disparity(tables: OracleTables, xcr: np.ndarray, ycr: np.ndarray, t: np.ndarray):
@@ -137,9 +137,17 @@ def event_disparity(tables: OracleTables, xcr: np.ndarray, ycr: np.ndarray, t: n
 # A3  scatter into a disparity map (last write wins)
 # --------------------------------------------------------------------------------------
 def _last_write_wins_scatter(shape, rows, cols, values) -> np.ndarray:
-    """``m[rows, cols] = values`` with the reference's semantics made explicit: for duplicate
-    targets the *last* occurrence (highest event index) is kept.  Implemented without relying
-    on NumPy's unspecified duplicate-assignment order: sort-free reverse-unique."""
+    """``m[rows, cols] = values`` exactly as the reference writes it (python/cam_proj_calibration.py:301-302,
+    315-316): one fancy assignment into a zeroed float32 map.  For duplicate targets NumPy keeps the LAST
+    occurrence (documented for integer-array assignment; ``_last_write_wins_scatter_explicit`` spells the rule
+    out without relying on it and tests/test_oracle_properties.py holds the two together)."""
+    out = np.zeros(shape, dtype=np.float32)
+    out[rows, cols] = values
+    return out
+
+
+def _last_write_wins_scatter_explicit(shape, rows, cols, values) -> np.ndarray:
+    """The same scatter with the duplicate rule made explicit: the highest event index wins."""
     out = np.zeros(shape, dtype=np.float32)
     if len(values) == 0:
         return out
@@ -155,17 +163,11 @@ def scatter_projector_view(tables: OracleTables, xcr, ycr, mask, disp) -> np.nda
     """python/cam_proj_calibration.py:299-303 (compute_disp_map_projector_view).
 
     ``xpr = int16(rint(xcr + disp))`` is int16 + int16 (wraps), i.e. ``x_proj - X_OFFSET``.
-    Negative indices follow NumPy's wrap-around; out-of-range ones raise IndexError as the
-    reference does.
+    Negative indices follow NumPy's wrap-around; out-of-range ones raise IndexError (NumPy's own
+    check, as in the reference).
     """
-    xpr = (xcr[mask].astype(np.int32) + disp.astype(np.int32)).astype(np.int16).astype(np.int64)
-    ypr = ycr[mask].astype(np.int64)
-    h, w = tables.rect_h, tables.rect_w
-    if len(xpr) and (xpr.min() < -w or xpr.max() >= w or ypr.min() < -h or ypr.max() >= h):
-        raise IndexError("scatter target outside the rectified disparity map")
-    xpr = np.where(xpr < 0, xpr + w, xpr)
-    ypr = np.where(ypr < 0, ypr + h, ypr)
-    return _last_write_wins_scatter((h, w), ypr, xpr, disp)
+    xpr = np.rint(xcr[mask] + disp).astype(np.int16)  # the reference's own expression (:300)
+    return _last_write_wins_scatter((tables.rect_h, tables.rect_w), ycr[mask], xpr, disp)
 
 
 def scatter_camera_view(tables: OracleTables, events, mask, disp) -> np.ndarray:
@@ -334,6 +336,42 @@ def synth_events(seed: int, n: int, cam_w: int, cam_h: int, frame_us: int = 1666
     t = np.sort(rng.integers(0, frame_us, n))
     ev = np.zeros(n, dtype=EVENT_DTYPE)
     ev["x"], ev["y"], ev["p"], ev["t"] = x, y, p, t + t0
+    return ev
+
+
+def synth_plane_events(tables: OracleTables, time_map_rect: np.ndarray, z: float, frame_us: int = 16666, repeat: int = 1,
+                       jitter_us: int = 0, seed: int = 0, t0: int = 0) -> np.ndarray:
+    """The ~100 %-inlier workload (SURVEY.md §8c "sanity oracle", §8d input 1): a fronto-parallel plane at
+    depth ``z`` seen by the rig.  It has the shape of the reference's real input
+    (python/eval/compute_depth_x_maps.py:83-96: one event per lit camera pixel, ``t`` from a time map):
+    every camera pixel (x, y) with rectified coordinates (xcr, ycr) fires when the projector column that
+    lights it passes, ``d = round(P2[0,3] / z)``, ``t = rint(time_map_rect[ycr, xcr + d] * frame_us)``;
+    pixels whose target lies outside the rectified image or in an undefined (0) part of the time map stay
+    dark.  Events come out time-sorted (stable: row-major pixel order inside one microsecond), ``p = 1``.
+
+    ``repeat`` > 1 lets every lit pixel fire ``repeat`` times (an event camera emits a burst per edge),
+    each with an extra uniform integer jitter in [-jitter_us, jitter_us] (seeded), clipped to the frame."""
+    d = int(np.rint(tables.depth_scale / z))
+    ys, xs = np.mgrid[0 : tables.cam_h, 0 : tables.cam_w]
+    xcr = tables.lut_x.astype(np.int64)
+    ycr = tables.lut_y.astype(np.int64)
+    xp = xcr + d
+    h, w = time_map_rect.shape
+    lit = (ycr >= 0) & (ycr < h) & (xp >= 0) & (xp < w)
+    tm = np.zeros(xcr.shape, dtype=np.float64)
+    tm[lit] = time_map_rect[ycr[lit], xp[lit]]
+    lit &= tm > 0
+    t = np.rint(tm[lit] * frame_us).astype(np.int64)
+    x, y = xs[lit], ys[lit]
+    if repeat > 1:
+        rng = np.random.default_rng(seed)
+        t = np.repeat(t, repeat)
+        x, y = np.repeat(x, repeat), np.repeat(y, repeat)
+        if jitter_us > 0:
+            t = np.clip(t + rng.integers(-jitter_us, jitter_us + 1, len(t)), 0, frame_us - 1)
+    order = np.argsort(t, kind="stable")
+    ev = np.zeros(len(t), dtype=EVENT_DTYPE)
+    ev["x"], ev["y"], ev["p"], ev["t"] = x[order], y[order], 1, t[order] + t0
     return ev
 
 
