@@ -165,9 +165,13 @@ int xm_ctx_set_colormap(XmCtx* ctx, const uint8_t* h_bgr256);
  *                     epilogue) of every frame; -1 resets the accumulators.  Read back with
  *                     "profile_k1_ns", "profile_k2_ns", "profile_frames", "profile_launches" (these
  *                     synchronise; a batch launch counts once in profile_launches, its frames in profile_frames)
+ *   "alive"           1: the batch kernel consults a shared-memory bitmap (one bit per 4x4 camera-pixel block,
+ *                     derived exactly from the LUT and the X-map at upload: can ANY time column make an
+ *                     event of the block an inlier?) and only counts / bounds-checks events of dead
+ *                     blocks -- no LUT gather, X-map lookup or scatter for them; 0: every event is looked up [1]
  *   "epoch"           test hook: clear the scatter map and set its 16-bit frame counter
  * read-only (xm_ctx_get_option): "cap_cols", "occupancy", "sm_count", "event_smem_bytes", "batch_occ",
- * "batch_smem", "batch_cols".  The environment variable XMAPS_B200_OPTS="key=value,key=value" applies options to
+ * "batch_smem", "batch_cols", "alive_px" (camera pixels inside alive blocks).  The environment variable XMAPS_B200_OPTS="key=value,key=value" applies options to
  * every context at creation (A/B runs without code changes). */
 int xm_ctx_set_option(XmCtx* ctx, const char* key, int64_t value);
 int xm_ctx_get_option(XmCtx* ctx, const char* key, int64_t* value);
@@ -251,6 +255,28 @@ int xm_filter_events(XmCtx* ctx, const void* d_events, int64_t n, int32_t mode, 
  * keeps events[next_idx - 2 :];  0: candidate rejected, keep events[next_idx :];  -1: none, keep nothing. */
 int xm_find_trigger(XmCtx* ctx, const void* d_events, int64_t n, int64_t pause_thresh_us, double frame_us,
                     int64_t min_events, int64_t* d_result /* [8] */, void* stream);
+
+/* ---- multi-GPU: depth frames gathered without a collective kernel ---------------
+ * One process per GPU, frames sharded round-robin; the path itself exchanges nothing.  The only transfer is the
+ * final gather of finished depth frames on one rank.  The reference has no multi-GPU code (nothing to mirror);
+ * these calls let rank r place its frames straight into the gathering rank's memory over NVLink / NVSwitch:
+ *   - the gathering rank allocates its slab with xm_peer_alloc (a plain cudaMalloc, so the IPC handle refers to
+ *     the allocation base) and sends the 64-byte handle to its peers (any host channel, e.g. torch.distributed);
+ *   - a peer maps it with xm_peer_open (peer access to `owner_device` is enabled explicitly and checked) and
+ *     either passes the mapped pointer as XmFrameArgs.d_out -- the epilogue warps of the frame / batch kernels
+ *     then store finished tiles directly into the gathering rank's HBM, a fused compute + gather with no extra
+ *     kernel and no SM taken from the persistent kernel -- or copies finished frames with xm_peer_copy
+ *     (cudaMemcpyPeerAsync: copy engines, no SM either). */
+typedef struct XmIpcHandle {
+    unsigned char bytes[64]; /* cudaIpcMemHandle_t */
+} XmIpcHandle;
+int xm_peer_alloc(int device, int64_t bytes, void** d_ptr, XmIpcHandle* handle);
+int xm_peer_free(int device, void* d_ptr);
+int xm_peer_open(int device, int owner_device, const XmIpcHandle* handle, void** d_ptr);
+int xm_peer_close(int device, void* d_ptr);
+int xm_peer_copy(void* d_dst, int dst_device, const void* d_src, int src_device, int64_t bytes, void* stream);
+/* can_access[0] = 1 if `device` can map memory of `peer_device`, perf_rank[0] = cudaDevP2PAttrPerformanceRank */
+int xm_peer_info(int device, int peer_device, int32_t* can_access, int32_t* perf_rank);
 
 /* ---- set-up time ("next" row N3) --------------------------------------------------------- */
 /* compute_x_map_from_time_map (python/x_map.py:5-55): float32 time map [h, w] (device) ->

@@ -1,4 +1,4 @@
-"""bench.py's contract where it can run without a GPU: the reference arm (CPU oracle port) prints ONE JSON line
+"""bench.py's contract where it can run without a GPU: the reference arm (oracle/_ref or the port) prints ONE JSON line
 with the agreed keys, and the product arm refuses to run without CUDA instead of falling back to the CPU."""
 import json
 import os
@@ -28,7 +28,18 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["metric"] == "events/sec" and d["unit"] == "events/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1
     assert d["config"]["workload"].startswith("synthetic Poisson stream")
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 2 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_chain
+
+    # the reference's own modules (oracle/_ref) when they were built, the NumPy restatement otherwise
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_chain.available() else "port")
+    assert d["cpu_baseline"]["cores"] == 2 and d["cpu_baseline"]["value"] == d["value"]
+    # both arms print the same `config` (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import argparse
+
+    import bench
+
+    assert d["config"] == bench.make_config("5m", argparse.Namespace(events=20000))
     assert d["e2e"] == {"value": d["value"], "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
 

@@ -187,3 +187,68 @@ def test_default_geometry_1m_events(default):
         # the other frames against the single-frame kernels
         for i in (1, 2, 4):
             assert np.array_equal(out[i], eng.frame(frames[i], view=view).cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------
+# the "alive" bitmap (events whose 4x4 pixel block can never yield an inlier are only counted / bounds-checked)
+# ------------------------------------------------------------------------------------------------
+def alive_blocks(tables):
+    """Host restatement of xm_capi.cu:build_alive: per camera pixel, can ANY time column make it an inlier?"""
+    xm = tables.x_map.astype(np.int32)
+    ly, lx = tables.lut_y.astype(np.int32), tables.lut_x.astype(np.int32)
+    h, w = ly.shape
+    alive = np.zeros((h, w), bool)
+    y_ok = (ly >= 0) & (ly < xm.shape[0] - 1)
+    for y in range(h):
+        for x in range(w):
+            if not y_ok[y, x]:
+                continue
+            d = (xm[ly[y, x]] - lx[y, x] - tables.x_offset).astype(np.int16)
+            alive[y, x] = bool((d >= 0).any())
+    bh, bw = (h + 3) // 4, (w + 3) // 4
+    pad = np.zeros((bh * 4, bw * 4), bool)
+    pad[:h, :w] = alive
+    blocks = pad.reshape(bh, 4, bw, 4).any(axis=(1, 3))
+    return alive, blocks
+
+
+def test_alive_bitmap_is_exact_and_invisible(small):
+    tables, _, eng = small
+    alive, blocks = alive_blocks(tables)
+    px_in_alive_blocks = int(np.kron(blocks, np.ones((4, 4), bool))[: tables.cam_h, : tables.cam_w].sum())
+    assert eng.get_option("alive_px") == px_in_alive_blocks
+    assert 0 < px_in_alive_blocks < tables.cam_h * tables.cam_w  # the small geometry has dead blocks
+    frames = [orc.synth_events(700 + i, 30_000 + 1000 * i, 160, 120) for i in range(5)]
+    outs = {}
+    for flag in (1, 0):
+        eng.set_option("alive", flag)
+        outs[flag] = [eng.frame_batch(frames, view=v).cpu().numpy() for v in (0, 1)]
+        st = eng.status()
+        outs[flag].append((st["n_valid"], st["n_inliers"], st["flags"]))
+    eng.set_option("alive", 1)
+    for v in (0, 1):
+        assert np.array_equal(outs[1][v], outs[0][v])
+        for i, f in enumerate(frames):
+            assert np.array_equal(outs[1][v][i], orc.frame_depth(tables, f, v))
+    assert outs[1][2] == outs[0][2]
+
+
+def test_dead_pixel_event_outside_bounds_still_triggers_the_redo(small):
+    """t.min() / t.max() run over ALL kept events (x_maps_disparity.py:12-13), dead pixels included: an
+    out-of-order timestamp on a dead pixel must invalidate the frame's assumed bounds like any other."""
+    tables, _, eng = small
+    _, blocks = alive_blocks(tables)
+    by, bx = np.argwhere(~blocks)[0]
+    ev = orc.synth_events(41, 40_000, 160, 120)
+    ev["p"] = 1
+    k = 20_000
+    ev["x"][k], ev["y"][k] = bx * 4, by * 4
+    ev["t"][k] = ev["t"].min() - 500  # earlier than the first event: the sorted-bounds assumption is wrong
+    other = orc.synth_events(42, 10_000, 160, 120)
+    out = eng.frame_batch([other, ev, other], view=0).cpu().numpy()
+    assert np.array_equal(out[1], orc.frame_depth(tables, ev, 0))
+    assert np.array_equal(out[0], orc.frame_depth(tables, other, 0)) and np.array_equal(out[0], out[2])
+    # and alone, so that the status block is this frame's
+    got = eng.frame_batch([ev, ev], view=0).cpu().numpy()
+    assert np.array_equal(got[1], orc.frame_depth(tables, ev, 0))
+    assert eng.status()["fixup_ran"]

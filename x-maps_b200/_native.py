@@ -76,6 +76,10 @@ class XmFrameStatus(C.Structure):
     ]
 
 
+class XmIpcHandle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * 64)]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _I32 = C.c_int32
@@ -109,6 +113,12 @@ SIGNATURES = {
     "xm_polarity_filter": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "xm_filter_events": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P, _P, _P]),
     "xm_find_trigger": (C.c_int, [_P, _P, _I64, _I64, C.c_double, _I64, _P, _P]),
+    "xm_peer_alloc": (C.c_int, [C.c_int, _I64, C.POINTER(_P), C.POINTER(XmIpcHandle)]),
+    "xm_peer_free": (C.c_int, [C.c_int, _P]),
+    "xm_peer_open": (C.c_int, [C.c_int, C.c_int, C.POINTER(XmIpcHandle), C.POINTER(_P)]),
+    "xm_peer_close": (C.c_int, [C.c_int, _P]),
+    "xm_peer_copy": (C.c_int, [_P, C.c_int, _P, C.c_int, _I64, _P]),
+    "xm_peer_info": (C.c_int, [C.c_int, C.c_int, C.POINTER(_I32), C.POINTER(_I32)]),
     "xm_build_xmap": (C.c_int, [C.c_int, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
 }
 

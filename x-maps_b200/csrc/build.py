@@ -24,11 +24,28 @@ NVCC_FLAGS = [
 LINK_LIBS = ["-lcudadevrt"]
 
 
+STAMP = OUT + ".srchash"
+
+
+def source_hash():
+    """sha256 over every source the library is built from + the flags: the built library carries the hash of
+    its sources next to it, so a stale .so (e.g. one that travelled with a snapshot whose sources changed, or
+    whose mtimes were reset by a copy) is rebuilt, and an up-to-date one is not."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for d in sorted(DEPS):
+        with open(os.path.join(HERE, d), "rb") as fh:
+            h.update(d.encode() + b"\0" + fh.read())
+    h.update(" ".join(NVCC_FLAGS + LINK_LIBS + os.environ.get("XM_NVCC_EXTRA", "").split()).encode())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(HERE, d)) > t for d in DEPS)
+    with open(STAMP) as fh:
+        return fh.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -44,6 +61,8 @@ def build(force=False, verbose=False):
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode:
         raise RuntimeError("nvcc failed building libxmaps_b200.so")
+    with open(STAMP, "w") as fh:
+        fh.write(source_hash() + "\n")
     return OUT
 
 

@@ -58,6 +58,11 @@ struct BatchParams {
     int t_px_scale, x_offset;
     int rect_w, rect_h;
     int cap_cols, stages, win_stages;
+    // "alive" bitmap: one bit per 4x4 block of camera pixels, set if ANY time column can make an event of a pixel of
+    // the block an inlier (derived from the LUT and the X-map at table upload, exact).  Events of dead blocks are
+    // only counted and bounds-checked: no LUT gather, no X-map lookup, no scatter.
+    const unsigned* alive;
+    int alive_bw, alive_words;  // blocks per row, 32-bit words (a multiple of 4)
     unsigned long long* maps[kBatchMaps];
     unsigned epoch0;        // frame f scatters with epoch0 + f
     FrameState* states;     // [n_frames + 1]; block n_frames is the control block (next_chunk = item counter)
@@ -75,9 +80,9 @@ struct BatchParams {
 
 __host__ __device__ __forceinline__ unsigned batch_chunks(long long n) { return static_cast<unsigned>((n + kEvChunk - 1) / kEvChunk); }
 
-inline int batch_smem_bytes(int stages, int win_stages, int win_bytes, int region_cells) {
-    // header | LUT double buffer | event ring | X-map window ring | two u16 regions per tile group
-    return kBatchHeader + kEvLutBytes + stages * (kEvChunk * 16) + win_stages * win_bytes + kTileGroups * region_cells * 4;
+inline int batch_smem_bytes(int stages, int win_stages, int win_bytes, int region_cells, int alive_words = 0) {
+    // header | LUT double buffer | event ring | X-map window ring | two u16 regions per tile group | alive bitmap
+    return kBatchHeader + kEvLutBytes + stages * (kEvChunk * 16) + win_stages * win_bytes + kTileGroups * region_cells * 4 + alive_words * 4;
 }
 
 struct BatchBoundsParams {
@@ -229,6 +234,8 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
         }
     }
     if (tid < 32) s_acc[tid] = 0u;
+    unsigned* const s_alive = reinterpret_cast<unsigned*>(win_ring + bp.win_stages * win_bytes + kTileGroups * bp.ep.region_cap * 4);
+    for (int i = tid; i < bp.alive_words; i += kBatchThreads) s_alive[i] = __ldg(bp.alive + i);
     __syncthreads();
 
     if (warp > kEvThreads / 32) {
@@ -342,6 +349,7 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
     const unsigned a_lut = sbase + kBatchHeader + tid * 4;                   // + parity * 4096 + k * 1024
     const unsigned a_ring = sbase + kBatchHeader + lut_tile + tid * 16;      // + slot * 16384 + k * 4096
     const unsigned a_win = sbase + kBatchHeader + lut_tile + bp.stages * (kEvChunk * 16);
+    const unsigned a_alive = smem_u32(s_alive);
     // geometry is read from the parameter bank where it is used (constant operands, no registers)
 #define XM_B_YLIM (static_cast<unsigned>(bp.xmap_h) - 1u)
 #define XM_B_CAMW (static_cast<unsigned>(bp.cam_w))
@@ -439,7 +447,8 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
 
     // FRONT half of chunk g of frame f (stage fe): events into registers, LUT gathers started, time columns
     // computed; releases the stage.  col[k]: time column, or -1 event not kept (polarity / past the end),
-    // -2 pixel outside the camera image, -3 timestamp outside the assumed bounds.
+    // -2 kept but its pixel block can never yield an inlier (counted, nothing else), -3 pixel outside the
+    // camera image, -4 timestamp outside the assumed bounds.
     auto front = [&](int f, int g, int (&col)[kEvPerThread], int (&pix)[kEvPerThread]) -> unsigned {
         if (f != front_f) prepare_frame(f);
         const unsigned a_fcf = a_fc + fslot * 48;
@@ -459,7 +468,7 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
         }
         const unsigned left = static_cast<unsigned>(lds32_a(a_fcf + 44)) - static_cast<unsigned>(g) * kEvChunk;
         const int limit = left < kEvChunk ? static_cast<int>(left) : kEvChunk;
-        unsigned bad_mask = 0;
+        unsigned bad_mask = 0, dead_mask = 0;
         // two events at a time: half the registers for the raw records (the per-event loop must not spill)
 #pragma unroll
         for (int h = 0; h < kEvPerThread; h += 2) {
@@ -474,13 +483,18 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
                 if (limit < kEvChunk) valid = valid && (k * kEvThreads + tid < limit);
                 const bool ok = valid && ex < XM_B_CAMW && ey < XM_B_CAMH;
                 const int px = static_cast<int>(ey * XM_B_CAMW + ex);
-                if (ok) cp_async_4_a(a_lut_c + k * (kEvThreads * 4), bp.lut_xy + px);
+                // can a pixel of this 4x4 block ever be an inlier?  (shared-memory bitmap; block 0 for events that are dropped anyway)
+                const unsigned blk = ok ? (ey >> 2) * static_cast<unsigned>(bp.alive_bw) + (ex >> 2) : 0u;
+                const bool live = ok && ((static_cast<unsigned>(lds32_a(a_alive + (blk >> 5) * 4u)) >> (blk & 31u)) & 1u);
+                if (live) cp_async_4_a(a_lut_c + k * (kEvThreads * 4), bp.lut_xy + px);
                 const long long t_bits = (static_cast<long long>(raw[j].w) << 32) | static_cast<unsigned>(raw[j].z);
                 bool bad;
                 const unsigned q = ic.column(t_bits, bad);
-                col[k] = ok ? static_cast<int>(q) : (valid ? -2 : -1);
+                col[k] = live ? static_cast<int>(q) : (ok ? -2 : (valid ? -3 : -1));
                 if (CAM) pix[k] = px;
+                // dead events too: a timestamp outside the assumed bounds invalidates the frame's normalisation
                 bad_mask |= (ok && (bad || !ic.ok)) ? (1u << k) : 0u;
+                dead_mask |= (ok && !live) ? (1u << k) : 0u;
             }
         }
         cp_async_commit();
@@ -496,7 +510,7 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
                 int cc = tc.column(t_bits, viol);
                 if (cc < 0) cc += bp.xmap_w;  // NumPy negative index (only reachable with wrong bounds)
                 viol = viol || cc < 0 || cc >= bp.xmap_w;
-                col[k] = viol ? -3 : cc;
+                col[k] = viol ? -4 : ((dead_mask >> k) & 1u ? -2 : cc);
             }
         }
         release();
@@ -529,18 +543,18 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
         unsigned hit_mask = 0, miss_mask = 0;
         {   // statistics of the chunk (col < 0: see front)
             unsigned kept = 0;
-            int special = 0;
+            int lowest = 0;
 #pragma unroll
             for (int k = 0; k < kEvPerThread; ++k) {
                 kept += col[k] != -1;
-                special |= col[k] + 1;  // negative only for -2 / -3
+                lowest = min(lowest, col[k]);
             }
             n_valid += kept;
-            if (special < 0) {
+            if (lowest <= -3) {
 #pragma unroll
                 for (int k = 0; k < kEvPerThread; ++k) {
-                    if (col[k] == -2) flags |= kStatusPixelOob;  // the reference raises IndexError here
-                    if (col[k] == -3) flags |= kStatusTBounds;
+                    if (col[k] == -3) flags |= kStatusPixelOob;  // the reference raises IndexError here
+                    if (col[k] == -4) flags |= kStatusTBounds;
                 }
             }
         }

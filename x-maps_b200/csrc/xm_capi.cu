@@ -6,6 +6,7 @@
 // records a thread-local message for xm_last_error().
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -73,6 +74,13 @@ struct XmCtx {
     int xmap_w = 0, xmap_h = 0, col_stride = 0, t_px_scale = 0, x_offset = 0, dilate = 7;
     double depth_scale = 0.0;
     int* d_lut_xy = nullptr;
+    std::vector<int> h_lut_xy;          // host copy of the packed LUT (the alive bitmap is rebuilt when the X-map changes)
+    unsigned* d_alive = nullptr;        // [alive_words] one bit per 4x4 camera-pixel block: some time column can make it an inlier
+    unsigned* d_alive_ones = nullptr;   // all ones (option alive = 0)
+    int alive_bw = 0, alive_words = 0;
+    long long alive_px = 0;             // camera pixels inside alive blocks (diagnostic, option "alive_px")
+    int opt_alive = 1;
+    int lut_x_min = 0;                  // smallest rectified x of the LUT (lut_safe = lut_x_min > -x_offset)
     float* d_lut_x_f32 = nullptr;
     float* d_lut_y_f32 = nullptr;
     short* d_xmap_t = nullptr;
@@ -113,6 +121,7 @@ struct XmCtx {
     int opt_smem_cols_bytes = 12 * 1024;
     int opt_k2_variant = 1;   // 1: sliding-window epilogue (7x7, even rect_w), 0: per-tap epilogue
     int opt_reserve_sms = 0;  // SMs the persistent batch kernel leaves free (room for NCCL's copy kernels next to it)
+    int opt_coop = 1;         // 1: frame_kernel (grid barrier inside) is launched cooperatively
     int opt_fused = 1;        // 1: one fused kernel per frame where the lean path applies
     int fused_occ = 0;        // resident CTAs per SM of frame_kernel
     int opt_batch = 1;        // 1: xm_frame_batch renders uniform batches with one persistent kernel per <= 32 frames
@@ -202,19 +211,39 @@ EvKernel ev_kernel(bool f64, bool safe, int variant = 0, bool cam = false) {
 
 // Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may start
 // while its predecessor in the stream is still running and synchronises with griddepcontrol.wait.
+// `coop`: cooperative launch -- the runtime guarantees that every CTA of the grid is resident at the same time (or
+// rejects the launch), which a kernel with a hand-rolled grid barrier needs when other streams, NCCL or a second
+// context share the GPU.
 template <typename P>
-cudaError_t launch_pdl(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, const P& params) {
+cudaError_t launch_pdl(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, const P& params, bool coop = false) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = pdl ? attr : nullptr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, params);
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (coop) {
+        attr[n].id = cudaLaunchAttributeCooperative;
+        attr[n].val.cooperative = 1;
+        ++n;
+    }
+    cfg.attrs = n ? attr : nullptr;
+    cfg.numAttrs = n;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, params);
+    if (e != cudaSuccess && pdl && coop) {
+        // the two attributes together are refused by some drivers: keep the co-residency guarantee, drop the overlap
+        cudaGetLastError();
+        cfg.attrs = attr + 1;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kernel, params);
+    }
+    return e;
 }
 
 int configure_event_kernels(XmCtx* c) {
@@ -271,7 +300,7 @@ int configure_event_kernels(XmCtx* c) {
     c->batch_occ = 0;
     if (variant == 2) {
         int bcols = cols;
-        auto smem_for = [&](int k) { return xm::batch_smem_bytes(c->opt_stages, c->opt_win_stages, k * c->col_stride * 2, c->opt_region_cells); };
+        auto smem_for = [&](int k) { return xm::batch_smem_bytes(c->opt_stages, c->opt_win_stages, k * c->col_stride * 2, c->opt_region_cells, c->alive_words); };
         while (bcols > 0 && 2 * (smem_for(bcols) + 1024) > 196 * 1024) --bcols;
         c->batch_cols = bcols;
         c->batch_smem = smem_for(bcols);
@@ -313,11 +342,78 @@ int configure_event_kernels(XmCtx* c) {
     return XM_OK;
 }
 
+// One bit per 4x4 block of camera pixels: can ANY time column make an event of a pixel of the block an inlier?
+// Exactly the reference's conditions (x_maps_disparity.py:23-30) evaluated for every value of the pixel's X-map
+// row: 0 <= y_rect < rows - 1 and int16(x_map[y_rect, col] - x_rect - X_OFFSET) >= 0 for some col.
+int build_alive(XmCtx* c, const int16_t* h_x_map, int rows, int cols, int x_offset) {
+    const int bw = (c->cam_w + 3) / 4, bh = (c->cam_h + 3) / 4;
+    const int words = ((bw * bh + 31) / 32 + 3) & ~3;
+    std::vector<std::vector<short>> uniq(rows);
+    {
+        std::vector<unsigned char> seen(65536);
+        for (int y = 0; y < rows; ++y) {
+            std::fill(seen.begin(), seen.end(), 0);
+            const int16_t* row = h_x_map + static_cast<size_t>(y) * cols;
+            for (int x = 0; x < cols; ++x) {
+                const unsigned u = static_cast<unsigned short>(row[x]);
+                if (!seen[u]) {
+                    seen[u] = 1;
+                    uniq[y].push_back(row[x]);
+                }
+            }
+            std::sort(uniq[y].begin(), uniq[y].end(), [](short a, short b) { return a > b; });  // largest first: the usual witness
+        }
+    }
+    std::vector<unsigned> bits(words, 0u);
+    long long alive_px = 0;
+    for (int y = 0; y < c->cam_h; ++y)
+        for (int x = 0; x < c->cam_w; ++x) {
+            const int packed = c->h_lut_xy[static_cast<size_t>(y) * c->cam_w + x];
+            const int xcr = static_cast<short>(packed & 0xffff), ycr = packed >> 16;
+            if (ycr < 0 || ycr >= rows - 1) continue;
+            bool alive = false;
+            for (short v : uniq[ycr])
+                if (static_cast<short>(v - xcr - x_offset) >= 0) {
+                    alive = true;
+                    break;
+                }
+            if (!alive) continue;
+            const int blk = (y >> 2) * bw + (x >> 2);
+            bits[blk >> 5] |= 1u << (blk & 31);
+        }
+    for (int by = 0; by < bh; ++by)
+        for (int bx = 0; bx < bw; ++bx) {
+            const int blk = by * bw + bx;
+            if (bits[blk >> 5] >> (blk & 31) & 1u) {
+                const int w = std::min(4, c->cam_w - bx * 4), h = std::min(4, c->cam_h - by * 4);
+                alive_px += static_cast<long long>(w) * h;
+            }
+        }
+    if (c->alive_words != words) {
+        cudaFree(c->d_alive);
+        cudaFree(c->d_alive_ones);
+        c->d_alive = c->d_alive_ones = nullptr;
+        XM_CUDA(cudaMalloc(&c->d_alive, words * sizeof(unsigned)));
+        XM_CUDA(cudaMalloc(&c->d_alive_ones, words * sizeof(unsigned)));
+        XM_CUDA(cudaMemset(c->d_alive_ones, 0xff, words * sizeof(unsigned)));
+    }
+    XM_CUDA(cudaMemcpy(c->d_alive, bits.data(), words * sizeof(unsigned), cudaMemcpyHostToDevice));
+    c->alive_bw = bw;
+    c->alive_words = words;
+    c->alive_px = alive_px;
+    return XM_OK;
+}
+
 int upload_xmap(XmCtx* c, const int16_t* h_x_map, int rows, int cols, int t_px_scale, int x_offset) {
     if (!h_x_map || rows <= 0 || cols <= 0) return fail(XM_ERR_INVALID_ARG, "x_map: bad shape %d x %d", rows, cols);
     // asserts of the reference (x_maps_disparity.py:52-53)
     if (rows > 32767) return fail(XM_ERR_TABLE_RANGE, "x_map has %d rows, int16 indices allow 32767", rows);
     if (cols > 32767) return fail(XM_ERR_TABLE_RANGE, "x_map has %d time columns, int16 indices allow 32767", cols);
+    // The kernels index the table with the time column rint(t_norm * t_px_scale) in [0, t_px_scale] without a
+    // bounds test; the reference would raise IndexError for a column >= cols (x_maps_disparity.py:25).
+    if (t_px_scale <= 0 || t_px_scale >= cols)
+        return fail(XM_ERR_INVALID_ARG, "t_px_scale = %d must lie in [1, %d) (time columns of the X-map)", t_px_scale, cols);
+    if (x_offset <= 0 || x_offset > 32767) return fail(XM_ERR_INVALID_ARG, "x_offset = %d must lie in [1, 32767]", x_offset);
     // With every defined X-map cell in [x_offset, x_offset + rect_w) (and LUT x > -x_offset, checked at
     // creation, so that undefined cells can never produce disp >= 0) an inlier's scatter target
     // x_rect + disp = x_map - x_offset is always inside the map: K1 may skip the checks.
@@ -327,6 +423,13 @@ int upload_xmap(XmCtx* c, const int16_t* h_x_map, int rows, int cols, int t_px_s
         safe = v == 0 || (v >= x_offset && v < x_offset + c->rect_w);
     }
     c->xmap_safe = safe;
+    // (re)derive the LUT's half of the check-free scatter condition for THIS x_offset: undefined cells (0) must
+    // never produce disp >= 0, i.e. every rectified x > -x_offset
+    c->lut_safe = c->lut_x_min > -x_offset;
+    {
+        int rc = build_alive(c, h_x_map, rows, cols, x_offset);
+        if (rc) return rc;
+    }
     const int stride = (rows + 7) & ~7;  // 16-byte multiple: one column range = one bulk copy
     std::vector<short> t(static_cast<size_t>(cols) * stride, 0);
     for (int y = 0; y < rows; ++y)
@@ -533,7 +636,8 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
             if (rc) return rc;
         }
         void (*k)(xm::FrameParams) = a->view == XM_VIEW_CAMERA ? xm::frame_kernel<true> : xm::frame_kernel<false>;
-        XM_CUDA(launch_pdl(k, dim3(grid), dim3(xm::kWsThreads), c->ev_smem, s, c->opt_pdl && c->prev_was_frame, fp));
+        // frame_kernel has a grid-wide barrier: launched cooperatively so that co-residency is guaranteed
+        XM_CUDA(launch_pdl(k, dim3(grid), dim3(xm::kWsThreads), c->ev_smem, s, c->opt_pdl && c->prev_was_frame, fp, c->opt_coop != 0));
         XM_LAUNCHED();
         c->prev_was_frame = true;
         if (c->opt_profile) {
@@ -682,6 +786,9 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     bp.cap_cols = c->batch_cols;
     bp.stages = c->opt_stages;
     bp.win_stages = c->opt_win_stages;
+    bp.alive = c->opt_alive ? c->d_alive : c->d_alive_ones;
+    bp.alive_bw = c->alive_bw;
+    bp.alive_words = c->alive_words;
     for (int i = 0; i < xm::kBatchMaps; ++i) bp.maps[i] = c->d_map_ring[i];
     bp.epoch0 = epoch0;
     bp.states = c->d_bstate;
@@ -860,6 +967,7 @@ int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
             max_x = t->lut_x[i] > max_x ? t->lut_x[i] : max_x;
         }
         c->lut_x_max = max_x;
+        c->lut_x_min = min_x;
         c->lut_safe = min_x > -t->x_offset && t->x_offset > 0;
         for (size_t i = 0; i < cam_px; ++i)
             packed[i] = static_cast<int>((static_cast<unsigned>(static_cast<unsigned short>(t->lut_y[i])) << 16) |
@@ -867,6 +975,7 @@ int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
         if (cudaMalloc(&c->d_lut_xy, cam_px * 4) != cudaSuccess ||
             cudaMemcpy(c->d_lut_xy, packed.data(), cam_px * 4, cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(XM_ERR_CUDA, "uploading the rectification LUT failed: %s", cudaGetErrorString(cudaGetLastError())));
+        c->h_lut_xy.swap(packed);
     }
     if (t->lut_x_f32 && t->lut_y_f32) {
         if (cudaMalloc(&c->d_lut_x_f32, cam_px * 4) != cudaSuccess || cudaMalloc(&c->d_lut_y_f32, cam_px * 4) != cudaSuccess ||
@@ -946,6 +1055,8 @@ int xm_ctx_destroy(XmCtx* c) {
     if (!c) return XM_OK;
     DeviceGuard guard(c->device);
     cudaFree(c->d_lut_xy);
+    cudaFree(c->d_alive);
+    cudaFree(c->d_alive_ones);
     cudaFree(c->d_lut_x_f32);
     cudaFree(c->d_lut_y_f32);
     cudaFree(c->d_xmap_t);
@@ -1039,6 +1150,14 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         c->opt_fused = v != 0;
         return XM_OK;
     }
+    if (!strcmp(key, "coop")) { /* 1: cooperative launch of the fused frame kernel (co-residency guaranteed by the runtime) */
+        c->opt_coop = v != 0;
+        return XM_OK;
+    }
+    if (!strcmp(key, "alive")) { /* 1: the batch kernel skips the look-ups of events whose pixel block can never yield an inlier */
+        c->opt_alive = v != 0;
+        return XM_OK;
+    }
     if (!strcmp(key, "pdl")) {
         c->opt_pdl = v != 0;
         return XM_OK;
@@ -1098,6 +1217,9 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     else if (!strcmp(key, "k1_variant")) *value = c->opt_k1_variant;
     else if (!strcmp(key, "pdl")) *value = c->opt_pdl;
     else if (!strcmp(key, "fused")) *value = c->opt_fused;
+    else if (!strcmp(key, "alive")) *value = c->opt_alive;
+    else if (!strcmp(key, "coop")) *value = c->opt_coop;
+    else if (!strcmp(key, "alive_px")) *value = c->alive_px;          /* read-only: camera pixels inside alive blocks */
     else if (!strcmp(key, "batch")) *value = c->opt_batch;
     else if (!strcmp(key, "reserve_sms")) *value = c->opt_reserve_sms;
     else if (!strcmp(key, "batch_occ")) *value = c->opt_batch == 2 ? c->batch2_occ : c->batch_occ;
@@ -1230,6 +1352,77 @@ int xm_host_alloc(void** h_ptr, int64_t bytes) {
 }
 int xm_host_free(void* h_ptr) {
     if (h_ptr) XM_CUDA(cudaFreeHost(h_ptr));
+    return XM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU gather without a collective kernel: CUDA IPC mapping of the gathering rank's slab
+// ---------------------------------------------------------------------------------------------
+int xm_peer_alloc(int device, int64_t bytes, void** d_ptr, XmIpcHandle* handle) {
+    if (!d_ptr || !handle || bytes <= 0) return fail(XM_ERR_INVALID_ARG, "xm_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(XmIpcHandle), "IPC handle size");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(XM_ERR_CUDA, "cannot select device %d", device);
+    *d_ptr = nullptr;
+    XM_CUDA(cudaMalloc(d_ptr, static_cast<size_t>(bytes)));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*d_ptr);
+        *d_ptr = nullptr;
+        return fail(XM_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle->bytes, &h, sizeof(h));
+    return XM_OK;
+}
+
+int xm_peer_free(int device, void* d_ptr) {
+    DeviceGuard guard(device);
+    if (d_ptr) XM_CUDA(cudaFree(d_ptr));
+    return XM_OK;
+}
+
+int xm_peer_open(int device, int owner_device, const XmIpcHandle* handle, void** d_ptr) {
+    if (!d_ptr || !handle) return fail(XM_ERR_INVALID_ARG, "xm_peer_open: bad arguments");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(XM_ERR_CUDA, "cannot select device %d", device);
+    *d_ptr = nullptr;
+    if (owner_device != device) {
+        int can = 0;
+        XM_CUDA(cudaDeviceCanAccessPeer(&can, device, owner_device));
+        if (!can) return fail(XM_ERR_UNSUPPORTED, "device %d cannot access memory of device %d (no P2P path)", device, owner_device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(owner_device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled)
+            cudaGetLastError();  // clear
+        else if (e != cudaSuccess)
+            return fail(XM_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", owner_device, cudaGetErrorString(e));
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle->bytes, sizeof(h));
+    XM_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return XM_OK;
+}
+
+int xm_peer_close(int device, void* d_ptr) {
+    DeviceGuard guard(device);
+    if (d_ptr) XM_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return XM_OK;
+}
+
+int xm_peer_copy(void* d_dst, int dst_device, const void* d_src, int src_device, int64_t bytes, void* stream) {
+    if (bytes < 0 || (bytes > 0 && (!d_dst || !d_src))) return fail(XM_ERR_INVALID_ARG, "xm_peer_copy: bad arguments");
+    if (bytes == 0) return XM_OK;
+    XM_CUDA(cudaMemcpyPeerAsync(d_dst, dst_device, d_src, src_device, static_cast<size_t>(bytes), static_cast<cudaStream_t>(stream)));
+    return XM_OK;
+}
+
+int xm_peer_info(int device, int peer_device, int32_t* can_access, int32_t* perf_rank) {
+    if (!can_access || !perf_rank) return fail(XM_ERR_INVALID_ARG, "xm_peer_info: null output");
+    int can = 0, rank = -1;
+    XM_CUDA(cudaDeviceCanAccessPeer(&can, device, peer_device));
+    if (can) XM_CUDA(cudaDeviceGetP2PAttribute(&rank, cudaDevP2PAttrPerformanceRank, device, peer_device));
+    *can_access = can;
+    *perf_rank = rank;
     return XM_OK;
 }
 

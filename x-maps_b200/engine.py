@@ -209,22 +209,29 @@ class DepthEngine:
         z_far: float = 1.0,
         out: Optional[torch.Tensor] = None,
         t_bounds: Optional[Sequence] = None,
-    ) -> torch.Tensor:
+        out_ptrs: Optional[Sequence[int]] = None,
+    ) -> Optional[torch.Tensor]:
         """Independent frames on one stream -> ``[n_frames, ...]``.  Uniform batches (one view / output,
         integer timestamps) are rendered by ONE persistent kernel per 32 frames (``xm_frame_batch``): the
         epilogue of a frame overlaps the event stream of the next one.  ``t_bounds``: per-frame
-        ``(t_min, t_max)`` for ``TBOUNDS_GIVEN``."""
+        ``(t_min, t_max)`` for ``TBOUNDS_GIVEN``.  ``out_ptrs``: raw device addresses, one per frame, instead of
+        ``out`` -- e.g. peer memory mapped with ``xm_peer_open``, so that the kernels write finished frames
+        straight into another GPU's buffer (``sharding.FrameSharder``); nothing is returned then."""
         evs = [self.events(f) for f in frames]
         shape = self.out_shape(view, output)
         dtype = torch.uint8 if output == OUT_BGR else torch.float32
-        if out is None:
+        if out_ptrs is not None:
+            if len(out_ptrs) != len(evs) or out is not None:
+                raise ValueError("out_ptrs needs one address per frame and excludes out")
+        elif out is None:
             out = torch.empty((len(evs),) + tuple(shape), dtype=dtype, device=self.device)
         elif tuple(out.shape) != (len(evs),) + tuple(shape) or out.dtype != dtype or not out.is_contiguous():
             raise ValueError("out has the wrong shape / dtype")
         arr = (N.XmFrameArgs * max(1, len(evs)))()
         for i, ev in enumerate(evs):
             lo, hi = t_bounds[i] if t_bounds is not None else (None, None)
-            arr[i] = self._args(ev, view, output, time_bounds, polarity, lo, hi, z_near, z_far, out[i].data_ptr())
+            dst = int(out_ptrs[i]) if out_ptrs is not None else out[i].data_ptr()
+            arr[i] = self._args(ev, view, output, time_bounds, polarity, lo, hi, z_near, z_far, dst)
         N.check(N.lib.xm_frame_batch(self._ctx, arr, len(evs), self._stream()))
         return out
 

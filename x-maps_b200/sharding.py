@@ -35,6 +35,18 @@ def global_order(gathered: Sequence[torch.Tensor], n_frames: int) -> torch.Tenso
     return out
 
 
+def _wrap_device_memory(ptr: int, shape, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+    """A torch view of device memory this process owns but torch did not allocate (xm_peer_alloc)."""
+    typestr = {torch.float32: "<f4", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]
+
+    class _Mem:
+        pass
+
+    m = _Mem()
+    m.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2, "strides": None}
+    return torch.as_tensor(m, device=device)
+
+
 class FrameSharder:
     """Renders this rank's frames with ``render(frames, out)`` and gathers all ranks' frames on
     rank ``dst``.
@@ -54,35 +66,92 @@ class FrameSharder:
         self.chunks = [max(1, int(c)) for c in sizes] or [8]
         self.chunk = self.chunks[0]
         self._comm_stream = None
-        self._remote = None  # peer-copy mode: this rank's slab of the destination's gather buffer (CUDA IPC mapping)
+        # peer modes (enable_peer): this rank's slab of the destination's gather buffer, mapped through CUDA IPC
+        self._peer_mode = None
+        self._remote_ptr, self._remote_dev = None, -1
+        self._mapped, self._owned = None, []
+        self._render_ptrs, self._frame_bytes = None, 0
+        self._done_flag = None
+        self.peer_error = None
 
-    def enable_peer_copies(self, gathered: Optional[List[torch.Tensor]]) -> bool:
-        """Gather with copy-engine peer copies instead of NCCL kernels: rank ``dst`` exports its per-rank gather
-        slabs through CUDA IPC, every other rank maps its own slab and writes finished frames straight into it
-        (``cudaMemcpyPeerAsync`` over NVLink).  No SM is involved, so the copies overlap the persistent render
-        kernel, which NCCL's copy kernels cannot (they find no free SM resources next to it).  All ranks of one
-        node only.  Returns False (and stays on ``dist.gather``) if any rank could not map its slab."""
-        from torch.multiprocessing.reductions import reduce_tensor
+    # ------------------------------------------------------------------ gather without a collective kernel
+    def enable_peer(self, out_local: torch.Tensor, mode: str = "direct", render_ptrs: Optional[Callable] = None):
+        """Gather through peer memory instead of ``dist.gather`` (all ranks on one node, NVLink / NVSwitch).
 
+        Rank ``dst`` allocates one slab per other rank with ``xm_peer_alloc`` (C ABI: cudaMalloc + CUDA IPC handle)
+        and broadcasts the handles; rank r maps its slab with ``xm_peer_open`` (peer access enabled explicitly and
+        checked).  Then, per chunk of frames,
+
+        * ``mode="direct"``: ``render_ptrs(frames, ptrs)`` renders with the MAPPED addresses as output, i.e. the
+          epilogue warps of the persistent kernel store finished tiles straight into rank ``dst``'s HBM -- compute
+          and gather fused, no extra kernel, no SM taken from the render kernel;
+        * ``mode="copy"``: frames are rendered locally and moved with ``xm_peer_copy`` (cudaMemcpyPeerAsync, copy
+          engines) on a side stream.
+
+        NCCL's copy kernels, by contrast, cannot be scheduled while the persistent kernel owns the SMs.  Returns the
+        list of per-rank slabs on rank ``dst`` (``[out_local, slab_1, ...]``), ``[]`` on other ranks, or ``None`` if
+        any rank failed to map (every rank then stays on ``dist.gather``)."""
+        import ctypes as C
+
+        from . import _native as N
+
+        if mode not in ("direct", "copy"):
+            raise ValueError("mode must be 'direct' or 'copy'")
+        if mode == "direct" and render_ptrs is None:
+            raise ValueError("mode='direct' needs render_ptrs(frames, ptrs)")
+        dev = out_local.device.index
+        frame_bytes = out_local[0].numel() * out_local.element_size()
+        n_local = out_local.shape[0]
         ok = 1
-        payload = [None]
+        slabs, handles = [], [None] * self.world
         try:
             if self.rank == self.dst:
-                payload = [[reduce_tensor(g) for g in gathered]]
-            dist.broadcast_object_list(payload, src=self.dst, group=self.group)
-            if self.rank != self.dst:
-                fn, args = payload[0][self.rank]
-                self._remote = fn(*args)
-        except Exception:  # noqa: BLE001 - any failure means: fall back to NCCL on every rank
+                for r in range(self.world):
+                    if r == self.dst:
+                        slabs.append(out_local)
+                        continue
+                    ptr, h = C.c_void_p(), N.XmIpcHandle()
+                    N.check(N.lib.xm_peer_alloc(dev, frame_bytes * n_local, C.byref(ptr), C.byref(h)))
+                    self._owned.append((dev, ptr.value))
+                    slabs.append(_wrap_device_memory(ptr.value, tuple(out_local.shape), out_local.dtype, out_local.device))
+                    handles[r] = bytes(h.bytes)
+        except Exception as exc:  # noqa: BLE001 - any failure means: every rank falls back to NCCL
+            self.peer_error = repr(exc)
             ok = 0
-        dev = torch.device("cuda", torch.cuda.current_device())
-        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        payload = [handles, dev]
+        dist.broadcast_object_list(payload, src=self.dst, group=self.group)
+        handles, dst_dev = payload
+        if self.rank != self.dst and ok:
+            try:
+                h = N.XmIpcHandle()
+                C.memmove(h.bytes, handles[self.rank], 64)
+                ptr = C.c_void_p()
+                N.check(N.lib.xm_peer_open(dev, int(dst_dev), C.byref(h), C.byref(ptr)))
+                self._mapped = (dev, ptr.value)
+                self._remote_ptr, self._remote_dev = ptr.value, int(dst_dev)
+            except Exception as exc:  # noqa: BLE001
+                self.peer_error = repr(exc)
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=out_local.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) != 1:
-            self._remote = None
-            return False
-        self._peer = True
-        return True
+            self.close_peer()
+            return None
+        self._peer_mode, self._render_ptrs, self._frame_bytes = mode, render_ptrs, frame_bytes
+        self._done_flag = torch.zeros(1, dtype=torch.int32, device=out_local.device)
+        return slabs if self.rank == self.dst else []
+
+    def close_peer(self):
+        from . import _native as N
+
+        if self._mapped is not None:
+            N.lib.xm_peer_close(self._mapped[0], self._mapped[1])
+            self._mapped = None
+        for dev, ptr in self._owned:
+            N.lib.xm_peer_free(dev, ptr)
+        self._owned = []
+        self._peer_mode = None
+        self._remote_ptr = None
 
     def _spans(self, n):
         lo, k = 0, 0
@@ -91,8 +160,6 @@ class FrameSharder:
             hi = min(n, lo + size)
             yield lo, hi
             lo, k = hi, k + 1
-
-    _peer = False
 
     def _gather_chunk(self, send: torch.Tensor, recv: Optional[List[torch.Tensor]], async_op: bool):
         if self.world == 1:
@@ -108,12 +175,17 @@ class FrameSharder:
         caller synchronises."""
         n = len(local_frames)
         on_cuda = out_local.is_cuda
+        peer = self._peer_mode if (gather and self.world > 1) else None
         if on_cuda and gather and self.world > 1 and self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(out_local.device)
         works = []
         for lo, hi in self._spans(n):
+            if peer == "direct" and self.rank != self.dst:
+                # the render kernel's epilogue writes straight into the destination rank's slab (NVLink stores)
+                self._render_ptrs(local_frames[lo:hi], [self._remote_ptr + j * self._frame_bytes for j in range(lo, hi)])
+                continue
             self.render(local_frames[lo:hi], out_local[lo:hi])
-            if not gather:
+            if not gather or peer == "direct":
                 continue
             recv = [g[lo:hi] for g in gathered] if (gathered is not None and self.rank == self.dst) else None
             if on_cuda and self.world > 1:
@@ -121,9 +193,13 @@ class FrameSharder:
                 done.record(torch.cuda.current_stream(out_local.device))
                 with torch.cuda.stream(self._comm_stream):
                     self._comm_stream.wait_event(done)
-                    if self._peer:
-                        if self._remote is not None:  # (the destination's own frames are already in place)
-                            self._remote[lo:hi].copy_(out_local[lo:hi], non_blocking=True)
+                    if peer == "copy":
+                        if self.rank != self.dst:  # (the destination's own frames are already in place)
+                            from . import _native as N
+
+                            N.check(N.lib.xm_peer_copy(
+                                self._remote_ptr + lo * self._frame_bytes, self._remote_dev, out_local[lo].data_ptr(), out_local.device.index,
+                                (hi - lo) * self._frame_bytes, self._comm_stream.cuda_stream))
                     else:
                         works.append(self._gather_chunk(out_local[lo:hi], recv, async_op=True))
             else:
@@ -133,4 +209,8 @@ class FrameSharder:
                 if w is not None:
                     w.wait()  # orders the NCCL stream before the comm stream
             torch.cuda.current_stream(out_local.device).wait_stream(self._comm_stream)
+        if peer is not None:
+            # stream-ordered arrival: once this tiny all-reduce has completed on rank dst's stream, every peer's
+            # render kernels / peer copies of this call have completed, i.e. their frames are in dst's slabs
+            dist.all_reduce(self._done_flag, group=self.group)
         return gathered if self.rank == self.dst else None
