@@ -160,7 +160,8 @@ int xm_ctx_set_colormap(XmCtx* ctx, const uint8_t* h_bgr256);
  *                     structure, plain-load event warps), 0 = the per-frame kernels back to back   [1]
  *   "reserve_sms"     SMs the persistent batch kernel leaves free (e.g. for NCCL's copy kernels)  [0]
  *   "ctas_per_sm"     resident CTAs per SM for the event kernel, 0 = occupancy query            [0]
- *   "region_cells"    shared-memory cells per buffer of the projector-view epilogue             [3072]
+ *   "region_cells"    shared-memory cells per buffer of the projector-view epilogue [largest tile region of
+ *                     the remap table, rounded up to 128; read-only "region_need" = the exact figure]
  *   "profile"         1 / 0: record CUDA events around K1 (per-event kernel) and K2 (per-pixel
  *                     epilogue) of every frame; -1 resets the accumulators.  Read back with
  *                     "profile_k1_ns", "profile_k2_ns", "profile_frames", "profile_launches" (these

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxmaps_b200.so")
+# XMAPS_B200_LIB: an alternative build of the same library (A/B runs of kernel variants); default = the in-tree build
+LIB_PATH = os.environ.get("XMAPS_B200_LIB") or os.path.join(_HERE, "libxmaps_b200.so")
 
 # ---- constants of include/xmaps_b200.h --------------------------------------------------------
 ABI_VERSION = 1

@@ -37,7 +37,14 @@ constexpr int kBatchMax = 32;    // frames per launch (the frame table travels i
 constexpr int kBatchMaps = 3;    // scatter maps in rotation
 constexpr int kBatchHeader = 1152;  // mbarriers, ring descriptors, CTA accumulators, per-warp frame constants (2 slots)
 constexpr int kCamTilePx = 4096;  // camera-view epilogue item
-constexpr int kTileWarps = 4;             // epilogue warps per CTA
+#ifndef XM_TILE_WARPS
+#define XM_TILE_WARPS 4
+#endif
+#ifndef XM_BATCH_CTAS
+#define XM_BATCH_CTAS 2
+#endif
+constexpr int kTileWarps = XM_TILE_WARPS;  // epilogue warps per CTA
+constexpr int kBatchCtasPerSm = XM_BATCH_CTAS;  // resident CTAs per SM the kernel is compiled for (register budget)
 constexpr int kTileGroupThreads = 64;     // threads that share one tile
 constexpr int kTileGroups = kTileWarps * 32 / kTileGroupThreads;
 constexpr int kBatchThreads = kWsThreads + kTileWarps * 32;
@@ -130,6 +137,20 @@ __global__ void __launch_bounds__(64) batch_bounds_kernel(const __grid_constant_
 // release fence for the "data, then counter" hand-offs below (lighter than __threadfence(), which is fence.sc)
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
+// one lane of a converged warp, without reading %laneid / %tid (the compiler re-reads the special register inside
+// the hot loop to save a register; the S2R round trip showed up as ~8 % of the consumers' stall samples)
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ long long ld_time_nc(const int4* ev) {
     long long t;
     asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(t) : "l"(reinterpret_cast<const char*>(ev) + 8));
@@ -180,7 +201,8 @@ __device__ __forceinline__ void batch_tile_groups(const BatchParams& bp, int grp
         int next_ticket = 0;
         if (gtid == 0) {
             const unsigned need = static_cast<unsigned>((bp.frames[f].n + CHUNK - 1) / CHUNK);
-            while (ld_acquire_u32(&st->blocks_done) < need) __nanosleep(200);
+            // (back-off: a group leader polls every 0.2 ... 1.6 us; the 3-map ring gives the tiles two frames of slack)
+            for (unsigned ns = 200; ld_acquire_u32(&st->blocks_done) < need; ns = min(ns * 2u, 1600u)) __nanosleep(ns);
             next_ticket = static_cast<int>(atomicAdd(&st->fix_chunk, 1u));
         }
         for (;;) {
@@ -204,7 +226,7 @@ __device__ __forceinline__ void batch_tile_groups(const BatchParams& bp, int grp
 }
 
 template <bool CAM>
-__global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_constant__ BatchParams bp) {
+__global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(const __grid_constant__ BatchParams bp) {
     extern __shared__ __align__(128) unsigned char ev_smem[];
     uint64_t* full_ev = reinterpret_cast<uint64_t*>(ev_smem);
     uint64_t* empty_ev = reinterpret_cast<uint64_t*>(ev_smem + 32);
@@ -294,7 +316,7 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
             fetch_ts(dB, tBa, tBb);
             const unsigned itC = dB.x >= 0 ? atomicAdd(item_counter, 1u) : 0xffffffffu;
 
-            if (issued >= bp.stages) mbar_wait(empty_ev + se, pe);
+            if (issued >= bp.stages) mbar_wait_relaxed(empty_ev + se, pe);
             ev_meta[se] = dA;
             if (dA.x < 0) {
                 mbar_arrive(full_ev + se);  // descriptor only (end of the batch)
@@ -324,7 +346,7 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
                 cb = min(max(cb, 0), bp.xmap_w - 1);
                 const int lo = min(ca, cb);
                 const int n = min(min(max(ca, cb) - lo + 1, bp.cap_cols), bp.xmap_w - lo);
-                mbar_wait(empty_win + sw, pw ^ 1u);  // first round passes immediately
+                mbar_wait_relaxed(empty_win + sw, pw ^ 1u);  // first round passes immediately
                 win_meta[sw] = make_int2(lo, n);
                 const unsigned bytes = static_cast<unsigned>(n) * bp.col_stride * 2u;
                 mbar_expect_tx(full_win + sw, bytes);
@@ -438,7 +460,7 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
     };
     auto release = [&]() {
         __syncwarp();
-        if (lane == 0) mbar_arrive_a(a_empty_ev + fe * 8);
+        if (elect_one()) mbar_arrive_a(a_empty_ev + fe * 8);
         if (++fe == bp.stages) {
             fe = 0;
             fpe ^= 1u;
@@ -468,15 +490,19 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
         }
         const unsigned left = static_cast<unsigned>(lds32_a(a_fcf + 44)) - static_cast<unsigned>(g) * kEvChunk;
         const int limit = left < kEvChunk ? static_cast<int>(left) : kEvChunk;
-        unsigned bad_mask = 0, dead_mask = 0;
-        // two events at a time: half the registers for the raw records (the per-event loop must not spill)
+        bool any_bad = false;
+        unsigned kept = 0;  // events of this thread that pass the polarity mask (n_valid); travels to the back half with the slot
+        // XM_FRONT_GROUP events at a time (registers for the raw records vs. independent work in flight)
+#ifndef XM_FRONT_GROUP
+#define XM_FRONT_GROUP 2
+#endif
 #pragma unroll
-        for (int h = 0; h < kEvPerThread; h += 2) {
-            int4 raw[2];
+        for (int h = 0; h < kEvPerThread; h += XM_FRONT_GROUP) {
+            int4 raw[XM_FRONT_GROUP];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) raw[j] = lds128_a(a_stage + (h + j) * (kEvThreads * 16));
+            for (int j = 0; j < XM_FRONT_GROUP; ++j) raw[j] = lds128_a(a_stage + (h + j) * (kEvThreads * 16));
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < XM_FRONT_GROUP; ++j) {
                 const int k = h + j;
                 const unsigned ex = static_cast<unsigned>(raw[j].x) & 0xffffu, ey = static_cast<unsigned>(raw[j].x) >> 16;
                 bool valid = ((static_cast<unsigned>(raw[j].y) ^ 1u) & pol_mask) == 0u;  // polarity: p == 1, or everything
@@ -486,39 +512,44 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
                 // can a pixel of this 4x4 block ever be an inlier?  (shared-memory bitmap; block 0 for events that are dropped anyway)
                 const unsigned blk = ok ? (ey >> 2) * static_cast<unsigned>(bp.alive_bw) + (ex >> 2) : 0u;
                 const bool live = ok && ((static_cast<unsigned>(lds32_a(a_alive + (blk >> 5) * 4u)) >> (blk & 31u)) & 1u);
+#ifdef XM_DEBUG_HOOKS  // timing experiments only (results WRONG): 2 = no LUT gathers, 64 = gathers hit one L1-resident 16 KB slice
+                if (live && !(bp.debug & 2)) cp_async_4_a(a_lut_c + k * (kEvThreads * 4), bp.lut_xy + ((bp.debug & 64) ? (px & 0xfff) : px));
+#else
                 if (live) cp_async_4_a(a_lut_c + k * (kEvThreads * 4), bp.lut_xy + px);
+#endif
                 const long long t_bits = (static_cast<long long>(raw[j].w) << 32) | static_cast<unsigned>(raw[j].z);
                 bool bad;
                 const unsigned q = ic.column(t_bits, bad);
                 col[k] = live ? static_cast<int>(q) : (ok ? -2 : (valid ? -3 : -1));
                 if (CAM) pix[k] = px;
                 // dead events too: a timestamp outside the assumed bounds invalidates the frame's normalisation
-                bad_mask |= (ok && (bad || !ic.ok)) ? (1u << k) : 0u;
-                dead_mask |= (ok && !live) ? (1u << k) : 0u;
+                any_bad = any_bad || (ok && bad);
+                kept += valid ? 1u : 0u;
             }
         }
         cp_async_commit();
-        if (bad_mask) {  // slow path: the reference's own float64 expression
+        if (any_bad || !ic.ok) {  // slow path (ties, bounds violations, frames the integer form does not cover): the reference's own float64 expression
             TimeCol<false> tc;  // rebuilt here: the float64 constants are not worth registers in the hot loop
             tc.init(__ldcg(&bp.states[f].t_lo_bits), __ldcg(&bp.states[f].t_hi_bits), bp.t_px_scale);
 #pragma unroll
             for (int k = 0; k < kEvPerThread; ++k) {
-                if (!(bad_mask & (1u << k))) continue;
+                if (col[k] < 0 && col[k] != -2) continue;  // not kept, or not inside the image: no time column
                 const int4 rec = lds128_a(a_stage + k * (kEvThreads * 16));  // the stage is ours until release()
                 const long long t_bits = (static_cast<long long>(rec.w) << 32) | static_cast<unsigned>(rec.z);
                 bool viol;
-                int cc = tc.column(t_bits, viol);
+                int cc = tc.column(t_bits, viol);  // exact for every event (== the integer form wherever that is valid)
                 if (cc < 0) cc += bp.xmap_w;  // NumPy negative index (only reachable with wrong bounds)
                 viol = viol || cc < 0 || cc >= bp.xmap_w;
-                col[k] = viol ? -4 : ((dead_mask >> k) & 1u ? -2 : cc);
+                col[k] = viol ? -4 : (col[k] == -2 ? -2 : cc);
             }
         }
         release();
-        return fslot;
+        return fslot | (kept << 1);
     };
 
     // BACK half: X-map lookups (window in shared memory, else through L2), disparity, scatter
-    auto back = [&](int f, unsigned slot, int g, const int (&col)[kEvPerThread], const int (&pix)[kEvPerThread]) {
+    auto back = [&](int f, unsigned slot_kept, int g, const int (&col)[kEvPerThread], const int (&pix)[kEvPerThread]) {
+        const unsigned slot = slot_kept & 1u;
         if (f != cur_f) {
             // first chunk of a new frame: the previous frame's scatter is complete for this warp.  Its fence
             // and counters run while the gathers of the next chunk (issued by the front half) are in flight.
@@ -542,14 +573,10 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
         for (int k = 0; k < kEvPerThread; ++k) lut[k] = lds32_a(a_lut_c + k * (kEvThreads * 4));
         unsigned hit_mask = 0, miss_mask = 0;
         {   // statistics of the chunk (col < 0: see front)
-            unsigned kept = 0;
             int lowest = 0;
 #pragma unroll
-            for (int k = 0; k < kEvPerThread; ++k) {
-                kept += col[k] != -1;
-                lowest = min(lowest, col[k]);
-            }
-            n_valid += kept;
+            for (int k = 0; k < kEvPerThread; ++k) lowest = min(lowest, col[k]);
+            n_valid += slot_kept >> 1;
             if (lowest <= -3) {
 #pragma unroll
                 for (int k = 0; k < kEvPerThread; ++k) {
@@ -591,13 +618,17 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
             const unsigned idx = idx0 + static_cast<unsigned>(k * kEvThreads);
             const unsigned long long key =
                 (static_cast<unsigned long long>(epoch16 | (idx >> 16)) << 32) | ((idx << 16) | static_cast<unsigned>(disp));
+#ifdef XM_DEBUG_HOOKS  // 1 = no scatter atomics
+            red_max_u64_if(map + cell, key, inl && !(bp.debug & 1));
+#else
             red_max_u64_if(map + cell, key, inl);
+#endif
             imask |= inl ? (1u << k) : 0u;
         }
         n_inl += __popc(imask);
         if (bp.cap_cols > 0) {
             __syncwarp();
-            if (lane == 0) mbar_arrive_a(a_empty_win + bw * 8);
+            if (elect_one()) mbar_arrive_a(a_empty_win + bw * 8);
             if (++bw == bp.win_stages) {
                 bw = 0;
                 bpw ^= 1u;
@@ -606,6 +637,33 @@ __global__ void __launch_bounds__(kBatchThreads, 2) batch_kernel(const __grid_co
         ++my_chunks;
     };
 
+#ifdef XM_DEBUG_HOOKS  // 32 = consumers only take and release the stages (pure TMA stream through this pipeline)
+    if (bp.debug & 32) {
+        for (;;) {
+            const int2 mm = peek();
+            if (mm.x < 0) break;
+            if (mm.x != cur_f) {  // the tile groups still wait for every frame's chunk count
+                leave_frame();
+                cur_f = mm.x;
+            }
+            ++my_chunks;
+            const int4 r = lds128_a(a_ring + fe * (kEvChunk * 16));
+            if (r.x == 0x7fffffff && r.y == 0x7fffffff) flags |= 1u << 30;  // keep the load
+            release();
+            if (bp.cap_cols > 0) {
+                mbar_wait_a(a_full_win + bw * 8, bpw);
+                __syncwarp();
+                if (elect_one()) mbar_arrive_a(a_empty_win + bw * 8);
+                if (++bw == bp.win_stages) {
+                    bw = 0;
+                    bpw ^= 1u;
+                }
+            }
+        }
+        leave_frame();
+        return;
+    }
+#endif
     // The software pipeline runs across frame boundaries: FRONT half of chunk c+1 (possibly the first chunk
     // of the next frame), then BACK half of chunk c.
     int2 m = peek();

@@ -138,7 +138,8 @@ struct XmCtx {
     int opt_win_stages = 2;   // depth of the X-map window ring (warp-specialised K1)
     int opt_k1_variant = 2;   // 2: lean warp-specialised K1 (integer time, verified tables; else falls back to 1),
                               // 1: warp-specialised K1 (mbarrier pipelines), 0: block-barrier K1
-    int opt_region_cells = 48 * 64;
+    int opt_region_cells = 48 * 64;  // per buffer; replaced at creation by the largest tile region of the remap table
+    long long region_need = 0;
     // per-kernel CUDA-event timing (option "profile"): pairs around K1 and K2 of every frame
     int opt_profile = 0;
     std::vector<cudaEvent_t> prof_events;  // 3 per frame: before K1, after K1 (+ fix-up), after K2
@@ -301,7 +302,7 @@ int configure_event_kernels(XmCtx* c) {
     if (variant == 2) {
         int bcols = cols;
         auto smem_for = [&](int k) { return xm::batch_smem_bytes(c->opt_stages, c->opt_win_stages, k * c->col_stride * 2, c->opt_region_cells, c->alive_words); };
-        while (bcols > 0 && 2 * (smem_for(bcols) + 1024) > 196 * 1024) --bcols;
+        while (bcols > 0 && xm::kBatchCtasPerSm * (smem_for(bcols) + 1024) > 196 * 1024) --bcols;
         c->batch_cols = bcols;
         c->batch_smem = smem_for(bcols);
         int occ_min = 1 << 30;
@@ -1004,7 +1005,20 @@ int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
                         y1 = my > y1 ? my : y1;
                     }
                 boxes[static_cast<size_t>(by) * tx + bx] = make_short4(static_cast<short>(x0), static_cast<short>(y0), static_cast<short>(x1), static_cast<short>(y1));
+                if (x1 >= 0) {  // shared-memory cells this tile's region needs (tile_region(), dilate radius 3)
+                    const int rx0 = (x0 - 3) & ~1, rw = (x1 + 3 - rx0 + 2) & ~1, rh = y1 - y0 + 1 + 6;
+                    const long long cells = static_cast<long long>(rw + xm::kRowExtra) * rh;
+                    if (cells > c->region_need) c->region_need = cells;
+                }
             }
+        // the projector epilogue's regions are sized to the largest tile of THIS remap table (rounded up), so that
+        // no tile falls back to direct 49-tap reads and no shared memory is spent on cells no tile uses
+        if (c->region_need > 0) {
+            long long cells = (c->region_need + 127) & ~127LL;
+            if (cells < 1024) cells = 1024;
+            if (cells > 48 * 1024 / 4) cells = 48 * 1024 / 4;
+            c->opt_region_cells = static_cast<int>(cells);
+        }
         if (cudaMalloc(&c->d_tile_box, boxes.size() * sizeof(short4)) != cudaSuccess ||
             cudaMemcpy(c->d_tile_box, boxes.data(), boxes.size() * sizeof(short4), cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(XM_ERR_CUDA, "uploading the tile boxes failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -1231,6 +1245,7 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     else if (!strcmp(key, "lookahead")) *value = c->opt_lookahead;
     else if (!strcmp(key, "ctas_per_sm")) *value = c->opt_ctas_per_sm;
     else if (!strcmp(key, "region_cells")) *value = c->opt_region_cells;
+    else if (!strcmp(key, "region_need")) *value = c->region_need;    /* read-only: cells of the largest tile region */
     else if (!strcmp(key, "epoch")) *value = c->epoch;
     else if (!strcmp(key, "profile")) *value = c->opt_profile;
     else if (!strcmp(key, "profile_k1_ns") || !strcmp(key, "profile_k2_ns") || !strcmp(key, "profile_frames") || !strcmp(key, "profile_launches")) {
