@@ -156,8 +156,8 @@ int xm_ctx_set_colormap(XmCtx* ctx, const uint8_t* h_bgr256);
  *   "auto_fixup"      0/1  with XM_TBOUNDS_SORTED / _GIVEN: when an event lies outside the assumed
  *                     bounds, redo the frame on the device with exact (reduced) bounds         [1]
  *   "batch"           xm_frame_batch on uniform batches: 1 = batch_kernel (one persistent kernel per <= 32
- *                     frames: staged event pipeline + epilogue warp groups), 2 = batch2_kernel (same batch
- *                     structure, plain-load event warps), 0 = the per-frame kernels back to back   [1]
+ *                     frames: staged event pipeline + epilogue warp groups), 0 = the per-frame kernels
+ *                     back to back                                                              [1]
  *   "reserve_sms"     SMs the persistent batch kernel leaves free (e.g. for NCCL's copy kernels)  [0]
  *   "ctas_per_sm"     resident CTAs per SM for the event kernel, 0 = occupancy query            [0]
  *   "region_cells"    shared-memory cells per buffer of the projector-view epilogue [largest tile region of

@@ -13,10 +13,10 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-BATCH_KERNELS = [1, 2]  # 1: batch_kernel (staged event pipeline), 2: batch2_kernel (plain-load event warps)
+BATCH_KERNELS = [1]  # 1: batch_kernel (the persistent batch kernel)
 
 
-@pytest.fixture(scope="module", params=BATCH_KERNELS, ids=["staged", "plain"])
+@pytest.fixture(scope="module", params=BATCH_KERNELS, ids=["staged"])
 def small(request):
     tables, z = load_golden_tables("small")
     eng = make_engine(tables, z)
@@ -26,7 +26,7 @@ def small(request):
     eng.close()
 
 
-@pytest.fixture(scope="module", params=BATCH_KERNELS, ids=["staged", "plain"])
+@pytest.fixture(scope="module", params=BATCH_KERNELS, ids=["staged"])
 def default(request):
     tables, z = load_golden_tables("default")
     eng = make_engine(tables)

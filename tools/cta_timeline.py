@@ -7,7 +7,7 @@ import numpy as np, torch
 import bench
 from xmaps_b200.engine import DepthEngine, TableSet, OUT_DEPTH
 dev = torch.device("cuda", 0)
-t = bench.load_tables()
+t = bench.load_geometry("5m")[0]
 eng = DepthEngine(TableSet(t.lut_x, t.lut_y, t.x_map, t.remap_xy, t.rect_w, t.rect_h, t.t_px_scale, t.x_offset, t.depth_scale), device=dev)
 for kv in sys.argv[1:]:
     k, v = kv.split("="); eng.set_option(k, int(v))

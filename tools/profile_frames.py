@@ -22,17 +22,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=4)
     ap.add_argument("--reps", type=int, default=4)
-    ap.add_argument("--events", type=int, default=bench.EVENTS_PER_FRAME)
+    ap.add_argument("--events", type=int, default=bench.WORKLOADS["5m"][5])
     ap.add_argument("--view", type=int, default=0)
     ap.add_argument("--opt", action="append", default=[])
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
-    t = bench.load_tables()
+    t = bench.load_geometry("5m")[0]
     eng = DepthEngine(TableSet(t.lut_x, t.lut_y, t.x_map, t.remap_xy, t.rect_w, t.rect_h, t.t_px_scale, t.x_offset, t.depth_scale), device=dev)
     for kv in a.opt:
         k, v = kv.split("=")
         eng.set_option(k, int(v))
-    frames = [bench.synth_frame_cuda(i, a.events, dev) for i in range(a.frames)]
+    frames = [bench.synth_frame_cuda(i, a.events, dev, 640, 480) for i in range(a.frames)]
     torch.cuda.synchronize()
     for _ in range(a.reps):
         eng.frame_batch(frames, view=a.view, output=OUT_DEPTH)

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libxmaps_b200.so")
 SOURCES = ["xm_capi.cu"]
-DEPS = SOURCES + ["xm_device.cuh", "xm_frame_kernels.cuh", "xm_stage_kernels.cuh", "xm_fused_kernel.cuh", "xm_batch_kernel.cuh", "xm_batch2_kernel.cuh", "xm_stream_kernels.cuh", os.path.join("..", "..", "include", "xmaps_b200.h")]
+DEPS = SOURCES + ["xm_device.cuh", "xm_frame_kernels.cuh", "xm_stage_kernels.cuh", "xm_fused_kernel.cuh", "xm_batch_kernel.cuh", "xm_stream_kernels.cuh", os.path.join("..", "..", "include", "xmaps_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

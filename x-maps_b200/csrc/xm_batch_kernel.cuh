@@ -40,6 +40,10 @@ constexpr int kCamTilePx = 4096;  // camera-view epilogue item
 #ifndef XM_TILE_WARPS
 #define XM_TILE_WARPS 4
 #endif
+#ifndef XM_POLL_NS0  // back-off of a tile group leader waiting for a frame's events: first / longest sleep
+#define XM_POLL_NS0 200
+#define XM_POLL_NS1 1600
+#endif
 #ifndef XM_BATCH_CTAS
 #define XM_BATCH_CTAS 2
 #endif
@@ -68,8 +72,11 @@ struct BatchParams {
     // "alive" bitmap: one bit per 4x4 block of camera pixels, set if ANY time column can make an event of a pixel of
     // the block an inlier (derived from the LUT and the X-map at table upload, exact).  Events of dead blocks are
     // only counted and bounds-checked: no LUT gather, no X-map lookup, no scatter.
+    // Layout: block (bx, by) = bit (bx & 31) of word by * (alive_row_bytes / 4) + (bx >> 5); the table is padded to a
+    // power of two of words and the kernel masks the byte address, so that any 16-bit coordinate pair reads inside it.
     const unsigned* alive;
-    int alive_bw, alive_words;  // blocks per row, 32-bit words (a multiple of 4)
+    int alive_row_bytes, alive_words;
+    unsigned alive_mask;  // alive_words * 4 - 4
     unsigned long long* maps[kBatchMaps];
     unsigned epoch0;        // frame f scatters with epoch0 + f
     FrameState* states;     // [n_frames + 1]; block n_frames is the control block (next_chunk = item counter)
@@ -87,9 +94,16 @@ struct BatchParams {
 
 __host__ __device__ __forceinline__ unsigned batch_chunks(long long n) { return static_cast<unsigned>((n + kEvChunk - 1) / kEvChunk); }
 
-inline int batch_smem_bytes(int stages, int win_stages, int win_bytes, int region_cells, int alive_words = 0) {
-    // header | LUT double buffer | event ring | X-map window ring | two u16 regions per tile group | alive bitmap
-    return kBatchHeader + kEvLutBytes + stages * (kEvChunk * 16) + win_stages * win_bytes + kTileGroups * region_cells * 4 + alive_words * 4;
+// Live lists: the front half of a chunk compacts the events that can become inliers (polarity, inside the image,
+// "alive" pixel block) warp by warp into dense lists -- gathered LUT word, (time column | index inside the chunk),
+// and for the camera view the pixel index -- so that the back half only runs over those (~40 % of a uniform stream).
+// Two buffers (front half of chunk c+1 / back half of chunk c), kEvChunk 32-bit entries per list and buffer.
+constexpr int kListBytes = kEvChunk * 4;  // one list of one buffer
+__host__ __device__ __forceinline__ int batch_list_bytes(bool cam) { return (cam ? 3 : 2) * 2 * kListBytes; }
+
+inline int batch_smem_bytes(int stages, int win_stages, int win_bytes, int region_cells, int alive_words = 0, bool cam = false) {
+    // header | live lists | event ring | X-map window ring | two u16 regions per tile group | alive bitmap
+    return kBatchHeader + batch_list_bytes(cam) + stages * (kEvChunk * 16) + win_stages * win_bytes + kTileGroups * region_cells * 4 + alive_words * 4;
 }
 
 struct BatchBoundsParams {
@@ -171,7 +185,11 @@ template <bool CAM>
 static __device__ __noinline__ void batch_tile(const BatchParams& bp, int f, int t, unsigned short* bufA, unsigned short* bufB, int tid,
                                                int bar_id) {
     const unsigned epoch = bp.epoch0 + static_cast<unsigned>(f);
+#ifdef XM_PROBE_NO_TILE
+    if (true) {
+#else
     if (bp.debug & 16) {
+#endif
         // timing experiment: no epilogue work (results WRONG)
     } else if (CAM) {
         const unsigned long long* mp = bp.maps[f % kBatchMaps];
@@ -202,7 +220,7 @@ __device__ __forceinline__ void batch_tile_groups(const BatchParams& bp, int grp
         if (gtid == 0) {
             const unsigned need = static_cast<unsigned>((bp.frames[f].n + CHUNK - 1) / CHUNK);
             // (back-off: a group leader polls every 0.2 ... 1.6 us; the 3-map ring gives the tiles two frames of slack)
-            for (unsigned ns = 200; ld_acquire_u32(&st->blocks_done) < need; ns = min(ns * 2u, 1600u)) __nanosleep(ns);
+            for (unsigned ns = XM_POLL_NS0; ld_acquire_u32(&st->blocks_done) < need; ns = min(ns * 2u, static_cast<unsigned>(XM_POLL_NS1))) __nanosleep(ns);
             next_ticket = static_cast<int>(atomicAdd(&st->fix_chunk, 1u));
         }
         for (;;) {
@@ -225,6 +243,62 @@ __device__ __forceinline__ void batch_tile_groups(const BatchParams& bp, int grp
     }
 }
 
+// What a chunk carries from its front half to its back half (one register):
+//   bit 0 constant slot | bits 1-3 events of this thread that pass the polarity mask | bit 4 a pixel outside the
+//   camera image | bit 5 a timestamp outside the assumed bounds | bits 8.. entries of the warp's live list
+constexpr unsigned kCarryOob = 1u << 4, kCarryTb = 1u << 5;
+constexpr unsigned kMetaSkip = 0x8000u;  // list entry of an event whose column is not usable (bounds violation)
+constexpr unsigned kMetaOff = 2 * kListBytes, kPixOff = 4 * kListBytes;  // (column | index << 16) / camera pixel lists behind the LUT words
+
+// "alive" bit of the 4x4 pixel block of a record's first word (x | y << 16): masked address, any coordinates are safe
+__device__ __forceinline__ unsigned batch_alive_bit(const BatchParams& bp, unsigned a_alive, unsigned xy) {
+    const unsigned addr = ((xy >> 18) * static_cast<unsigned>(bp.alive_row_bytes) + ((xy >> 5) & 0x7fcu)) & bp.alive_mask;
+    return __funnelshift_r(static_cast<unsigned>(lds32_a(a_alive + addr)), 0u, xy >> 2) & 1u;
+}
+
+// GENERAL front half of a chunk (whole warp, out of line): partial chunks, frames the integer time column does not
+// cover, and chunks in which the fast pass found an exact rounding tie or a timestamp outside the assumed bounds.
+// Evaluates the reference's own float64 expression for every event and (re)writes the warp's live list; the list
+// positions only depend on the live flags, so gathers the fast pass already started land in the same slots with the
+// same words.  Returns the chunk's carry (without the constant slot).
+template <bool CAM>
+static __device__ __noinline__ unsigned batch_front_general(const BatchParams& bp, int f, unsigned a_stage, unsigned a_list_c, int limit,
+                                                            unsigned a_alive, int tid) {
+    TimeCol<false> tc;
+    tc.init(__ldcg(&bp.states[f].t_lo_bits), __ldcg(&bp.states[f].t_hi_bits), bp.t_px_scale);
+    const unsigned pol_mask = bp.polarity ? 0xffffu : 0u;
+    const unsigned lt_mask = (1u << (tid & 31)) - 1u;
+    bool tb = false, oob = false;
+    unsigned count = 0, kept = 0;
+#pragma unroll 1
+    for (int k = 0; k < kEvPerThread; ++k) {
+        const int4 rec = lds128_a(a_stage + k * (kEvThreads * 16));  // the stage is ours until release()
+        const unsigned ex = static_cast<unsigned>(rec.x) & 0xffffu, ey = static_cast<unsigned>(rec.x) >> 16;
+        const bool valid = ((static_cast<unsigned>(rec.y) ^ 1u) & pol_mask) == 0u && (k * kEvThreads + tid < limit);
+        const bool ok = valid && ex < static_cast<unsigned>(bp.cam_w) && ey < static_cast<unsigned>(bp.cam_h);
+        const bool live = ok && batch_alive_bit(bp, a_alive, static_cast<unsigned>(rec.x)) != 0u;
+        const unsigned mask = __ballot_sync(0xffffffffu, live);
+        const unsigned pos = count + __popc(mask & lt_mask);
+        count += __popc(mask);
+        kept += valid ? 1u : 0u;
+        oob = oob || (valid && !ok);  // the reference raises IndexError here
+        if (!ok) continue;            // not kept, or not inside the image: no time column
+        const long long t_bits = (static_cast<long long>(rec.w) << 32) | static_cast<unsigned>(rec.z);
+        bool viol;
+        int cc = tc.column(t_bits, viol);  // exact for every event (== the integer form wherever that is valid)
+        if (cc < 0) cc += bp.xmap_w;       // NumPy negative index (only reachable with wrong bounds)
+        viol = viol || cc < 0 || cc >= bp.xmap_w;
+        tb = tb || viol;  // dead events too: a timestamp outside the assumed bounds invalidates the frame's normalisation
+        if (live) {
+            const int px = static_cast<int>(ey * static_cast<unsigned>(bp.cam_w) + ex);
+            cp_async_4_a(a_list_c + pos * 4u, bp.lut_xy + px);
+            sts32_a(a_list_c + kMetaOff + pos * 4u, (viol ? kMetaSkip : static_cast<unsigned>(cc)) | (static_cast<unsigned>(k * kEvThreads + tid) << 16));
+            if (CAM) sts32_a(a_list_c + kPixOff + pos * 4u, static_cast<unsigned>(px));
+        }
+    }
+    return (kept << 1) | (oob ? kCarryOob : 0u) | (tb ? kCarryTb : 0u) | (count << 8);
+}
+
 template <bool CAM>
 __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(const __grid_constant__ BatchParams bp) {
     extern __shared__ __align__(128) unsigned char ev_smem[];
@@ -235,12 +309,13 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(c
     int2* win_meta = reinterpret_cast<int2*>(ev_smem + 128);  // [4] (first column, count) of a window stage
     int2* ev_meta = reinterpret_cast<int2*>(ev_smem + 160);   // [4] (kind << 16 | frame, chunk or tile index); x < 0: end
     unsigned* s_acc = reinterpret_cast<unsigned*>(ev_smem + 192);  // [8][4] per-frame CTA accumulators: valid, inliers, flags, warps
-    constexpr int lut_tile = kEvLutBytes;
+    const int lut_tile = batch_list_bytes(CAM);  // the live lists
     unsigned char* ring = ev_smem + kBatchHeader + lut_tile;
     const int win_bytes = bp.cap_cols * bp.col_stride * 2;
     unsigned char* win_ring = ring + bp.stages * (kEvChunk * 16);
 
-    const int tid = threadIdx.x;
+    int tid;  // (opaque: the compiler otherwise re-reads the special register inside the hot loop to save a register)
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const bool producer = warp == kEvThreads / 32;
@@ -368,10 +443,13 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(c
     const unsigned sbase = smem_u32(ev_smem);
     const unsigned a_full_ev = sbase, a_empty_ev = sbase + 32, a_full_win = sbase + 64, a_empty_win = sbase + 96;
     const unsigned a_wmeta = sbase + 128, a_emeta = sbase + 160;
-    const unsigned a_lut = sbase + kBatchHeader + tid * 4;                   // + parity * 4096 + k * 1024
+    // live lists of this warp: kEvPerThread * 32 entries per list and buffer
+    //   LUT words at a_list + buffer * kListBytes, (column | index << 16) at + 2 * kListBytes, camera pixel at + 4 * kListBytes
+    const unsigned a_list = sbase + kBatchHeader + warp * (kEvPerThread * 32 * 4);
     const unsigned a_ring = sbase + kBatchHeader + lut_tile + tid * 16;      // + slot * 16384 + k * 4096
     const unsigned a_win = sbase + kBatchHeader + lut_tile + bp.stages * (kEvChunk * 16);
     const unsigned a_alive = smem_u32(s_alive);
+    const unsigned lt_mask = (1u << lane) - 1u;
     // geometry is read from the parameter bank where it is used (constant operands, no registers)
 #define XM_B_YLIM (static_cast<unsigned>(bp.xmap_h) - 1u)
 #define XM_B_CAMW (static_cast<unsigned>(bp.cam_w))
@@ -380,7 +458,7 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(c
 
     int fe = 0, bw = 0;
     unsigned fpe = 0, bpw = 0;
-    unsigned fpar = 0, bpar = 0;  // LUT double-buffer halves of the next front / back half
+    unsigned fpar = 0, bpar = 0;  // list buffers of the next front / back half
 
     // per-frame state: all statistics are taken in the BACK half, so they belong to exactly one frame
     int cur_f = -1;    // frame of the back half (the one whose statistics are being accumulated)
@@ -467,167 +545,237 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(c
         }
     };
 
-    // FRONT half of chunk g of frame f (stage fe): events into registers, LUT gathers started, time columns
-    // computed; releases the stage.  col[k]: time column, or -1 event not kept (polarity / past the end),
-    // -2 kept but its pixel block can never yield an inlier (counted, nothing else), -3 pixel outside the
-    // camera image, -4 timestamp outside the assumed bounds.
-    auto front = [&](int f, int g, int (&col)[kEvPerThread], int (&pix)[kEvPerThread]) -> unsigned {
+    auto alive_bit = [&](unsigned xy) -> unsigned { return batch_alive_bit(bp, a_alive, xy); };
+
+    // FRONT half of chunk g of frame f (stage fe): polarity / image / alive tests, bounds check and time column of
+    // every event; live events are compacted into the warp's lists and their LUT gathers started; releases the stage.
+    auto front = [&](int f, int g) -> unsigned {
         if (f != front_f) prepare_frame(f);
         const unsigned a_fcf = a_fc + fslot * 48;
         const unsigned a_stage = a_ring + fe * (kEvChunk * 16);
-        const unsigned a_lut_c = a_lut + fpar * (kEvChunk * 4);
+        const unsigned a_list_c = a_list + fpar * kListBytes;
         fpar ^= 1u;
-        IntCol ic;
-        {
-            const int4 c0 = lds128_a(a_fcf), c1 = lds128_a(a_fcf + 16);
-            ic.lo = (static_cast<unsigned long long>(static_cast<unsigned>(c0.y)) << 32) | static_cast<unsigned>(c0.x);
-            ic.range = static_cast<unsigned>(c0.z);
-            ic.scale2 = static_cast<unsigned>(c0.w);
-            ic.d = static_cast<unsigned>(c1.x);
-            ic.M = static_cast<unsigned>(c1.y);
-            ic.sh = c1.z;
-            ic.ok = c1.w != 0;
-        }
+        const int4 c1 = lds128_a(a_fcf + 16);
         const unsigned left = static_cast<unsigned>(lds32_a(a_fcf + 44)) - static_cast<unsigned>(g) * kEvChunk;
-        const int limit = left < kEvChunk ? static_cast<int>(left) : kEvChunk;
-        bool any_bad = false;
-        unsigned kept = 0;  // events of this thread that pass the polarity mask (n_valid); travels to the back half with the slot
-        // XM_FRONT_GROUP events at a time (registers for the raw records vs. independent work in flight)
+        unsigned carry;
+        if (left >= kEvChunk && c1.w != 0) {
+            // FAST pass: a full chunk of a frame whose time columns have the integer form
+            IntCol ic;
+            {
+                const int4 c0 = lds128_a(a_fcf);
+                ic.lo = (static_cast<unsigned long long>(static_cast<unsigned>(c0.y)) << 32) | static_cast<unsigned>(c0.x);
+                ic.range = static_cast<unsigned>(c0.z);
+                ic.scale2 = static_cast<unsigned>(c0.w);
+                ic.d = static_cast<unsigned>(c1.x);
+                ic.M = static_cast<unsigned>(c1.y);
+                ic.sh = c1.z;
+                ic.ok = true;
+            }
+            bool any_bad = false, oob = false;
+            unsigned kept = 0;   // events of this thread that pass the polarity mask (n_valid)
+            unsigned count = 0;  // entries of the warp's live list so far (warp-uniform)
+            // XM_FRONT_GROUP events at a time (registers for the raw records vs. independent work in flight)
 #ifndef XM_FRONT_GROUP
 #define XM_FRONT_GROUP 2
 #endif
 #pragma unroll
-        for (int h = 0; h < kEvPerThread; h += XM_FRONT_GROUP) {
-            int4 raw[XM_FRONT_GROUP];
+            for (int h = 0; h < kEvPerThread; h += XM_FRONT_GROUP) {
+                int4 raw[XM_FRONT_GROUP];
 #pragma unroll
-            for (int j = 0; j < XM_FRONT_GROUP; ++j) raw[j] = lds128_a(a_stage + (h + j) * (kEvThreads * 16));
+                for (int j = 0; j < XM_FRONT_GROUP; ++j) raw[j] = lds128_a(a_stage + (h + j) * (kEvThreads * 16));
 #pragma unroll
-            for (int j = 0; j < XM_FRONT_GROUP; ++j) {
-                const int k = h + j;
-                const unsigned ex = static_cast<unsigned>(raw[j].x) & 0xffffu, ey = static_cast<unsigned>(raw[j].x) >> 16;
-                bool valid = ((static_cast<unsigned>(raw[j].y) ^ 1u) & pol_mask) == 0u;  // polarity: p == 1, or everything
-                if (limit < kEvChunk) valid = valid && (k * kEvThreads + tid < limit);
-                const bool ok = valid && ex < XM_B_CAMW && ey < XM_B_CAMH;
-                const int px = static_cast<int>(ey * XM_B_CAMW + ex);
-                // can a pixel of this 4x4 block ever be an inlier?  (shared-memory bitmap; block 0 for events that are dropped anyway)
-                const unsigned blk = ok ? (ey >> 2) * static_cast<unsigned>(bp.alive_bw) + (ex >> 2) : 0u;
-                const bool live = ok && ((static_cast<unsigned>(lds32_a(a_alive + (blk >> 5) * 4u)) >> (blk & 31u)) & 1u);
+                for (int j = 0; j < XM_FRONT_GROUP; ++j) {
+                    const int k = h + j;
+                    const unsigned xy = static_cast<unsigned>(raw[j].x);
+                    const unsigned ex = xy & 0xffffu, ey = xy >> 16;
+                    const bool valid = ((static_cast<unsigned>(raw[j].y) ^ 1u) & pol_mask) == 0u;  // polarity: p == 1, or everything
+                    const bool ok = valid && ex < XM_B_CAMW && ey < XM_B_CAMH;
+                    // can a pixel of this 4x4 block ever be an inlier?  (shared-memory bitmap; looked up unconditionally:
+                    // a branch per event costs more than the load, and the masked address is safe for any coordinates)
+                    const unsigned abit = alive_bit(xy);
+                    const bool live = ok & (abit != 0u);
+                    const long long t_bits = (static_cast<long long>(raw[j].w) << 32) | static_cast<unsigned>(raw[j].z);
+                    bool bad;
+                    const unsigned q = ic.column(t_bits, bad);
+                    // dead events too: a timestamp outside the assumed bounds invalidates the frame's normalisation
+                    any_bad = any_bad || (ok && bad);
+                    oob = oob || (valid && !ok);  // the reference raises IndexError here
+                    kept += valid ? 1u : 0u;
+                    const unsigned mask = __ballot_sync(0xffffffffu, live);
+                    const unsigned pos = count + __popc(mask & lt_mask);
+                    count += __popc(mask);
+                    if (live) {
+                        const int px = static_cast<int>(ey * XM_B_CAMW + ex);
+                        // (gather first: ptxas pads a shared-memory store that is followed by an LDGSTS with three dummy loads)
 #ifdef XM_DEBUG_HOOKS  // timing experiments only (results WRONG): 2 = no LUT gathers, 64 = gathers hit one L1-resident 16 KB slice
-                if (live && !(bp.debug & 2)) cp_async_4_a(a_lut_c + k * (kEvThreads * 4), bp.lut_xy + ((bp.debug & 64) ? (px & 0xfff) : px));
+                        if (!(bp.debug & 2)) cp_async_4_a(a_list_c + pos * 4u, bp.lut_xy + ((bp.debug & 64) ? (px & 0xfff) : px));
 #else
-                if (live) cp_async_4_a(a_lut_c + k * (kEvThreads * 4), bp.lut_xy + px);
+                        cp_async_4_a(a_list_c + pos * 4u, bp.lut_xy + px);
 #endif
-                const long long t_bits = (static_cast<long long>(raw[j].w) << 32) | static_cast<unsigned>(raw[j].z);
-                bool bad;
-                const unsigned q = ic.column(t_bits, bad);
-                col[k] = live ? static_cast<int>(q) : (ok ? -2 : (valid ? -3 : -1));
-                if (CAM) pix[k] = px;
-                // dead events too: a timestamp outside the assumed bounds invalidates the frame's normalisation
-                any_bad = any_bad || (ok && bad);
-                kept += valid ? 1u : 0u;
+                        sts32_a(a_list_c + kMetaOff + pos * 4u, q | (static_cast<unsigned>(k * kEvThreads + tid) << 16));
+                        if (CAM) sts32_a(a_list_c + kPixOff + pos * 4u, static_cast<unsigned>(px));
+                    }
+                }
             }
+            carry = (kept << 1) | (oob ? kCarryOob : 0u) | (count << 8);
+            if (__any_sync(0xffffffffu, any_bad)) carry = batch_front_general<CAM>(bp, f, a_stage, a_list_c, kEvChunk, a_alive, tid);
+        } else {
+            carry = batch_front_general<CAM>(bp, f, a_stage, a_list_c, left < kEvChunk ? static_cast<int>(left) : kEvChunk, a_alive, tid);
         }
         cp_async_commit();
-        if (any_bad || !ic.ok) {  // slow path (ties, bounds violations, frames the integer form does not cover): the reference's own float64 expression
-            TimeCol<false> tc;  // rebuilt here: the float64 constants are not worth registers in the hot loop
-            tc.init(__ldcg(&bp.states[f].t_lo_bits), __ldcg(&bp.states[f].t_hi_bits), bp.t_px_scale);
-#pragma unroll
-            for (int k = 0; k < kEvPerThread; ++k) {
-                if (col[k] < 0 && col[k] != -2) continue;  // not kept, or not inside the image: no time column
-                const int4 rec = lds128_a(a_stage + k * (kEvThreads * 16));  // the stage is ours until release()
-                const long long t_bits = (static_cast<long long>(rec.w) << 32) | static_cast<unsigned>(rec.z);
-                bool viol;
-                int cc = tc.column(t_bits, viol);  // exact for every event (== the integer form wherever that is valid)
-                if (cc < 0) cc += bp.xmap_w;  // NumPy negative index (only reachable with wrong bounds)
-                viol = viol || cc < 0 || cc >= bp.xmap_w;
-                col[k] = viol ? -4 : (col[k] == -2 ? -2 : cc);
-            }
-        }
         release();
-        return fslot | (kept << 1);
+        return carry | fslot;
     };
 
-    // BACK half: X-map lookups (window in shared memory, else through L2), disparity, scatter
-    auto back = [&](int f, unsigned slot_kept, int g, const int (&col)[kEvPerThread], const int (&pix)[kEvPerThread]) {
-        const unsigned slot = slot_kept & 1u;
+    // BACK half: the warp's live list -- X-map lookups (window in shared memory, else through L2), disparity, scatter
+    auto back = [&](int f, unsigned carry, int g) {
+        const unsigned slot = carry & 1u;
+        const unsigned count = carry >> 8;
         if (f != cur_f) {
             // first chunk of a new frame: the previous frame's scatter is complete for this warp.  Its fence
             // and counters run while the gathers of the next chunk (issued by the front half) are in flight.
             leave_frame();
             cur_f = f;
         }
+        n_valid += (carry >> 1) & 7u;
+        if (carry & (kCarryOob | kCarryTb)) {
+            if (carry & kCarryOob) flags |= kStatusPixelOob;
+            if (carry & kCarryTb) flags |= kStatusTBounds;
+        }
         const unsigned a_fcb = a_fc + slot * 48;
-        int win_lo = 0;
-        unsigned win_n = 0;
-        unsigned a_win_c = a_lut;  // any valid address: without a window every lookup misses
+        unsigned win_lo = 0, win_n = 0;
+        unsigned a_win_c = a_list;  // any valid address: without a window every lookup misses
         if (bp.cap_cols > 0) {
             mbar_wait_a(a_full_win + bw * 8, bpw);
-            win_lo = lds32_a(a_wmeta + bw * 8);
-            win_n = static_cast<unsigned>(lds32_a(a_wmeta + bw * 8 + 4));
+            const int2 wm = lds64_a(a_wmeta + bw * 8);
+            win_lo = static_cast<unsigned>(wm.x);
+            win_n = static_cast<unsigned>(wm.y);
             a_win_c = a_win + bw * win_bytes;
         }
-        const unsigned a_lut_c = a_lut + bpar * (kEvChunk * 4);
+        const unsigned a_list_c = a_list + bpar * kListBytes + lane * 4u;
         bpar ^= 1u;
-        int lut[kEvPerThread], xp[kEvPerThread];
-#pragma unroll
-        for (int k = 0; k < kEvPerThread; ++k) lut[k] = lds32_a(a_lut_c + k * (kEvThreads * 4));
-        unsigned hit_mask = 0, miss_mask = 0;
-        {   // statistics of the chunk (col < 0: see front)
-            int lowest = 0;
-#pragma unroll
-            for (int k = 0; k < kEvPerThread; ++k) lowest = min(lowest, col[k]);
-            n_valid += slot_kept >> 1;
-            if (lowest <= -3) {
-#pragma unroll
-                for (int k = 0; k < kEvPerThread; ++k) {
-                    if (col[k] == -3) flags |= kStatusPixelOob;  // the reference raises IndexError here
-                    if (col[k] == -4) flags |= kStatusTBounds;
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kEvPerThread; ++k) {
-            const unsigned ycr = static_cast<unsigned>(lut[k] >> 16);
-            const unsigned rel = static_cast<unsigned>(col[k] - win_lo);  // dropped events (col < 0) wrap to huge
-            const bool y_ok = ycr < XM_B_YLIM;  // x_maps_disparity.py:23: 0 <= y_rect < H - 1 (last row excluded)
-            const bool hit = y_ok && rel < win_n;
-            xp[k] = lds_s16_a(a_win_c + (hit ? (rel * static_cast<unsigned>(bp.col_stride) + ycr) * 2u : 0u));
-            hit_mask |= hit ? (1u << k) : 0u;
-            miss_mask |= (y_ok && !hit && col[k] >= 0) ? (1u << k) : 0u;
-        }
-        if (miss_mask) {  // column outside the staged window: read the transposed table through L2
-#pragma unroll
-            for (int k = 0; k < kEvPerThread; ++k)
-                if (miss_mask & (1u << k)) xp[k] = __ldg(bp.xmap_t + static_cast<long long>(col[k]) * bp.col_stride + (lut[k] >> 16));
-            hit_mask |= miss_mask;
-        }
-        const unsigned idx0 = static_cast<unsigned>(g) * kEvChunk + static_cast<unsigned>(tid);
         const int4 c2 = lds128_a(a_fcb + 32);
         unsigned long long* const map = reinterpret_cast<unsigned long long*>(
             (static_cast<unsigned long long>(static_cast<unsigned>(c2.y)) << 32) | static_cast<unsigned>(c2.x));
-        const unsigned epoch16 = static_cast<unsigned>(c2.z);
-        unsigned imask = 0;
-#pragma unroll
-        for (int k = 0; k < kEvPerThread; ++k) {
-            const int xcr = static_cast<short>(lut[k] & 0xffff);
-            const int ycr = lut[k] >> 16;
-            const int disp = static_cast<short>(xp[k] - xcr - bp.x_offset);  // int16 arithmetic wraps
-            const bool inl = ((hit_mask >> k) & 1u) && disp >= 0;
-            // projector view: x_rect + disp = x_map - x_offset, in [0, rect_w) for verified tables
-            const int cell = CAM ? pix[k] : ycr * bp.rect_w + (xp[k] - bp.x_offset);
-            const unsigned idx = idx0 + static_cast<unsigned>(k * kEvThreads);
-            const unsigned long long key =
-                (static_cast<unsigned long long>(epoch16 | (idx >> 16)) << 32) | ((idx << 16) | static_cast<unsigned>(disp));
-#ifdef XM_DEBUG_HOOKS  // 1 = no scatter atomics
-            red_max_u64_if(map + cell, key, inl && !(bp.debug & 1));
-#else
-            red_max_u64_if(map + cell, key, inl);
-#endif
-            imask |= inl ? (1u << k) : 0u;
+        // event index = g * kEvChunk + index inside the chunk: its bits 16.. are the same for the whole chunk
+        static_assert(kEvChunk == 1024, "key halves below assume 1024-event chunks");
+        const unsigned key_hi = static_cast<unsigned>(c2.z) | (static_cast<unsigned>(g) >> 6);
+        const unsigned idx_lo = (static_cast<unsigned>(g) & 63u) << 26;  // bits 16.. of the key's low word
+        unsigned missed = 0;  // entries whose column is not in the staged window (or that carry the skip flag)
+#pragma unroll 1
+        for (unsigned j0 = lane; j0 < count; j0 += 64u) {
+            // Two list entries per lane and round, everything for entries whose column is in the window, in one block of
+            // PTX: predicates stay predicates (no masks in registers), the scatter is a predicated RED.
+            const unsigned a_e = a_list_c + (j0 - lane) * 4u;
+            unsigned n_in, n_miss;
+            if (!CAM) {
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred pa0, pa1, ph0, ph1, pi0, pi1, pm0, pm1;\n\t"
+                    ".reg .b32 m0, m1, l0, l1, y0, y1, c0, c1, r0, r1, a0, a1, x0, x1, xc0, xc1, d0, d1, cl0, cl1, k0, k1, j1;\n\t"
+                    ".reg .s16 xs0, xs1;\n\t"
+                    ".reg .b64 ad0, ad1, kk0, kk1;\n\t"
+                    "ld.shared.u32 m0, [%2 + 8192];\n\t"
+                    "ld.shared.u32 m1, [%2 + 8320];\n\t"
+                    "ld.shared.u32 l0, [%2];\n\t"
+                    "ld.shared.u32 l1, [%2 + 128];\n\t"
+                    "add.u32 j1, %3, 32;\n\t"
+                    "shr.s32 y0, l0, 16;\n\t"
+                    "shr.s32 y1, l1, 16;\n\t"
+                    "and.b32 c0, m0, 0xffff;\n\t"
+                    "and.b32 c1, m1, 0xffff;\n\t"
+                    "sub.u32 r0, c0, %5;\n\t"
+                    "sub.u32 r1, c1, %5;\n\t"
+                    "setp.lt.u32 pa0, y0, %7;\n\t"                 // 0 <= y_rect < H - 1 (x_maps_disparity.py:23)
+                    "setp.lt.u32 pa1, y1, %7;\n\t"
+                    "setp.lt.and.u32 pa1, j1, %4, pa1;\n\t"        // entry exists (entry 0 always does: j0 < count)
+                    "setp.lt.and.u32 ph0, r0, %6, pa0;\n\t"        // column inside the staged window
+                    "setp.lt.and.u32 ph1, r1, %6, pa1;\n\t"
+                    "setp.ge.and.u32 pm0, r0, %6, pa0;\n\t"
+                    "setp.ge.and.u32 pm1, r1, %6, pa1;\n\t"
+                    "mad.lo.u32 a0, r0, %8, y0;\n\t"
+                    "mad.lo.u32 a1, r1, %8, y1;\n\t"
+                    "shl.b32 a0, a0, 1;\n\t"
+                    "shl.b32 a1, a1, 1;\n\t"
+                    "add.u32 a0, a0, %9;\n\t"
+                    "add.u32 a1, a1, %9;\n\t"
+                    "mov.b16 xs0, 0;\n\t"
+                    "mov.b16 xs1, 0;\n\t"
+                    "@ph0 ld.shared.s16 xs0, [a0];\n\t"
+                    "@ph1 ld.shared.s16 xs1, [a1];\n\t"
+                    "cvt.s32.s16 x0, xs0;\n\t"
+                    "cvt.s32.s16 x1, xs1;\n\t"
+                    "sub.s32 x0, x0, %10;\n\t"                     // x_map - X_OFFSET = x_rect + disparity
+                    "sub.s32 x1, x1, %10;\n\t"
+                    "cvt.s32.s16 xc0, l0;\n\t"
+                    "cvt.s32.s16 xc1, l1;\n\t"
+                    "sub.s32 d0, x0, xc0;\n\t"
+                    "sub.s32 d1, x1, xc1;\n\t"
+                    "and.b32 k0, d0, 0x8000;\n\t"                  // int16 arithmetic wraps: sign of the low half
+                    "and.b32 k1, d1, 0x8000;\n\t"
+                    "setp.eq.and.u32 pi0, k0, 0, ph0;\n\t"
+                    "setp.eq.and.u32 pi1, k1, 0, ph1;\n\t"
+                    "mad.lo.s32 cl0, y0, %11, x0;\n\t"
+                    "mad.lo.s32 cl1, y1, %11, x1;\n\t"
+                    "mad.wide.s32 ad0, cl0, 8, %12;\n\t"
+                    "mad.wide.s32 ad1, cl1, 8, %12;\n\t"
+                    "prmt.b32 k0, d0, m0, 0x7610;\n\t"             // disparity (low half) | index inside the chunk << 16
+                    "prmt.b32 k1, d1, m1, 0x7610;\n\t"
+                    "add.u32 k0, k0, %13;\n\t"
+                    "add.u32 k1, k1, %13;\n\t"
+                    "mov.b64 kk0, {k0, %14};\n\t"
+                    "mov.b64 kk1, {k1, %14};\n\t"
+                    "@pi0 red.global.max.u64 [ad0], kk0;\n\t"
+                    "@pi1 red.global.max.u64 [ad1], kk1;\n\t"
+                    "selp.u32 %0, 1, 0, pi0;\n\t"
+                    "@pi1 add.u32 %0, %0, 1;\n\t"
+                    "selp.u32 %1, 1, 0, pm0;\n\t"
+                    "@pm1 or.b32 %1, %1, 2;\n\t"
+                    "}"
+                    : "=r"(n_in), "=r"(n_miss)
+                    : "r"(a_e), "r"(j0), "r"(count), "r"(win_lo), "r"(win_n), "r"(XM_B_YLIM), "r"(static_cast<unsigned>(bp.col_stride)),
+                      "r"(a_win_c), "r"(bp.x_offset), "r"(bp.rect_w), "l"(map), "r"(idx_lo), "r"(key_hi)
+                    : "memory");
+                n_inl += n_in;
+                missed |= n_miss;
+            } else {
+                missed |= 3u;  // camera view: the general loop below does everything
+            }
         }
-        n_inl += __popc(imask);
+        if (__any_sync(0xffffffffu, missed != 0u)) {
+            // entries the block above left out: column outside the staged window (read the transposed table through
+            // L2), skip flag, camera view
+#pragma unroll 1
+            for (unsigned j = lane; j < count; j += 32u) {
+                const unsigned meta = static_cast<unsigned>(lds32_a(a_list_c + kMetaOff + (j - lane) * 4u));
+                const int lut = lds32_a(a_list_c + (j - lane) * 4u);
+                const int ycr = lut >> 16, xcr = static_cast<short>(lut & 0xffff);
+                const unsigned col = meta & 0xffffu;
+                if (static_cast<unsigned>(ycr) >= XM_B_YLIM || (meta & kMetaSkip)) continue;
+                const unsigned rel = col - win_lo;
+                int xp;
+                if (rel < win_n) {
+                    if (!CAM) continue;  // done above
+                    xp = lds_s16_a(a_win_c + (rel * static_cast<unsigned>(bp.col_stride) + static_cast<unsigned>(ycr)) * 2u);
+                } else {
+                    xp = __ldg(bp.xmap_t + static_cast<long long>(col) * bp.col_stride + ycr);
+                }
+                const int disp = static_cast<short>(xp - xcr - bp.x_offset);  // int16 arithmetic wraps
+                if (disp < 0) continue;
+                // projector view: x_rect + disp = x_map - x_offset, in [0, rect_w) for verified tables
+                const int cell = CAM ? lds32_a(a_list_c + kPixOff + (j - lane) * 4u) : ycr * bp.rect_w + (xp - bp.x_offset);
+                const unsigned key_lo = (idx_lo + (meta & 0xffff0000u)) | (static_cast<unsigned>(disp) & 0xffffu);
+                const unsigned long long key = (static_cast<unsigned long long>(key_hi) << 32) | key_lo;
+#ifdef XM_DEBUG_HOOKS  // 1 = no scatter atomics
+                red_max_u64_if(map + cell, key, !(bp.debug & 1));
+#else
+                red_max_u64_if(map + cell, key, true);
+#endif
+                ++n_inl;
+            }
+        }
+        __syncwarp();  // the list buffer is rewritten by the front half after next
         if (bp.cap_cols > 0) {
-            __syncwarp();
             if (elect_one()) mbar_arrive_a(a_empty_win + bw * 8);
             if (++bw == bp.win_stages) {
                 bw = 0;
@@ -665,47 +813,47 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(c
     }
 #endif
     // The software pipeline runs across frame boundaries: FRONT half of chunk c+1 (possibly the first chunk
-    // of the next frame), then BACK half of chunk c.
-    int2 m = peek();
-    if (m.x >= 0) {
-        int col_cur[kEvPerThread], pix_cur[kEvPerThread];
-        int f_cur = m.x, g_cur = m.y;
-        unsigned s_cur = front(f_cur, g_cur, col_cur, pix_cur);
-        for (;;) {
-            m = peek();
-            const bool more = m.x >= 0;
-            // Entering frame F waits for the tiles of frame F - kBatchMaps, which wait for every warp's count
-            // of that frame's chunks.  This warp publishes a frame's count only in the BACK half of a later
-            // frame's chunk, so if one of its two unpublished frames (cur_f: back half, f_cur: front half done)
-            // is that old, the pipeline is drained first (tiny frames / many more CTAs than chunks per frame).
-            bool drain = more && bp.hard_frames && m.x != f_cur;
-            if (!drain && more && m.x != front_f && m.x >= kBatchMaps) {
+    // of the next frame), then BACK half of chunk c.  (One call site each: the two halves are long, and the loop
+    // body has to stay inside the instruction cache.)
+    bool have_cur = false;
+    int f_cur = -1, g_cur = 0;
+    unsigned s_cur = 0;
+    for (;;) {
+        const int2 m = peek();  // (does not consume the stage: front() releases it)
+        const bool more = m.x >= 0;
+        // Entering frame F waits for the tiles of frame F - kBatchMaps, which wait for every warp's count
+        // of that frame's chunks.  This warp publishes a frame's count only in the BACK half of a later
+        // frame's chunk, so if one of its two unpublished frames (cur_f: back half, f_cur: front half done)
+        // is that old, the pipeline is drained first (tiny frames / many more CTAs than chunks per frame).
+        bool drain = false;
+        if (more && have_cur && m.x != f_cur) {
+            drain = bp.hard_frames != 0;
+            if (!drain && m.x != front_f && m.x >= kBatchMaps) {
                 const int must_be_out = m.x - kBatchMaps;
                 drain = f_cur <= must_be_out || (cur_f >= 0 && cur_f <= must_be_out);
             }
-            int col_nxt[kEvPerThread], pix_nxt[kEvPerThread];
-            unsigned s_nxt = 0;
-            if (more && !drain) {
-                s_nxt = front(m.x, m.y, col_nxt, pix_nxt);
+        }
+        const bool do_front = more && !drain;
+        unsigned s_nxt = 0;
+        if (do_front) s_nxt = front(m.x, m.y);
+        if (have_cur) {
+            if (do_front)
                 cp_async_wait<1>();  // the gathers of the current chunk have landed; the next chunk's stay in flight
-            } else {
+            else
                 cp_async_wait<0>();
-            }
-            back(f_cur, s_cur, g_cur, col_cur, pix_cur);
-            if (!more) break;
-            if (drain) {
-                leave_frame();
-                s_nxt = front(m.x, m.y, col_cur, pix_cur);
-            } else {
-#pragma unroll
-                for (int k = 0; k < kEvPerThread; ++k) {
-                    col_cur[k] = col_nxt[k];
-                    if (CAM) pix_cur[k] = pix_nxt[k];
-                }
-            }
+            __syncwarp();  // ... those of every lane: a list entry is read by another lane than the one that gathered it
+            back(f_cur, s_cur, g_cur);
+            have_cur = false;
+        }
+        if (do_front) {
             f_cur = m.x;
             g_cur = m.y;
             s_cur = s_nxt;
+            have_cur = true;
+        } else if (more) {
+            leave_frame();  // drained: publish, then take the same chunk again
+        } else {
+            break;
         }
     }
     leave_frame();

@@ -19,7 +19,6 @@
 #include "xm_stage_kernels.cuh"
 #include "xm_fused_kernel.cuh"
 #include "xm_batch_kernel.cuh"
-#include "xm_batch2_kernel.cuh"
 #include "xm_stream_kernels.cuh"
 
 namespace {
@@ -77,7 +76,7 @@ struct XmCtx {
     std::vector<int> h_lut_xy;          // host copy of the packed LUT (the alive bitmap is rebuilt when the X-map changes)
     unsigned* d_alive = nullptr;        // [alive_words] one bit per 4x4 camera-pixel block: some time column can make it an inlier
     unsigned* d_alive_ones = nullptr;   // all ones (option alive = 0)
-    int alive_bw = 0, alive_words = 0;
+    int alive_wpr = 0, alive_words = 0;  // words per row of blocks, words in total (a power of two)
     long long alive_px = 0;             // camera pixels inside alive blocks (diagnostic, option "alive_px")
     int opt_alive = 1;
     int lut_x_min = 0;                  // smallest rectified x of the LUT (lut_safe = lut_x_min > -x_offset)
@@ -126,8 +125,7 @@ struct XmCtx {
     int fused_occ = 0;        // resident CTAs per SM of frame_kernel
     int opt_batch = 1;        // 1: xm_frame_batch renders uniform batches with one persistent kernel per <= 32 frames
                               //    (event warps + dedicated epilogue warps; 47 vs 57 us per 5 M-event frame, EXPERIMENTS_r01.md)
-    int batch_occ = 0, batch_smem = 0, batch_cols = 0;  // launch configuration of batch_kernel
-    int batch2_occ = 0, batch2_smem = 0;                // launch configuration of batch2_kernel (option batch = 2)
+    int batch_occ = 0, batch_smem[2] = {0, 0}, batch_cols[2] = {0, 0};  // launch configuration of batch_kernel ([view])
     unsigned long long* d_map_ring[xm::kBatchMaps] = {nullptr, nullptr, nullptr};  // [0] = d_map
     xm::FrameState* d_bstate = nullptr;  // [kBatchMax + 1] state blocks of the current batch
     const xm::FrameState* status_src = nullptr;  // state block xm_frame_status reports (NULL: d_state + last_slot)
@@ -300,45 +298,29 @@ int configure_event_kernels(XmCtx* c) {
     // shrinks to 28 KB and the LUT gathers slow down by 1.5x, EXPERIMENTS_r01.md)
     c->batch_occ = 0;
     if (variant == 2) {
-        int bcols = cols;
-        auto smem_for = [&](int k) { return xm::batch_smem_bytes(c->opt_stages, c->opt_win_stages, k * c->col_stride * 2, c->opt_region_cells, c->alive_words); };
-        while (bcols > 0 && xm::kBatchCtasPerSm * (smem_for(bcols) + 1024) > 196 * 1024) --bcols;
-        c->batch_cols = bcols;
-        c->batch_smem = smem_for(bcols);
         int occ_min = 1 << 30;
         for (int cam = 0; cam < 2; ++cam) {
+            int bcols = cols;
+            auto smem_for = [&](int k) {
+                return xm::batch_smem_bytes(c->opt_stages, c->opt_win_stages, k * c->col_stride * 2, c->opt_region_cells, c->alive_words, cam != 0);
+            };
+            while (bcols > 0 && xm::kBatchCtasPerSm * (smem_for(bcols) + 1024) > 196 * 1024) --bcols;
+            c->batch_cols[cam] = bcols;
+            c->batch_smem[cam] = smem_for(bcols);
             void (*k)(xm::BatchParams) = cam ? xm::batch_kernel<true> : xm::batch_kernel<false>;
             cudaFuncAttributes fa;
             XM_CUDA(cudaFuncGetAttributes(&fa, k));
             const int dyn = optin - static_cast<int>(fa.sharedSizeBytes);
-            if (c->batch_smem > dyn) {
+            if (c->batch_smem[cam] > dyn) {
                 occ_min = 0;
                 break;
             }
             XM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
             int occ = 0;
-            XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, xm::kBatchThreads, c->batch_smem));
+            XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, xm::kBatchThreads, c->batch_smem[cam]));
             occ_min = occ < occ_min ? occ : occ_min;
         }
         c->batch_occ = occ_min;
-        // batch2_kernel: plain-load event warps, shared memory only for the tile regions
-        c->batch2_smem = xm::batch2_smem_bytes(c->opt_region_cells);
-        occ_min = 1 << 30;
-        for (int cam = 0; cam < 2; ++cam) {
-            void (*k)(xm::BatchParams) = cam ? xm::batch2_kernel<true> : xm::batch2_kernel<false>;
-            cudaFuncAttributes fa;
-            XM_CUDA(cudaFuncGetAttributes(&fa, k));
-            const int dyn = optin - static_cast<int>(fa.sharedSizeBytes);
-            if (c->batch2_smem > dyn) {
-                occ_min = 0;
-                break;
-            }
-            XM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-            int occ = 0;
-            XM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, xm::kB2Threads, c->batch2_smem));
-            occ_min = occ < occ_min ? occ : occ_min;
-        }
-        c->batch2_occ = occ_min;
     }
     return XM_OK;
 }
@@ -347,8 +329,12 @@ int configure_event_kernels(XmCtx* c) {
 // Exactly the reference's conditions (x_maps_disparity.py:23-30) evaluated for every value of the pixel's X-map
 // row: 0 <= y_rect < rows - 1 and int16(x_map[y_rect, col] - x_rect - X_OFFSET) >= 0 for some col.
 int build_alive(XmCtx* c, const int16_t* h_x_map, int rows, int cols, int x_offset) {
+    // layout: one row of 32-bit words per row of blocks (block (bx, by) = bit bx & 31 of word by * wpr + (bx >> 5)), the
+    // word count rounded up to a power of two: the kernel masks the byte address instead of range-checking the pixel
     const int bw = (c->cam_w + 3) / 4, bh = (c->cam_h + 3) / 4;
-    const int words = ((bw * bh + 31) / 32 + 3) & ~3;
+    const int wpr = (bw + 31) / 32;
+    int words = 4;
+    while (words < wpr * bh) words *= 2;
     std::vector<std::vector<short>> uniq(rows);
     {
         std::vector<unsigned char> seen(65536);
@@ -366,7 +352,6 @@ int build_alive(XmCtx* c, const int16_t* h_x_map, int rows, int cols, int x_offs
         }
     }
     std::vector<unsigned> bits(words, 0u);
-    long long alive_px = 0;
     for (int y = 0; y < c->cam_h; ++y)
         for (int x = 0; x < c->cam_w; ++x) {
             const int packed = c->h_lut_xy[static_cast<size_t>(y) * c->cam_w + x];
@@ -379,17 +364,15 @@ int build_alive(XmCtx* c, const int16_t* h_x_map, int rows, int cols, int x_offs
                     break;
                 }
             if (!alive) continue;
-            const int blk = (y >> 2) * bw + (x >> 2);
-            bits[blk >> 5] |= 1u << (blk & 31);
+            bits[(y >> 2) * wpr + (x >> 7)] |= 1u << ((x >> 2) & 31);
         }
+    long long alive_px = 0;
     for (int by = 0; by < bh; ++by)
-        for (int bx = 0; bx < bw; ++bx) {
-            const int blk = by * bw + bx;
-            if (bits[blk >> 5] >> (blk & 31) & 1u) {
+        for (int bx = 0; bx < bw; ++bx)
+            if (bits[by * wpr + (bx >> 5)] >> (bx & 31) & 1u) {
                 const int w = std::min(4, c->cam_w - bx * 4), h = std::min(4, c->cam_h - by * 4);
                 alive_px += static_cast<long long>(w) * h;
             }
-        }
     if (c->alive_words != words) {
         cudaFree(c->d_alive);
         cudaFree(c->d_alive_ones);
@@ -399,7 +382,7 @@ int build_alive(XmCtx* c, const int16_t* h_x_map, int rows, int cols, int x_offs
         XM_CUDA(cudaMemset(c->d_alive_ones, 0xff, words * sizeof(unsigned)));
     }
     XM_CUDA(cudaMemcpy(c->d_alive, bits.data(), words * sizeof(unsigned), cudaMemcpyHostToDevice));
-    c->alive_bw = bw;
+    c->alive_wpr = wpr;
     c->alive_words = words;
     c->alive_px = alive_px;
     return XM_OK;
@@ -784,11 +767,12 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     bp.x_offset = c->x_offset;
     bp.rect_w = c->rect_w;
     bp.rect_h = c->rect_h;
-    bp.cap_cols = c->batch_cols;
+    bp.cap_cols = c->batch_cols[a[0].view == XM_VIEW_CAMERA ? 1 : 0];
     bp.stages = c->opt_stages;
     bp.win_stages = c->opt_win_stages;
     bp.alive = c->opt_alive ? c->d_alive : c->d_alive_ones;
-    bp.alive_bw = c->alive_bw;
+    bp.alive_row_bytes = c->alive_wpr * 4;
+    bp.alive_mask = static_cast<unsigned>(c->alive_words) * 4u - 4u;
     bp.alive_words = c->alive_words;
     for (int i = 0; i < xm::kBatchMaps; ++i) bp.maps[i] = c->d_map_ring[i];
     bp.epoch0 = epoch0;
@@ -814,11 +798,10 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     bp.tile_items = cam ? (c->cam_w * c->cam_h + xm::kCamTilePx - 1) / xm::kCamTilePx : tiles_x * tiles_y;
     bp.n_frames = n;
     bp.debug = c->opt_debug;
-    const bool v2 = c->opt_batch == 2 && c->batch2_occ > 0;
     unsigned long long items64 = 0;
     for (int f = 0; f < n; ++f) {
         bp.first_item[f] = static_cast<unsigned>(items64);
-        items64 += v2 ? xm::batch2_chunks(a[f].n_events) : xm::batch_chunks(a[f].n_events);
+        items64 += xm::batch_chunks(a[f].n_events);
     }
     if (items64 > 0xfffffff0ULL) return fail(XM_ERR_UNSUPPORTED, "batch too large");
     unsigned items = static_cast<unsigned>(items64);
@@ -829,10 +812,10 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
         bp.frames[f].dst = a[f].d_out;
         bp.frames[f].n = a[f].n_events;
     }
-    const int kocc = v2 ? c->batch2_occ : c->batch_occ;
+    const int kocc = c->batch_occ;
     const int occ = c->opt_ctas_per_sm > 0 && c->opt_ctas_per_sm < kocc ? c->opt_ctas_per_sm : kocc;
     // no more CTAs than there is work: a CTA takes chunks in pairs and runs kTileGroups tiles at a time
-    long long want = v2 ? (static_cast<long long>(items) + xm::kB2EventWarps - 1) / xm::kB2EventWarps : (static_cast<long long>(items) + 1) / 2;
+    long long want = (static_cast<long long>(items) + 1) / 2;
     const long long want_tiles = (static_cast<long long>(bp.tile_items) + xm::kTileGroups - 1) / xm::kTileGroups;
     if (want_tiles > want) want = want_tiles;
     int grid = (c->sm_count - c->opt_reserve_sms) * occ;
@@ -844,15 +827,10 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
         int rc = profile_mark(c, s);
         if (rc) return rc;
     }
-    if (v2) {
-        if (cam)
-            xm::batch2_kernel<true><<<grid, xm::kB2Threads, c->batch2_smem, s>>>(bp);
-        else
-            xm::batch2_kernel<false><<<grid, xm::kB2Threads, c->batch2_smem, s>>>(bp);
-    } else if (cam)
-        xm::batch_kernel<true><<<grid, xm::kBatchThreads, c->batch_smem, s>>>(bp);
+    if (cam)
+        xm::batch_kernel<true><<<grid, xm::kBatchThreads, c->batch_smem[1], s>>>(bp);
     else
-        xm::batch_kernel<false><<<grid, xm::kBatchThreads, c->batch_smem, s>>>(bp);
+        xm::batch_kernel<false><<<grid, xm::kBatchThreads, c->batch_smem[0], s>>>(bp);
     XM_LAUNCHED();
     if (c->opt_profile) {
         int rc = profile_mark(c, s);
@@ -1155,8 +1133,8 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         c->opt_reserve_sms = v;
         return XM_OK;
     }
-    if (!strcmp(key, "batch")) { /* 0: per-frame kernels, 1: batch_kernel (staged event pipeline), 2: batch2_kernel (plain-load event warps) */
-        if (v < 0 || v > 2) return fail(XM_ERR_INVALID_ARG, "batch must be 0, 1 or 2");
+    if (!strcmp(key, "batch")) { /* 0: per-frame kernels, 1: batch_kernel (one persistent kernel per <= 32 frames) */
+        if (v < 0 || v > 1) return fail(XM_ERR_INVALID_ARG, "batch must be 0 or 1");
         c->opt_batch = v;
         return XM_OK;
     }
@@ -1236,9 +1214,9 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     else if (!strcmp(key, "alive_px")) *value = c->alive_px;          /* read-only: camera pixels inside alive blocks */
     else if (!strcmp(key, "batch")) *value = c->opt_batch;
     else if (!strcmp(key, "reserve_sms")) *value = c->opt_reserve_sms;
-    else if (!strcmp(key, "batch_occ")) *value = c->opt_batch == 2 ? c->batch2_occ : c->batch_occ;
-    else if (!strcmp(key, "batch_smem")) *value = c->batch_smem;
-    else if (!strcmp(key, "batch_cols")) *value = c->batch_cols;
+    else if (!strcmp(key, "batch_occ")) *value = c->batch_occ;
+    else if (!strcmp(key, "batch_smem")) *value = c->batch_smem[0];
+    else if (!strcmp(key, "batch_cols")) *value = c->batch_cols[0];
     else if (!strcmp(key, "k2_variant")) *value = c->opt_k2_variant;
     else if (!strcmp(key, "safe_tables")) *value = c->opt_safe_tables && c->lut_safe && c->xmap_safe;
     else if (!strcmp(key, "auto_fixup")) *value = c->opt_auto_fixup;

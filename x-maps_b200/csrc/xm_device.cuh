@@ -455,6 +455,9 @@ __device__ __forceinline__ int lds32_a(unsigned addr) {
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(addr));
     return r;
 }
+__device__ __forceinline__ void sts32_a(unsigned addr, unsigned v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ int lds_s16_a(unsigned addr) {
     int r;
     asm volatile("ld.shared.s16 %0, [%1];" : "=r"(r) : "r"(addr));
