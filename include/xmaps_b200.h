@@ -144,6 +144,8 @@ int xm_ctx_set_colormap(XmCtx* ctx, const uint8_t* h_bgr256);
  *   "stage_xmap"      0/1  stage X-map time columns into shared memory with 1-D bulk (TMA) copies [1]
  *   "smem_cols_bytes" shared-memory budget per CTA for that window                              [12288]
  *   "stages"          depth of K1's shared-memory event ring (16 KB per stage, TMA-filled)      [2]
+ *   "win_stages"      depth of the X-map window ring of the per-frame kernels                   [2]
+ *   "batch_win_stages" ... of the batch kernel                                                  [3]
   *   "safe_tables"     0/1  allow the check-free scatter of K1 when the tables were verified at upload
  *                     (every defined X-map cell in [x_offset, x_offset + rect_w), LUT x > -x_offset) [1]
     *   "fused"           1: one fused kernel per frame (events + grid barrier + epilogue) where the lean path
