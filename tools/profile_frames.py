@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--events", type=int, default=bench.WORKLOADS["5m"][5])
     ap.add_argument("--view", type=int, default=0)
     ap.add_argument("--opt", action="append", default=[])
+    ap.add_argument("--single", action="store_true", help="one xm_frame call per frame instead of one batch")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     t = bench.load_geometry("5m")[0]
@@ -35,7 +36,11 @@ def main():
     frames = [bench.synth_frame_cuda(i, a.events, dev, 640, 480) for i in range(a.frames)]
     torch.cuda.synchronize()
     for _ in range(a.reps):
-        eng.frame_batch(frames, view=a.view, output=OUT_DEPTH)
+        if a.single:
+            for f in frames:
+                eng.frame(f, view=a.view, output=OUT_DEPTH)
+        else:
+            eng.frame_batch(frames, view=a.view, output=OUT_DEPTH)
     torch.cuda.synchronize()
     print("done", eng.status())
 

@@ -85,6 +85,8 @@ struct XmCtx {
     short* d_xmap_t = nullptr;
     short2* d_remap_xy = nullptr;
     short4* d_tile_box = nullptr;  // bounding box of the remap targets of every 32x32 output tile
+    unsigned short* d_tile_off = nullptr;  // per output pixel: its cell inside the tile's shared-memory region (EpilogueParams::tile_off)
+    int opt_tile_off = 1;
     unsigned char* d_turbo = nullptr;
     unsigned long long* d_dbg = nullptr;  // per-CTA phase timestamps (option debug & 8)
     float* d_depth_lut = nullptr;  // [32768], exact depth of every integer disparity
@@ -603,6 +605,7 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
         c->slot_dirty[slot] = true;
         q.remap_xy = c->d_remap_xy;
         q.tile_box = c->d_tile_box;
+    q.tile_off = c->opt_tile_off ? c->d_tile_off : nullptr;
         q.rect_w = c->rect_w;
         q.rect_h = c->rect_h;
         q.radius = c->dilate / 2;
@@ -670,6 +673,7 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     }
     q.remap_xy = c->d_remap_xy;
     q.tile_box = c->d_tile_box;
+    q.tile_off = c->opt_tile_off ? c->d_tile_off : nullptr;
     q.rect_w = c->rect_w;
     q.rect_h = c->rect_h;
     q.radius = c->dilate / 2;
@@ -786,6 +790,7 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     q.recycle = nullptr;
     q.remap_xy = c->d_remap_xy;
     q.tile_box = c->d_tile_box;
+    q.tile_off = c->opt_tile_off ? c->d_tile_off : nullptr;
     q.rect_w = c->rect_w;
     q.rect_h = c->rect_h;
     q.radius = c->dilate / 2;
@@ -1001,6 +1006,30 @@ int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
         if (cudaMalloc(&c->d_tile_box, boxes.size() * sizeof(short4)) != cudaSuccess ||
             cudaMemcpy(c->d_tile_box, boxes.data(), boxes.size() * sizeof(short4), cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(fail(XM_ERR_CUDA, "uploading the tile boxes failed: %s", cudaGetErrorString(cudaGetLastError())));
+        // every output pixel's cell inside its tile's region (the layout of xm::tile_region(): even rx0, 3-cell halo,
+        // kRowPad zero cells left of the data, row stride rw + kRowExtra); tiles whose region exceeds 65535 cells keep 0xffff
+        // and never take the table path (such a region does not fit the shared-memory buffers either)
+        {
+            std::vector<unsigned short> offs(static_cast<size_t>(t->proj_w) * t->proj_h, 0xffffu);
+            for (int by = 0; by < ty; ++by)
+                for (int bx = 0; bx < tx; ++bx) {
+                    const short4 b = boxes[static_cast<size_t>(by) * tx + bx];
+                    if (b.z < 0) continue;
+                    const int rx0 = (b.x - 3) & ~1, rw = (b.z + 3 - rx0 + 2) & ~1, ry0 = b.y - 3, rh = b.w - b.y + 1 + 6;
+                    const int stride = rw + xm::kRowExtra;
+                    if (static_cast<long long>(stride) * rh >= 0xffff) continue;
+                    for (int v = by * xm::kTile; v < (by + 1) * xm::kTile && v < t->proj_h; ++v)
+                        for (int u = bx * xm::kTile; u < (bx + 1) * xm::kTile && u < t->proj_w; ++u) {
+                            const int mx = t->remap_xy[(static_cast<size_t>(v) * t->proj_w + u) * 2];
+                            const int my = t->remap_xy[(static_cast<size_t>(v) * t->proj_w + u) * 2 + 1];
+                            if (mx < 0 || mx >= t->rect_w || my < 0 || my >= t->rect_h) continue;
+                            offs[static_cast<size_t>(v) * t->proj_w + u] = static_cast<unsigned short>((my - ry0) * stride + (mx - rx0) + xm::kRowPad);
+                        }
+                }
+            if (cudaMalloc(&c->d_tile_off, offs.size() * sizeof(unsigned short)) != cudaSuccess ||
+                cudaMemcpy(c->d_tile_off, offs.data(), offs.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess)
+                return bail(fail(XM_ERR_CUDA, "uploading the tile offsets failed: %s", cudaGetErrorString(cudaGetLastError())));
+        }
     }
     c->map_cells = static_cast<long long>(t->rect_w) * t->rect_h;
     if (static_cast<long long>(cam_px) > c->map_cells) c->map_cells = static_cast<long long>(cam_px);
@@ -1055,6 +1084,7 @@ int xm_ctx_destroy(XmCtx* c) {
     cudaFree(c->d_xmap_t);
     cudaFree(c->d_remap_xy);
     cudaFree(c->d_tile_box);
+    cudaFree(c->d_tile_off);
     cudaFree(c->d_turbo);
     cudaFree(c->d_depth_lut);
     cudaFree(c->d_dbg);
@@ -1152,6 +1182,10 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         c->opt_coop = v != 0;
         return XM_OK;
     }
+    if (!strcmp(key, "tile_off")) { /* 1: projector epilogue reads each pixel's region cell from the precomputed table */
+        c->opt_tile_off = v != 0;
+        return XM_OK;
+    }
     if (!strcmp(key, "alive")) { /* 1: the batch kernel skips the look-ups of events whose pixel block can never yield an inlier */
         c->opt_alive = v != 0;
         return XM_OK;
@@ -1217,6 +1251,7 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     else if (!strcmp(key, "pdl")) *value = c->opt_pdl;
     else if (!strcmp(key, "fused")) *value = c->opt_fused;
     else if (!strcmp(key, "alive")) *value = c->opt_alive;
+    else if (!strcmp(key, "tile_off")) *value = c->opt_tile_off;
     else if (!strcmp(key, "coop")) *value = c->opt_coop;
     else if (!strcmp(key, "alive_px")) *value = c->alive_px;          /* read-only: camera pixels inside alive blocks */
     else if (!strcmp(key, "batch")) *value = c->opt_batch;

@@ -1281,6 +1281,9 @@ struct EpilogueParams {
     int use_pdl;             // 1: execute the griddepcontrol instructions
     const short2* remap_xy;
     const short4* tile_box;  // per 32x32 output tile: bounding box (x0, y0, x1, y1) of its remap targets; x1 < 0: none
+    // per output pixel: cell of the pixel's remap target inside its tile's shared-memory region (row stride and padding
+    // as tile_region() lays it out), 0xffff = outside the rectified image; NULL: derive it from remap_xy per pixel
+    const unsigned short* tile_off;
     int rect_w, rect_h;
     int out_w, out_h;  // projector (view 0) or camera (view 1) size
     int radius;        // dilate / 2
@@ -1688,6 +1691,29 @@ __device__ __forceinline__ void proj7_tile_late(const EpilogueParams& p, int bx,
     const short2* rp = p.remap_xy + static_cast<long long>(v0 + warp) * p.out_w + u;
     const int pix0 = (v0 + warp) * p.out_w + u;  // (frames are limited to 2^30 pixels at context creation)
     const int step = ROWS * p.out_w;
+    if (p.tile_off != nullptr && g.fits) {
+        // the pixel's cell inside the region was worked out when the remap table was uploaded: one 16-bit load, one
+        // shared-memory read, one table look-up and one store per pixel
+        const unsigned short* op = p.tile_off + pix0;
+        for (int k0 = 0; k0 < PX; k0 += PXB) {
+            unsigned off[PXB];
+            bool live[PXB];
+            int val[PXB], idx[PXB];
+#pragma unroll
+            for (int j = 0; j < PXB; ++j) {
+                live[j] = full || v0 + warp + (k0 + j) * ROWS < p.out_h;
+                off[j] = 0xffffu;
+                if (live[j]) off[j] = __ldg(op + (k0 + j) * step);
+            }
+#pragma unroll
+            for (int j = 0; j < PXB; ++j) {
+                val[j] = off[j] != 0xffffu ? bufA[off[j]] : 0;
+                idx[j] = pix0 + (k0 + j) * step;
+            }
+            emit_pixels_int<PXB>(p.out, p.dst, idx, val, live);
+        }
+        return;
+    }
     for (int k0 = 0; k0 < PX; k0 += PXB) {
         short2 m[PXB];
         bool live[PXB];
