@@ -242,6 +242,15 @@ int xm_point_cloud(XmCtx* ctx, const float* d_x, const float* d_y, const float* 
  * events[events["p"] == 1] (frame_event_filter.py:21), order preserved; d_out needs room for n records.
  * (xm_frame fuses this mask; this entry point materialises it for the stream in front of the trigger finder.) */
 int xm_polarity_filter(XmCtx* ctx, const void* d_events, int64_t n, void* d_out, int64_t* d_count, void* stream);
+/* ActivityNoiseFilterAlgorithm(width, height, threshold_us).process_events (Metavision, closed binary; constructed at
+ * depth_reprojection_pipe.py:65-67 with threshold = 1e6 / projector_fps, applied to every packet at :116-117, between the
+ * polarity filter and the trigger finder).  Restated from its published semantics ("parity unpinned", see the oracle): an
+ * event passes iff one of the 8 neighbours of its pixel saw an event less than threshold_us earlier; per-pixel
+ * timestamps start at 0 and are carried from call to call (xm_activity_reset clears them).  Events must be sorted by
+ * time (int64 timestamps); survivors keep their order; d_out needs room for n records.  The call synchronises the
+ * stream (it reads the packet's sub-division and the sortedness flag back). */
+int xm_activity_filter(XmCtx* ctx, const void* d_events, int64_t n, int64_t threshold_us, void* d_out, int64_t* d_count, void* stream);
+int xm_activity_reset(XmCtx* ctx, void* stream);
 /* FrameEventFilter.filter_events (python/frame_event_filter.py:19-128): one survivor per key -- pixel
  * (x, y), or (y, rectified x) for XM_FILTER_FIRST_YT, which needs d_x_rect = rectify_cam_coords_i16 of the
  * frame -- written as EventCD records (p = 1, t wrapped to int32 as the reference's int32 images do) in
@@ -287,6 +296,15 @@ int xm_peer_info(int device, int peer_device, int32_t* can_access, int32_t* perf
 int xm_build_xmap(int device, const float* d_time_map, int32_t h, int32_t w, int32_t x_map_width,
                   int32_t t_px_scale, int32_t x_offset, int32_t num_scanlines, int16_t* d_x_map,
                   float* d_t_diffs /* may be NULL */, void* stream);
+
+/* initUndistortRectifyMapInverse (python/cam_proj_calibration.py:31-41; builds disp_cam_map{x,y} at :246-254 and
+ * disp_proj_mapxy at :262-270) = cv2.undistortPoints over the whole w x h pixel grid, on the device: float32 maps
+ * [h, w] (either may be NULL) and/or the interleaved int16 (x, y) table [h, w, 2] = mapf_to_i16 of them (:44-48).
+ * h_K: 3x3 camera matrix (row-major), h_D: n_dist distortion coefficients in OpenCV order (0, 4, 5, 8, 12 or 14; the
+ * tilt terms must be 0), h_RR: the 3x3 product P[:, :3] * R the way OpenCV forms it (cv2.gemm).  Bit-identical to
+ * OpenCV's result (same float64 operations in the same order, 5 iterations).  Synchronises the stream. */
+int xm_build_inverse_lut(int device, const double* h_K, const double* h_D, int32_t n_dist, const double* h_RR, int32_t w,
+                         int32_t h, float* d_mapx, float* d_mapy, int16_t* d_xy_i16, void* stream);
 
 #ifdef __cplusplus
 }

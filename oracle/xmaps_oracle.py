@@ -13,6 +13,10 @@ Parity status: PINNED.  The reference is pure Python and imports in the authorin
 container, so ``tests/golden/generate_golden.py`` runs the *real* reference on seeded
 inputs and commits its outputs under ``tests/golden/``; ``tests/test_oracle_golden.py``
 checks this restatement against those vectors bit-for-bit.
+
+One exception, marked where it stands: ``ActivityNoiseFilterOracle`` restates the closed Metavision
+``ActivityNoiseFilterAlgorithm`` from its published semantics only -- PARITY UNPINNED (no binary, no
+golden vector to check it against).
 """
 from __future__ import annotations
 
@@ -390,6 +394,41 @@ def synth_plane_events(tables: OracleTables, time_map_rect: np.ndarray, z: float
 # Restated with one stable argsort of the keys instead of dense images.
 # --------------------------------------------------------------------------------------
 FILTER_NONE, FILTER_FIRST_YT, FILTER_FIRST_XY, FILTER_LAST_XY, FILTER_MEAN_XY = 0, 1, 2, 3, 4
+
+
+class ActivityNoiseFilterOracle:
+    """PARITY UNPINNED.  Metavision's ``ActivityNoiseFilterAlgorithm(width, height, threshold)`` is a closed binary
+    (``metavision_sdk_cv``) that is absent here and on the GPU box; the reference constructs it at
+    python/depth_reprojection_pipe.py:65-67 (``threshold = int(1e6 / projector_fps)``) and applies it to every packet
+    at :116-117.  This restates its published behaviour ("accepts an event if a similar event happened in its
+    neighbourhood during the last `threshold` microseconds"), the way the SDK's open-source edition implements it:
+
+      * one timestamp per pixel, initially 0, set to the event's timestamp by EVERY incoming event;
+      * an event passes iff one of the 8 neighbours of its pixel (the pixel itself excluded, neighbours outside the
+        sensor skipped) holds a timestamp  >  t - threshold;
+      * events are processed strictly in stream order and the state is carried from packet to packet.
+
+    Sequential by definition, hence a plain loop: use it on small inputs (~3 us per event)."""
+
+    def __init__(self, width: int, height: int, threshold_us: int):
+        self.width, self.height, self.threshold = int(width), int(height), int(threshold_us)
+        self.last_ts = np.zeros((self.height, self.width), dtype=np.int64)
+
+    def reset(self):
+        self.last_ts[:] = 0
+
+    def process_events(self, events: np.ndarray) -> np.ndarray:
+        keep = np.zeros(len(events), dtype=bool)
+        xs, ys, ts = events["x"].astype(np.int64), events["y"].astype(np.int64), events["t"].astype(np.int64)
+        last, w, h, thr = self.last_ts, self.width, self.height, self.threshold
+        for i in range(len(events)):
+            x, y, t = int(xs[i]), int(ys[i]), int(ts[i])
+            if x >= w or y >= h:
+                continue  # (outside the sensor: dropped, no state)
+            last[y, x] = np.iinfo(np.int64).min  # the pixel itself is not a witness
+            keep[i] = bool((last[max(y - 1, 0):y + 2, max(x - 1, 0):x + 2] > t - thr).any())
+            last[y, x] = t
+        return events[keep]
 
 
 def _first_last_per_key(key: np.ndarray):

@@ -388,6 +388,45 @@ def test_x_map_builder(small):
     assert np.array_equal(t_diffs.cpu().numpy(), want_diffs)
 
 
+def test_inverse_lut_builder_matches_reference_tables(manifest):
+    """xm_build_inverse_lut = initUndistortRectifyMapInverse (cam_proj_calibration.py:31-41) on the device: the float32
+    maps and the int16 tables of the default and the HD geometry carry the hashes of the REAL reference's tables, and
+    equal OpenCV's undistortPoints value for value (a strongly distorted lens included)."""
+    import os
+
+    import cv2
+
+    from xmaps_b200.calibration import CamProjCalibrationParams, CamProjMaps, inverse_rectify_map
+    from xmaps_b200.engine import build_inverse_lut
+    from xm_helpers import ROOT
+
+    calib = os.path.join(ROOT, "data", "esl_calib_hhi.json")
+    h = manifest["configs"]["default"]["hash"]
+    maps = CamProjMaps(CamProjCalibrationParams.from_yaml(calib, 640, 480, 720, 1280), table_device="cuda:0")
+    assert sha(maps.disp_cam_mapx_f32) == h["lut_x_f32"] and sha(maps.disp_cam_mapy_f32) == h["lut_y_f32"]
+    assert sha(maps.disp_cam_mapx_i16) == h["lut_x"] and sha(maps.disp_cam_mapy_i16) == h["lut_y"]
+    assert sha(maps.disp_proj_mapxy_i16) == h["remap_xy"]
+    # HD geometry (BASELINE config 3) against the host builder, int16 table straight from the device
+    p = CamProjCalibrationParams.from_yaml(calib, 1280, 720, 1080, 1920)
+    k = p.camera_K.copy()
+    k[:2, :] *= 2.0
+    k[1, 2] += -120.0
+    p.camera_K = k
+    host = CamProjMaps(p)
+    mx, my, xy = build_inverse_lut(p.camera_K, p.camera_D, host.R1, host.P1, (1280, 720), device="cuda:0", with_i16=True)
+    assert np.array_equal(mx.cpu().numpy(), host.disp_cam_mapx_f32) and np.array_equal(my.cpu().numpy(), host.disp_cam_mapy_f32)
+    assert np.array_equal(xy.cpu().numpy()[..., 0], host.disp_cam_mapx_i16) and np.array_equal(xy.cpu().numpy()[..., 1], host.disp_cam_mapy_i16)
+    # all 12 non-tilt coefficients, strong distortion
+    d12 = np.array([-0.31, 0.12, 1.5e-3, -2.1e-3, -0.02, 0.01, -0.004, 0.002, 1e-3, -2e-4, 5e-4, 1e-4])
+    want_x, want_y = inverse_rectify_map(p.camera_K, d12, host.R1, host.P1, (1280, 720))
+    got_x, got_y = build_inverse_lut(p.camera_K, d12, host.R1, host.P1, (1280, 720), device="cuda:0")
+    assert np.array_equal(got_x.cpu().numpy(), want_x) and np.array_equal(got_y.cpu().numpy(), want_y)
+    # no coefficient vector at all (OpenCV skips the iteration)
+    pts = cv2.undistortPoints(np.array([[[3.0, 5.0]], [[100.0, 7.0]]], dtype=np.float32), p.camera_K, None, None, host.R1, host.P1)
+    gx, gy = build_inverse_lut(p.camera_K, None, host.R1, host.P1, (101, 8), device="cuda:0")
+    assert gx[5, 3].item() == pts[0, 0, 0] and gy[5, 3].item() == pts[0, 0, 1] and gx[7, 100].item() == pts[1, 0, 0]
+
+
 # ------------------------------------------------------------------------------------------------
 # full-size workloads (BASELINE.json configs 2 and 3)
 # ------------------------------------------------------------------------------------------------

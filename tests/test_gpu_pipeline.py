@@ -149,6 +149,7 @@ def test_stream_through_the_pipe(pipes):
     got = []
     proj.frame_callback = got.append
     proj.reset()
+    proj.activity_filter = False  # (this stream is far too sparse for the activity filter: next test)
     try:
         for i in range(0, len(stream), 23_000):
             part = stream[i : i + 23_000]
@@ -156,6 +157,33 @@ def test_stream_through_the_pipe(pipes):
             proj.process_events(part)
     finally:
         proj.frame_callback = None
+        proj.activity_filter = True
     assert len(got) == len(want_frames) >= 5
+    for bgr, f in zip(got, want_frames):
+        assert np.array_equal(bgr, orc.colorize(orc.frame_disparity_map(tables, f, 0), tables.depth_scale, 0.1, 1.0))
+
+
+def test_stream_through_the_pipe_with_activity_filter(pipes):
+    """The whole of process_events as the reference runs it (depth_reprojection_pipe.py:110-119): polarity filter ->
+    activity-noise filter (state carried across packets) -> trigger finder -> process_ev_frame."""
+    proj, _ = pipes
+    tables, _ = load_golden_tables("default")
+    rng = np.random.default_rng(6)
+    stream = orc.synth_projector_stream(7, 11, 100_000, 640, 480)
+    stream["p"] = rng.random(len(stream)) < 0.9
+    want_frames = []
+    otf = orc.TriggerFinderOracle(60, lambda e: want_frames.append(e.copy()))
+    oaf = orc.ActivityNoiseFilterOracle(640, 480, int(1e6 / 60))
+    got = []
+    proj.frame_callback = got.append
+    proj.reset()
+    try:
+        for i in range(0, len(stream), 61_000):
+            part = stream[i : i + 61_000]
+            otf.process_events(oaf.process_events(part[part["p"] == 1]))
+            proj.process_events(part)
+    finally:
+        proj.frame_callback = None
+    assert len(got) == len(want_frames) >= 3
     for bgr, f in zip(got, want_frames):
         assert np.array_equal(bgr, orc.colorize(orc.frame_disparity_map(tables, f, 0), tables.depth_scale, 0.1, 1.0))

@@ -210,3 +210,73 @@ def test_drop_frame_rule(small):
         tf.process_events(part)
     assert a == b and len(a) > 3
     assert otf.last_frame_start_us == tf.last_frame_start_us
+
+
+# ---- N2: activity-noise filter (Metavision semantics restated; the oracle is UNPINNED) ------------------------
+def same_events(a, b):
+    """field by field (the records have two padding bytes that NumPy does not carry through fancy indexing)"""
+    return len(a) == len(b) and all(np.array_equal(a[k], b[k]) for k in ("x", "y", "p", "t"))
+
+
+def activity_stream(seed, n, w, h, span_us, hot=0):
+    """Time-sorted events: uniform background + `hot` bursts on small patches (so that both outcomes occur)."""
+    rng = np.random.default_rng(seed)
+    ev = np.zeros(n, dtype=orc.EVENT_DTYPE)
+    ev["x"] = rng.integers(0, w, n)
+    ev["y"] = rng.integers(0, h, n)
+    for k in range(hot):
+        cx, cy = rng.integers(2, w - 2), rng.integers(2, h - 2)
+        idx = rng.choice(n, n // (4 * max(hot, 1)), replace=False)
+        ev["x"][idx] = cx + rng.integers(-2, 3, len(idx))
+        ev["y"][idx] = cy + rng.integers(-2, 3, len(idx))
+    ev["p"] = 1
+    ev["t"] = np.sort(rng.integers(0, span_us, n)) + 1_000_000
+    return ev
+
+
+@pytest.mark.parametrize("n,span,thr,hot", [(60_000, 12_000, 16_666, 0), (60_000, 12_000, 800, 3), (40_000, 100_000, 5_000, 2), (30_000, 400, 16_666, 0)])
+def test_activity_filter_matches_oracle(small, n, span, thr, hot):
+    """One packet: sparse / dense, thresholds shorter and longer than the packet (the long packet of case 3 is cut
+    into ~20 sub-packets on the device), borders included."""
+    tables, eng = small
+    w, h = tables.cam_w, tables.cam_h
+    ev = activity_stream(n, n, w, h, span, hot)
+    ev["x"][:50] = 0  # image borders
+    ev["y"][50:100] = h - 1
+    eng.activity_reset()
+    want = orc.ActivityNoiseFilterOracle(w, h, thr).process_events(ev)
+    got = eng.activity_filter(ev, thr).numpy()
+    assert 0 < len(want) < len(ev)
+    assert same_events(got, want)
+
+
+def test_activity_filter_carries_state_across_packets(small):
+    """The per-pixel timestamps survive from packet to packet (and activity_reset clears them); ties in time included."""
+    tables, eng = small
+    w, h = tables.cam_w, tables.cam_h
+    ev = activity_stream(11, 90_000, w, h, 30_000, hot=2)
+    ev["t"] = (ev["t"] // 7) * 7  # many equal timestamps: only the stream order separates them
+    thr = 2_000
+    oaf = orc.ActivityNoiseFilterOracle(w, h, thr)
+    eng.activity_reset()
+    for part in chunked(ev, [1, 7_000, 20_000, 3, 40_000, 0, 22_996]):
+        want = oaf.process_events(part)
+        got = eng.activity_filter(part, thr).numpy()
+        assert same_events(got, want)
+    # a fresh state: the very first event of a recording has no witness unless t < threshold (timestamps start at 0)
+    eng.activity_reset()
+    first = ev[:1].copy()
+    assert len(eng.activity_filter(first, thr)) == 0
+    first["t"] = thr - 1
+    eng.activity_reset()
+    assert len(eng.activity_filter(first, thr)) == 1
+
+
+def test_activity_filter_rejects_unsorted_packets(small):
+    tables, eng = small
+    ev = activity_stream(3, 5_000, tables.cam_w, tables.cam_h, 10_000)
+    ev["t"][2_000] -= 5_000
+    eng.activity_reset()
+    with pytest.raises(Exception, match="sorted"):
+        eng.activity_filter(ev, 1_000)
+    eng.activity_reset()

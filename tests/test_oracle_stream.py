@@ -86,3 +86,25 @@ def test_find_trigger_statuses():
     assert orc.find_trigger(trigger_case(7, 2500), 60)[:3] == (0, 2499, 4999)   # 17.6 ms: longer than a frame
     assert orc.find_trigger(trigger_case(17, 900), 60)[:3] == (0, 2499, 3399)   # long enough, too few events
     assert orc.find_trigger(trigger_case(2, 2500), 60)[0] == -1                 # 5.1 ms: shorter than half a frame
+
+
+def test_activity_filter_oracle_semantics():
+    """The restated Metavision activity filter (UNPINNED): witnesses are the 8 neighbours only, strictly younger
+    than the threshold, in stream order, with the state carried across packets."""
+    def ev(rows):
+        a = np.zeros(len(rows), dtype=orc.EVENT_DTYPE)
+        for i, (x, y, t) in enumerate(rows):
+            a[i] = (x, y, 1, t)
+        return a
+
+    f = orc.ActivityNoiseFilterOracle(8, 8, 100)
+    out = f.process_events(ev([(3, 3, 1000), (3, 3, 1010), (4, 4, 1020), (7, 7, 1030), (5, 5, 1119), (5, 5, 1120), (0, 0, 1130), (1, 0, 1229), (1, 1, 1330)]))
+    # 1: nothing around; 2: same pixel is no witness; 3: diagonal neighbour 20 us ago; 4: too far; 5: (4,4) 99 us ago;
+    # 6: (4,4) exactly 100 us ago does not count; 7: corner, nothing; 8: (0,0) 99 us ago; 9: (1,0) 101 us ago
+    assert [tuple(int(v) for v in (e["x"], e["y"], e["t"])) for e in out] == [(4, 4, 1020), (5, 5, 1119), (1, 0, 1229)]
+    # carried state: a new packet still sees (1,1) at t = 1330
+    assert len(f.process_events(ev([(2, 2, 1400)]))) == 1
+    f.reset()
+    assert len(f.process_events(ev([(2, 2, 1400)]))) == 0
+    # timestamps start at 0: during the first `threshold` us everything passes
+    assert len(orc.ActivityNoiseFilterOracle(8, 8, 100).process_events(ev([(2, 2, 99), (7, 7, 100)]))) == 1

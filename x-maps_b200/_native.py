@@ -112,6 +112,8 @@ SIGNATURES = {
     "xm_colorize": (C.c_int, [_P, _P, _I64, C.c_double, C.c_float, C.c_float, _P, _P]),
     "xm_point_cloud": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P]),
     "xm_polarity_filter": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
+    "xm_activity_filter": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P]),
+    "xm_activity_reset": (C.c_int, [_P, _P]),
     "xm_filter_events": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P, _P, _P]),
     "xm_find_trigger": (C.c_int, [_P, _P, _I64, _I64, C.c_double, _I64, _P, _P]),
     "xm_peer_alloc": (C.c_int, [C.c_int, _I64, C.POINTER(_P), C.POINTER(XmIpcHandle)]),
@@ -121,6 +123,7 @@ SIGNATURES = {
     "xm_peer_copy": (C.c_int, [_P, C.c_int, _P, C.c_int, _I64, _P]),
     "xm_peer_info": (C.c_int, [C.c_int, C.c_int, C.POINTER(_I32), C.POINTER(_I32)]),
     "xm_build_xmap": (C.c_int, [C.c_int, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "xm_build_inverse_lut": (C.c_int, [C.c_int, _P, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
 }
 
 

@@ -105,11 +105,17 @@ class CamProjCalibrationParams:
         )
 
 
-def inverse_rectify_map(K, D, R, P, size):
+def inverse_rectify_map(K, D, R, P, size, device=None):
     """Map every pixel of an *unrectified* ``size = (W, H)`` image to rectified coordinates
     (reference: initUndistortRectifyMapInverse :31-41): ``cv2.undistortPoints`` over the full
-    pixel grid in float32."""
+    pixel grid in float32 -- on the host with OpenCV as the reference does, or with ``device`` set by the
+    CUDA builder (``engine.build_inverse_lut``, bit-identical)."""
     width, height = size
+    if device is not None:
+        from .engine import build_inverse_lut
+
+        mx, my = build_inverse_lut(K, D, R, P, size, device=device)
+        return mx.cpu().numpy(), my.cpu().numpy()
     grid = np.empty((height * width, 1, 2), dtype=np.float32)
     grid[:, 0, 0] = np.tile(np.arange(width, dtype=np.float32), height)
     grid[:, 0, 1] = np.repeat(np.arange(height, dtype=np.float32), width)
@@ -135,6 +141,7 @@ class CamProjMaps:
     calib: CamProjCalibrationParams
     cam_is_left: bool = False
     zero_undistort_proj_map: bool = False
+    table_device: Optional[str] = None  # e.g. "cuda:0": build the inverse LUTs on the GPU (bit-identical to the OpenCV path)
 
     R1: np.ndarray = field(init=False, repr=False)
     R2: np.ndarray = field(init=False, repr=False)
@@ -168,13 +175,13 @@ class CamProjMaps:
         )
         # inverse LUTs cam -> rect (reference :246-254)
         self.disp_cam_mapx_f32, self.disp_cam_mapy_f32 = inverse_rectify_map(
-            c.camera_K, c.camera_D, self.R1, self.P1, (c.camera_width, c.camera_height)
+            c.camera_K, c.camera_D, self.R1, self.P1, (c.camera_width, c.camera_height), device=self.table_device
         )
         self.disp_cam_mapx_i16 = round_map_to_i16(self.disp_cam_mapx_f32)
         self.disp_cam_mapy_i16 = round_map_to_i16(self.disp_cam_mapy_f32)
         # inverse LUT proj -> rect, interleaved (x, y) int16 (reference :262-270)
         px, py = inverse_rectify_map(
-            c.projector_K, c.projector_D, self.R2, self.P2, (c.projector_width, c.projector_height)
+            c.projector_K, c.projector_D, self.R2, self.P2, (c.projector_width, c.projector_height), device=self.table_device
         )
         self.disp_proj_mapxy_i16 = np.stack((round_map_to_i16(px), round_map_to_i16(py)), axis=-1)
 

@@ -34,7 +34,10 @@
 namespace xm {
 
 constexpr int kBatchMax = 32;    // frames per launch (the frame table travels in the kernel parameters)
-constexpr int kBatchMaps = 3;    // scatter maps in rotation
+#ifndef XM_BATCH_MAPS
+#define XM_BATCH_MAPS 3
+#endif
+constexpr int kBatchMaps = XM_BATCH_MAPS;  // scatter maps in rotation
 constexpr int kBatchHeader = 1152;  // mbarriers, ring descriptors, CTA accumulators, per-warp frame constants (2 slots)
 constexpr int kCamTilePx = 4096;  // camera-view epilogue item
 #ifndef XM_TILE_WARPS

@@ -109,6 +109,9 @@ struct XmCtx {
     unsigned* d_pause_idx = nullptr;
     long long pause_cap = 0;
     void* d_stream_scratch = nullptr;  // TriggerScratch + xp_max
+    unsigned* d_act_first = nullptr;    // [cam_h * cam_w] activity filter: first event index of the sub-packet per pixel
+    long long* d_act_last = nullptr;    // [cam_h * cam_w] ... latest timestamp per pixel, carried across packets (starts at 0)
+    long long* d_act_plan = nullptr;    // [kActPlanCap + 1] sub-packet bounds, then: count (int), unsorted flag (unsigned), running total, part total
     // staging for xm_frame_host
     void* d_stage_ev = nullptr;
     long long stage_ev_cap = 0;
@@ -128,7 +131,7 @@ struct XmCtx {
     int opt_batch = 1;        // 1: xm_frame_batch renders uniform batches with one persistent kernel per <= 32 frames
                               //    (event warps + dedicated epilogue warps; 47 vs 57 us per 5 M-event frame, EXPERIMENTS_r01.md)
     int batch_occ = 0, batch_smem[2] = {0, 0}, batch_cols[2] = {0, 0};  // launch configuration of batch_kernel ([view])
-    unsigned long long* d_map_ring[xm::kBatchMaps] = {nullptr, nullptr, nullptr};  // [0] = d_map
+    unsigned long long* d_map_ring[xm::kBatchMaps] = {};  // [0] = d_map
     xm::FrameState* d_bstate = nullptr;  // [kBatchMax + 1] state blocks of the current batch
     const xm::FrameState* status_src = nullptr;  // state block xm_frame_status reports (NULL: d_state + last_slot)
     int opt_pdl = 1;          // programmatic dependent launch between K1 / K2 / next K1
@@ -1097,6 +1100,9 @@ int xm_ctx_destroy(XmCtx* c) {
     cudaFree(c->d_filter_last);
     cudaFree(c->d_pause_idx);
     cudaFree(c->d_stream_scratch);
+    cudaFree(c->d_act_first);
+    cudaFree(c->d_act_last);
+    cudaFree(c->d_act_plan);
     cudaFree(c->d_stage_ev);
     cudaFree(c->d_stage_out);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
@@ -1678,6 +1684,94 @@ int xm_polarity_filter(XmCtx* c, const void* d_events, int64_t n, void* d_out, i
     return XM_OK;
 }
 
+namespace {
+constexpr int kActPlanCap = 4096;  // sub-packets per call (a packet of kActPlanCap thresholds' length; the last one takes the rest)
+
+int ensure_activity(XmCtx* c) {
+    const size_t cells = static_cast<size_t>(c->cam_w) * c->cam_h;
+    if (!c->d_act_first) XM_CUDA(cudaMalloc(&c->d_act_first, cells * sizeof(unsigned)));
+    if (!c->d_act_last) {
+        XM_CUDA(cudaMalloc(&c->d_act_last, cells * sizeof(long long)));
+        XM_CUDA(cudaMemset(c->d_act_last, 0, cells * sizeof(long long)));
+    }
+    if (!c->d_act_plan) XM_CUDA(cudaMalloc(&c->d_act_plan, (kActPlanCap + 1 + 4) * sizeof(long long)));
+    return XM_OK;
+}
+}  // namespace
+
+int xm_activity_reset(XmCtx* c, void* stream) {
+    if (!c) return fail(XM_ERR_INVALID_ARG, "activity_reset: NULL context");
+    DeviceGuard guard(c->device);
+    if (c->d_act_last)
+        XM_CUDA(cudaMemsetAsync(c->d_act_last, 0, static_cast<size_t>(c->cam_w) * c->cam_h * sizeof(long long), static_cast<cudaStream_t>(stream)));
+    return XM_OK;
+}
+
+int xm_activity_filter(XmCtx* c, const void* d_events, int64_t n, int64_t threshold_us, void* d_out, int64_t* d_count, void* stream) {
+    if (!c || n < 0 || !d_count || (n > 0 && (!d_events || !d_out))) return fail(XM_ERR_INVALID_ARG, "activity_filter: bad arguments");
+    if (threshold_us <= 0) return fail(XM_ERR_INVALID_ARG, "activity_filter: threshold must be positive");
+    if (n > 0xfffffffeLL) return fail(XM_ERR_UNSUPPORTED, "more than 2^32 - 2 events");
+    if (reinterpret_cast<uintptr_t>(d_events) & 15 || reinterpret_cast<uintptr_t>(d_out) & 15)
+        return fail(XM_ERR_INVALID_ARG, "event buffers must be 16-byte aligned");
+    DeviceGuard guard(c->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    XM_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
+    if (n == 0) return XM_OK;
+    int rc = ensure_activity(c);
+    if (rc) return rc;
+    const int4* ev = static_cast<const int4*>(d_events);
+    long long* bounds = c->d_act_plan;
+    int* d_nsub = reinterpret_cast<int*>(c->d_act_plan + kActPlanCap + 1);
+    unsigned* d_unsorted = reinterpret_cast<unsigned*>(c->d_act_plan + kActPlanCap + 2);
+    long long* d_part = c->d_act_plan + kActPlanCap + 3;
+    XM_CUDA(cudaMemsetAsync(d_unsorted, 0, 8, s));
+    // sub-packets that each span less than the threshold (normally one: a packet is a slice of a frame)
+    xm::activity_plan_kernel<<<1, 1, 0, s>>>(ev, n, threshold_us, bounds, kActPlanCap, d_nsub);
+    XM_LAUNCHED();
+    std::vector<long long> h_bounds(kActPlanCap + 2);
+    XM_CUDA(cudaMemcpyAsync(h_bounds.data(), bounds, (kActPlanCap + 2) * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    XM_CUDA(cudaStreamSynchronize(s));
+    const int nsub = *reinterpret_cast<const int*>(&h_bounds[kActPlanCap + 1]);
+    const long long cells = static_cast<long long>(c->cam_w) * c->cam_h;
+    for (int k = 0; k < nsub; ++k) {
+        const long long lo = h_bounds[k], cnt = h_bounds[k + 1] - lo;
+        if (cnt <= 0) continue;
+        xm::ActivityParams p;
+        p.events = ev + lo;
+        p.n = cnt;
+        p.threshold = threshold_us;
+        p.cols = c->cam_w;
+        p.rows = c->cam_h;
+        p.first = c->d_act_first;
+        p.last = c->d_act_last;
+        p.unsorted = d_unsorted;
+        const long long blocks = (cnt + xm::kCompactBlock - 1) / xm::kCompactBlock;
+        rc = ensure_counts(c, blocks, s);
+        if (rc) return rc;
+        xm::activity_clear_kernel<<<grid_for(cells, 256, 4, c->sm_count * 8), 256, 0, s>>>(p.first, cells);
+        XM_LAUNCHED();
+        xm::activity_mark_kernel<<<grid_for(cnt, 256, 4, c->sm_count * 8), 256, 0, s>>>(p);
+        XM_LAUNCHED();
+        const xm::ActivityPred pred{p};
+        const xm::ActivityEmit emit{p.events, static_cast<int4*>(d_out), reinterpret_cast<const long long*>(d_count)};
+        xm::flag_count_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(pred, cnt, c->d_counts);
+        XM_LAUNCHED();
+        xm::compact_scan_kernel<<<1, 1024, 0, s>>>(c->d_counts, blocks, d_part);
+        XM_LAUNCHED();
+        xm::flag_write_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(pred, emit, cnt, c->d_counts);
+        XM_LAUNCHED();
+        xm::activity_update_kernel<<<grid_for(cnt, 256, 4, c->sm_count * 8), 256, 0, s>>>(p);
+        XM_LAUNCHED();
+        xm::activity_advance_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(d_count), d_part);
+        XM_LAUNCHED();
+    }
+    unsigned h_unsorted = 0;
+    XM_CUDA(cudaMemcpyAsync(&h_unsorted, d_unsorted, 4, cudaMemcpyDeviceToHost, s));
+    XM_CUDA(cudaStreamSynchronize(s));
+    if (h_unsorted) return fail(XM_ERR_INVALID_ARG, "activity_filter: timestamps are not sorted (the filter's state is now undefined: xm_activity_reset)");
+    return XM_OK;
+}
+
 int xm_filter_events(XmCtx* c, const void* d_events, int64_t n, int32_t mode, const int16_t* d_x_rect, int32_t as_reference,
                      void* d_out, int64_t* d_count, void* stream) {
     if (!c || n < 0 || !d_count || (n > 0 && (!d_events || !d_out))) return fail(XM_ERR_INVALID_ARG, "filter: bad arguments");
@@ -1799,6 +1893,42 @@ int xm_build_xmap(int device, const float* d_time_map, int32_t h, int32_t w, int
     xm::build_xmap_kernel<<<h, 256, static_cast<size_t>(w) * 4, s>>>(d_time_map, h, w, x_map_width, t_px_scale, x_offset, num_scanlines,
                                                                     d_x_map, d_t_diffs);
     XM_LAUNCHED();
+    return XM_OK;
+}
+
+int xm_build_inverse_lut(int device, const double* h_K, const double* h_D, int32_t n_dist, const double* h_RR, int32_t w, int32_t h,
+                         float* d_mapx, float* d_mapy, int16_t* d_xy_i16, void* stream) {
+    if (!h_K || !h_RR || w <= 0 || h <= 0 || n_dist < 0 || (n_dist > 0 && !h_D) || (!d_mapx && !d_mapy && !d_xy_i16))
+        return fail(XM_ERR_INVALID_ARG, "build_inverse_lut: bad arguments");
+    if (n_dist != 0 && n_dist != 4 && n_dist != 5 && n_dist != 8 && n_dist != 12 && n_dist != 14)
+        return fail(XM_ERR_INVALID_ARG, "build_inverse_lut: %d distortion coefficients (OpenCV takes 4, 5, 8, 12 or 14)", n_dist);
+    if (n_dist == 14 && (h_D[12] != 0.0 || h_D[13] != 0.0)) return fail(XM_ERR_UNSUPPORTED, "build_inverse_lut: tilted sensor model (tau_x, tau_y) is not supported");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(XM_ERR_CUDA, "cannot select device %d", device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    xm::InverseLutParams p;
+    memset(&p, 0, sizeof(p));
+    p.ifx = 1.0 / h_K[0];
+    p.ify = 1.0 / h_K[4];
+    p.cx = h_K[2];
+    p.cy = h_K[5];
+    for (int i = 0; i < n_dist && i < 12; ++i) p.k[i] = h_D[i];
+    p.has_dist = n_dist > 0 ? 1 : 0;  // (OpenCV runs the iteration whenever a coefficient vector is given, zeros included)
+    for (int i = 0; i < 9; ++i) p.rr[i] = h_RR[i];
+    p.w = w;
+    p.h = h;
+    unsigned* d_flag = nullptr;
+    XM_CUDA(cudaMalloc(&d_flag, 4));
+    XM_CUDA(cudaMemsetAsync(d_flag, 0, 4, s));
+    const long long n = static_cast<long long>(w) * h;
+    xm::build_inverse_lut_kernel<<<grid_for(n, 256, 1, 148 * 16), 256, 0, s>>>(p, d_mapx, d_mapy, d_xy_i16, d_flag);
+    XM_LAUNCHED();
+    unsigned h_flag = 0;
+    cudaError_t e = cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_flag);
+    XM_CUDA(e);
+    if (h_flag) return fail(XM_ERR_TABLE_RANGE, "rectification map does not fit int16");
     return XM_OK;
 }
 

@@ -347,4 +347,71 @@ __global__ void __launch_bounds__(256) build_xmap_kernel(const float* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// N3 (second half): initUndistortRectifyMapInverse (python/cam_proj_calibration.py:31-41, used at :246-270)
+// = cv2.undistortPoints over the whole pixel grid.  OpenCV's point loop (cvUndistortPointsInternal, default
+// criteria = 5 iterations, no tilt model) restated operation by operation in float64 without contraction, so the
+// float32 maps -- and the int16 tables rounded from them -- are bit-identical to the host's:
+//   x = (u - cx) / fx (as * (1 / fx)), y likewise; 5 x { r2; icdist = (1 + ((k7 r2 + k6) r2 + k5) r2) / (1 + ((k4 r2 +
+//   k1) r2 + k0) r2); dX = 2 k2 x y + k3 (r2 + 2 x x) + k8 r2 + k9 r2 r2; dY likewise; x = (x0 - dX) icdist; ... };
+//   [xx yy ww] = RR [x y 1], RR = P[:, :3] R (passed in, computed by the caller the way OpenCV does); out = xx / ww.
+// ---------------------------------------------------------------------------------------------
+struct InverseLutParams {
+    double ifx, ify, cx, cy;
+    double k[12];   // k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 (OpenCV order)
+    double rr[9];   // row-major
+    int w, h;
+    int has_dist;
+};
+
+__global__ void __launch_bounds__(256) build_inverse_lut_kernel(const InverseLutParams p, float* __restrict__ mapx, float* __restrict__ mapy,
+                                                                short* __restrict__ xy_i16, unsigned* __restrict__ overflow) {
+    const long long n = static_cast<long long>(p.w) * p.h;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(i / p.w), u = static_cast<int>(i - static_cast<long long>(v) * p.w);
+        double x = __dmul_rn(__dsub_rn(static_cast<double>(u), p.cx), p.ifx);
+        double y = __dmul_rn(__dsub_rn(static_cast<double>(v), p.cy), p.ify);
+        const double x00 = x, y00 = y;
+        if (p.has_dist) {
+            const double x0 = x, y0 = y;
+            const double* k = p.k;
+#pragma unroll 1
+            for (int j = 0; j < 5; ++j) {
+                const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+                const double num = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[7], r2), k[6]), r2), k[5]), r2));
+                const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[4], r2), k[1]), r2), k[0]), r2));
+                const double icdist = __ddiv_rn(num, den);
+                if (icdist < 0) {  // (OpenCV: give up and return the undistorted start value)
+                    x = x00;
+                    y = y00;
+                    break;
+                }
+                const double two_k2 = __dmul_rn(2.0, k[2]), two_k3 = __dmul_rn(2.0, k[3]);
+                const double dx = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(two_k2, x), y),
+                                                                  __dmul_rn(k[3], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x)))),
+                                                        __dmul_rn(k[8], r2)),
+                                              __dmul_rn(__dmul_rn(k[9], r2), r2));
+                const double dy = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(k[2], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))),
+                                                                  __dmul_rn(__dmul_rn(two_k3, x), y)),
+                                                        __dmul_rn(k[10], r2)),
+                                              __dmul_rn(__dmul_rn(k[11], r2), r2));
+                x = __dmul_rn(__dsub_rn(x0, dx), icdist);
+                y = __dmul_rn(__dsub_rn(y0, dy), icdist);
+            }
+        }
+        const double xx = __dadd_rn(__dadd_rn(__dmul_rn(p.rr[0], x), __dmul_rn(p.rr[1], y)), p.rr[2]);
+        const double yy = __dadd_rn(__dadd_rn(__dmul_rn(p.rr[3], x), __dmul_rn(p.rr[4], y)), p.rr[5]);
+        const double ww = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(__dmul_rn(p.rr[6], x), __dmul_rn(p.rr[7], y)), p.rr[8]));
+        const float fx = __double2float_rn(__dmul_rn(xx, ww)), fy = __double2float_rn(__dmul_rn(yy, ww));
+        if (mapx) mapx[i] = fx;
+        if (mapy) mapy[i] = fy;
+        if (xy_i16) {  // mapf_to_i16 (:44-48): np.rint (half-even), range-checked
+            const float rx = rintf(fx), ry = rintf(fy);
+            if (!(rx >= -32768.0f && rx <= 32767.0f && ry >= -32768.0f && ry <= 32767.0f)) *overflow = 1u;
+            xy_i16[2 * i] = static_cast<short>(static_cast<int>(rx));
+            xy_i16[2 * i + 1] = static_cast<short>(static_cast<int>(ry));
+        }
+    }
+}
+
 }  // namespace xm

@@ -81,6 +81,109 @@ struct CopyEventEmit {
 };
 
 // ---------------------------------------------------------------------------------------------
+// N2: ActivityNoiseFilterAlgorithm(width, height, threshold).process_events (Metavision, closed binary; call
+// site python/depth_reprojection_pipe.py:65-67,116-117).  Restated from its published semantics -- an event
+// passes iff one of the 8 neighbours of its pixel saw an event less than `threshold` us earlier (t_n > t -
+// threshold, per-pixel timestamps start at 0 and are carried across packets; the event's own pixel is not a
+// witness) -- see oracle/xmaps_oracle.py:activity_filter ("parity unpinned").
+//
+// The definition is sequential (every event updates its pixel before the next event is looked at).  On a
+// time-sorted packet that spans less than `threshold` it is equivalent to an order-free test: neighbour n is a
+// witness for event i iff an event of THIS packet with a smaller index sits on n (it is younger than the
+// threshold by construction) or the timestamp carried in from earlier packets is.  So: first[n] = smallest
+// event index on pixel n (atomicMin), the test reads first[] and the carried image, survivors are written by
+// the ordered compaction, and last[n] takes the packet's timestamps afterwards (atomicMax).  Longer packets are
+// cut into sub-packets that each span less than the threshold (xm_activity_filter).
+// ---------------------------------------------------------------------------------------------
+struct ActivityParams {
+    const int4* events;  // the sub-packet
+    long long n;
+    long long threshold;
+    int cols, rows;
+    unsigned* first;       // [rows * cols] first event index of the sub-packet per pixel, 0xffffffff = none
+    long long* last;       // [rows * cols] latest timestamp per pixel carried across packets
+    unsigned* unsorted;    // device flag: a timestamp smaller than its predecessor's
+};
+
+__global__ void __launch_bounds__(256) activity_clear_kernel(unsigned* first, long long cells) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < cells; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        first[i] = 0xffffffffu;
+}
+
+__global__ void __launch_bounds__(256) activity_mark_kernel(const ActivityParams p) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const EventFields e = unpack_event(ld_event_plain(p.events + i));
+        if (i > 0 && unpack_event(ld_event_plain(p.events + i - 1)).t_bits > e.t_bits) *p.unsorted = 1u;
+        if (e.x < static_cast<unsigned>(p.cols) && e.y < static_cast<unsigned>(p.rows))
+            atomicMin(p.first + static_cast<long long>(e.y) * p.cols + e.x, static_cast<unsigned>(i));
+    }
+}
+
+struct ActivityPred {
+    ActivityParams p;
+    __device__ __forceinline__ bool operator()(long long i) const {
+        const EventFields e = unpack_event(ld_event_plain(p.events + i));
+        if (e.x >= static_cast<unsigned>(p.cols) || e.y >= static_cast<unsigned>(p.rows)) return false;
+        const long long th = e.t_bits - p.threshold;
+        const int x = static_cast<int>(e.x), y = static_cast<int>(e.y);
+        bool keep = false;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= p.rows) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = x + dx;
+                if ((dx == 0 && dy == 0) || xx < 0 || xx >= p.cols) continue;
+                const long long c = static_cast<long long>(yy) * p.cols + xx;
+                keep = keep || __ldg(p.first + c) < static_cast<unsigned>(i) || __ldg(p.last + c) > th;
+            }
+        }
+        return keep;
+    }
+};
+
+// output position = *base + position inside the sub-packet
+struct ActivityEmit {
+    const int4* events;
+    int4* out;
+    const long long* base;
+    __device__ __forceinline__ void operator()(long long i, unsigned pos) const { out[*base + pos] = ld_event_plain(events + i); }
+};
+
+__global__ void __launch_bounds__(256) activity_update_kernel(const ActivityParams p) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const EventFields e = unpack_event(ld_event_plain(p.events + i));
+        if (e.x < static_cast<unsigned>(p.cols) && e.y < static_cast<unsigned>(p.rows))
+            atomicMax(p.last + static_cast<long long>(e.y) * p.cols + e.x, e.t_bits);
+    }
+}
+
+// *total += *part (one sub-packet's survivors)
+__global__ void activity_advance_kernel(long long* total, const long long* part) { *total += *part; }
+
+// Cuts a time-sorted packet into sub-packets that each span less than `threshold`: bounds[0] = 0, bounds[k + 1] =
+// first index whose timestamp is >= t[bounds[k]] + threshold, ... until n; *count = number of sub-packets
+// (at most `cap`, the last one takes the rest).  One thread, a binary search per cut.
+__global__ void activity_plan_kernel(const int4* events, long long n, long long threshold, long long* bounds, int cap, int* count) {
+    int k = 0;
+    long long lo = 0;
+    bounds[0] = 0;
+    while (lo < n && k < cap - 1) {
+        const long long limit = unpack_event(ld_event_plain(events + lo)).t_bits + threshold;
+        long long a = lo + 1, b = n;  // first index in (lo, n] with t >= limit
+        while (a < b) {
+            const long long m = a + (b - a) / 2;
+            if (unpack_event(ld_event_plain(events + m)).t_bits >= limit) b = m; else a = m + 1;
+        }
+        bounds[++k] = a;
+        lo = a;
+    }
+    if (lo < n) bounds[++k] = n;
+    *count = k;
+}
+
+// ---------------------------------------------------------------------------------------------
 // N4: de-duplication filters.  Key image of `rows` x `stride` cells; per cell the index of the first
 // and of the last event that hit it (atomicMin / atomicMax).  Modes as XM_FILTER_*.
 // ---------------------------------------------------------------------------------------------

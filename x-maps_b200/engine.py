@@ -264,6 +264,23 @@ class DepthEngine:
         N.check(N.lib.xm_polarity_filter(self._ctx, ev.raw.data_ptr() if n else None, n, out.data_ptr(), count.data_ptr(), self._stream()))
         return DeviceEvents(out[: int(count.item())], ev.time_f64)
 
+    def activity_filter(self, events, threshold_us: int) -> DeviceEvents:
+        """The reference's Metavision ``ActivityNoiseFilterAlgorithm(w, h, threshold_us).process_events``
+        (depth_reprojection_pipe.py:65-67,116-117) on the device: keeps an event iff one of the 8 neighbours of its
+        pixel fired less than ``threshold_us`` earlier; the per-pixel timestamps live in the context and are carried
+        from packet to packet (``activity_reset``).  Semantics restated from the SDK's documentation (closed binary)."""
+        ev = self.events(events)
+        n = len(ev)
+        if ev.time_f64:
+            raise ValueError("the activity filter works on integer timestamps")
+        out = torch.empty((max(n, 1), 4), dtype=torch.int32, device=self.device)
+        count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        N.check(N.lib.xm_activity_filter(self._ctx, ev.raw.data_ptr() if n else None, n, int(threshold_us), out.data_ptr(), count.data_ptr(), self._stream()))
+        return DeviceEvents(out[: int(count.item())], False)
+
+    def activity_reset(self):
+        N.check(N.lib.xm_activity_reset(self._ctx, self._stream()))
+
     def filter_events(self, events, mode: int, x_rect: Optional[torch.Tensor] = None, as_reference: bool = True) -> DeviceEvents:
         """One survivor per key (``frame_event_filter.py``'s filters, ``N.FILTER_*``) as a new device
         event buffer in row-major key order; see ``xm_filter_events`` in the header."""
@@ -458,3 +475,31 @@ def build_x_map(time_map_rect, x_map_width: int, t_px_scale: int, x_offset: int,
         )
     )
     return x_map, t_diffs
+
+
+def build_inverse_lut(K, D, R, P, size, device=None, with_i16: bool = False):
+    """initUndistortRectifyMapInverse (/root/reference/python/cam_proj_calibration.py:31-41) on the GPU: the rectified
+    coordinates of every pixel of an unrectified ``size = (W, H)`` image, i.e. ``cv2.undistortPoints`` over the whole
+    grid, bit-identical to OpenCV's float32 result.  Returns ``(map_x, map_y)`` float32 CUDA tensors [H, W] (and the
+    interleaved int16 table [H, W, 2] = ``mapf_to_i16`` of both with ``with_i16``)."""
+    import cv2
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("xmaps_b200 needs a CUDA device")
+    dev = torch.device("cuda" if device is None else device)
+    dev = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+    w, h = int(size[0]), int(size[1])
+    k = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(3, 3))
+    d = np.ascontiguousarray(np.asarray(D, dtype=np.float64).reshape(-1)) if D is not None else np.zeros(0)
+    # RR = P[:, :3] * R exactly as cvUndistortPointsInternal forms it (cvMatMul = cv::gemm)
+    rr = np.ascontiguousarray(cv2.gemm(np.ascontiguousarray(np.asarray(P, dtype=np.float64)[:3, :3]), np.ascontiguousarray(np.asarray(R, dtype=np.float64)), 1, None, 0))
+    mx = torch.empty((h, w), dtype=torch.float32, device=dev)
+    my = torch.empty((h, w), dtype=torch.float32, device=dev)
+    xy = torch.empty((h, w, 2), dtype=torch.int16, device=dev) if with_i16 else None
+    N.check(
+        N.lib.xm_build_inverse_lut(
+            dev.index, k.ctypes.data, d.ctypes.data if d.size else None, int(d.size), rr.ctypes.data, w, h,
+            mx.data_ptr(), my.data_ptr(), xy.data_ptr() if xy is not None else None, torch.cuda.current_stream(dev).cuda_stream,
+        )
+    )
+    return (mx, my, xy) if with_i16 else (mx, my)

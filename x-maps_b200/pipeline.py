@@ -54,7 +54,8 @@ class _NullStats:
 
 
 class DepthFramePipeline:
-    def __init__(self, params: RuntimeParams, stats_printer=None, frame_callback: Optional[Callable] = None, return_host: bool = True):
+    def __init__(self, params: RuntimeParams, stats_printer=None, frame_callback: Optional[Callable] = None, return_host: bool = True,
+                 activity_filter: bool = True):
         self.params = params
         self.stats_printer = stats_printer if stats_printer is not None else _NullStats()
         self.frame_callback = frame_callback
@@ -78,16 +79,24 @@ class DepthFramePipeline:
         # the rows either side of the path (depth_reprojection_pipe.py:97-105): per-frame de-duplication
         # filter (NoFilter until select_next_frame_event_filter) and the frame segmentation of the stream
         eng = self.calib_maps.engine()
+        # ActivityNoiseFilterAlgorithm(width, height, int(1e6 / projector_fps)) (depth_reprojection_pipe.py:65-67)
+        self.activity_filter = activity_filter
+        self.activity_threshold_us = int(1e6 / params.projector_fps)
+        eng.activity_reset()
         self.ev_filter_proc = FrameEventFilterProcessor(engine=eng)
         self.trigger_finder = RobustTriggerFinder(
             projector_fps=params.projector_fps, stats=self.stats_printer, pool=None, frame_callback=self.process_ev_frame, engine=eng,
         )
 
     def process_events(self, evs):
-        """A slice of the continuous stream (depth_reprojection_pipe.py:108-119): polarity filter, then
-        the trigger finder, which calls process_ev_frame once per projector frame it finds.  (The
-        Metavision activity-noise filter of :116-117 is a closed binary and is not applied.)"""
-        pos = self.calib_maps.engine().polarity_filter(evs)
+        """A slice of the continuous stream (depth_reprojection_pipe.py:108-119): polarity filter,
+        activity-noise filter (:116-117; the Metavision binary's semantics restated, see
+        ``DepthEngine.activity_filter``), then the trigger finder, which calls process_ev_frame once per
+        projector frame it finds."""
+        eng = self.calib_maps.engine()
+        pos = eng.polarity_filter(evs)
+        if self.activity_filter:
+            pos = eng.activity_filter(pos, self.activity_threshold_us)
         self.trigger_finder.process_events(pos)
 
     def select_next_frame_event_filter(self):
@@ -95,6 +104,7 @@ class DepthFramePipeline:
 
     def reset(self):
         self.trigger_finder.reset()
+        self.calib_maps.engine().activity_reset()
 
     def process_ev_frame(self, evs):
         """One frame of (already polarity-filtered) events -> colourised depth frame; the call
