@@ -85,7 +85,7 @@ struct CopyEventEmit {
 // site python/depth_reprojection_pipe.py:65-67,116-117).  Restated from its published semantics -- an event
 // passes iff one of the 8 neighbours of its pixel saw an event less than `threshold` us earlier (t_n > t -
 // threshold, per-pixel timestamps start at 0 and are carried across packets; the event's own pixel is not a
-// witness) -- see oracle/xmaps_oracle.py:activity_filter ("parity unpinned").
+// witness) -- the test oracle's ActivityNoiseFilterOracle restates the same ("parity unpinned").
 //
 // The definition is sequential (every event updates its pixel before the next event is looked at).  On a
 // time-sorted packet that spans less than `threshold` it is equivalent to an order-free test: neighbour n is a
