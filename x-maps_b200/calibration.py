@@ -229,13 +229,19 @@ class CamProjMaps:
         from .events import DeviceEvents
         from .lazy import FrameTicket, as_device_events
 
-        last = getattr(self, "_last_ticket", None)
-        if last is not None and last[0] is events:
-            return last[1]
-        dev = events if isinstance(events, DeviceEvents) else as_device_events(events)
-        ticket = FrameTicket(self.engine(dev.device), dev)
-        self._last_ticket = (events, ticket)
-        return ticket
+        # Only device buffers are remembered by identity: a host array (Metavision's pooled buffers, a preallocated
+        # frame array) may be refilled in place between two calls and must be uploaded again; between the stages of
+        # one frame the ticket travels on the lazy handles instead.
+        if isinstance(events, DeviceEvents):
+            last = getattr(self, "_last_ticket", None)
+            if last is not None and last[0] is events:
+                return last[1]
+            ticket = FrameTicket(self.engine(events.device), events)
+            self._last_ticket = (events, ticket)
+            return ticket
+        self._last_ticket = None
+        dev = as_device_events(events)
+        return FrameTicket(self.engine(dev.device), dev)
 
     def rectify_cam_coords_i16(self, events):
         """Reference :277-281.  Returns lazy device columns (x_rect, y_rect) bound to ``events``."""

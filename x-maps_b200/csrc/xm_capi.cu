@@ -204,14 +204,11 @@ unsigned next_epoch(XmCtx* c, unsigned count, cudaStream_t s, cudaError_t* err) 
 }
 
 using EvKernel = void (*)(xm::EventParams);
-EvKernel ev_kernel(bool f64, bool safe, int variant = 0, bool cam = false) {
+EvKernel ev_kernel(bool f64, bool safe, int variant = 1, bool cam = false) {
+    // 2: the lean integer-time kernel (verified tables); float64 timestamps and unverified tables take the general one
     if (variant == 2 && !f64 && safe) return cam ? xm::events_lean_kernel<true> : xm::events_lean_kernel<false>;
-    if (variant >= 1) {
-        if (f64) return safe ? xm::events_ws_kernel<true, true> : xm::events_ws_kernel<true, false>;
-        return safe ? xm::events_ws_kernel<false, true> : xm::events_ws_kernel<false, false>;
-    }
-    if (f64) return safe ? xm::events_kernel<true, true> : xm::events_kernel<true, false>;
-    return safe ? xm::events_kernel<false, true> : xm::events_kernel<false, false>;
+    if (f64) return safe ? xm::events_ws_kernel<true, true> : xm::events_ws_kernel<true, false>;
+    return safe ? xm::events_ws_kernel<false, true> : xm::events_ws_kernel<false, false>;
 }
 
 // Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may start
@@ -258,9 +255,8 @@ int configure_event_kernels(XmCtx* c) {
     c->cap_cols = cols;
     const int win_bytes = cols * c->col_stride * 2;
     const int variant = c->opt_k1_variant;
-    const int threads = variant >= 1 ? xm::kWsThreads : xm::kEvThreads;
-    c->ev_smem = variant >= 1 ? xm::events_ws_smem_bytes(c->opt_stages, c->opt_win_stages, win_bytes)
-                              : xm::events_smem_bytes(c->opt_stages, win_bytes);
+    const int threads = xm::kWsThreads;
+    c->ev_smem = xm::events_ws_smem_bytes(c->opt_stages, c->opt_win_stages, win_bytes);
     // the attribute is per function, not per context: always allow the device maximum so that
     // contexts with different X-map geometries can coexist in one process
     int optin = 0;
@@ -650,7 +646,7 @@ int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
         // when an event violates the assumed bounds the last CTA of K1 tail-launches the exact
         // two-pass fix-up from the device (no extra host launches in the common case)
         const EvKernel k1 = ev_kernel(f64, c->lut_safe && c->xmap_safe && c->opt_safe_tables, c->opt_k1_variant, a->view == XM_VIEW_CAMERA);
-        const int threads = c->opt_k1_variant >= 1 ? xm::kWsThreads : xm::kEvThreads;
+        const int threads = xm::kWsThreads;
         // programmatic dependent launch: K1's input-only prologue may overlap the previous frame's epilogue
         XM_CUDA(launch_pdl(k1, dim3(grid), dim3(threads), c->ev_smem, s, use_pdl && c->prev_was_frame, p));
         XM_LAUNCHED();
@@ -1162,7 +1158,7 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
     }
     if (!strcmp(key, "k1_variant")) {
-        if (v < 0 || v > 2) return fail(XM_ERR_INVALID_ARG, "k1_variant must be 0, 1 or 2");
+        if (v < 1 || v > 2) return fail(XM_ERR_INVALID_ARG, "k1_variant must be 1 or 2");
         c->opt_k1_variant = v;
         return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;
     }

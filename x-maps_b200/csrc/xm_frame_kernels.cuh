@@ -1,7 +1,7 @@
 // xm_frame_kernels.cuh — the per-frame hot path as sm_100a kernels.
 //
 //   K0  bounds_*        t.min() / t.max() of the polarity-masked events          (x_maps_disparity.py:12-13)
-//   K1  events_kernel   polarity mask -> rectify LUT -> time column -> X-map lookup -> disparity ->
+//   K1  events_*_kernel polarity mask -> rectify LUT -> time column -> X-map lookup -> disparity ->
 //                       last-write-wins scatter as a 64-bit atomicMax            (depth_reprojection_pipe.py:114,128,142,150-160)
 //   K2  epilogue_*      [7x7 dilate + nearest remap] -> depth / disparity / BGR  (disp_to_depth.py:46-115)
 //
@@ -326,284 +326,12 @@ __device__ __forceinline__ void front_half(const EventParams& p, const TimeCol<F
     cp_async_commit();
 }
 
-// BACK half.  SAFE: the tables were verified at upload so that every inlier's scatter target lies
-// inside the map (no wrap / bound checks).  FROM_SMEM: X-map columns come from the shared window
-// (kept a separate instantiation so that the hot path only ever waits on shared-memory loads).
-// The SAFE + FROM_SMEM variant is branch-free (predicated loads / atomics).
-template <bool SAFE, bool FROM_SMEM>
-__device__ __forceinline__ void back_half(const EventParams& p, const ChunkRegs& r, const int* s_lut, const short* s_cols, int win_lo,
-                                          int tid, unsigned idx_base, unsigned& n_inl, unsigned& flags) {
-    const unsigned y_lim = static_cast<unsigned>(p.xmap_h - 1);
-    if constexpr (SAFE && FROM_SMEM) {
-        int lut[kEvPerThread];
-#pragma unroll
-        for (int k = 0; k < kEvPerThread; ++k) lut[k] = s_lut[k * kEvThreads + tid];
-        int xp[kEvPerThread];
-        bool y_ok[kEvPerThread];
-#pragma unroll
-        for (int k = 0; k < kEvPerThread; ++k) {
-            const int ycr = lut[k] >> 16;
-            // x_maps_disparity.py:23: 0 <= y_rect < H - 1 (last row excluded)
-            y_ok[k] = r.col[k] >= 0 && static_cast<unsigned>(ycr) < y_lim;
-            const int off = y_ok[k] ? (r.col[k] - win_lo) * p.col_stride + ycr : 0;
-            xp[k] = s_cols[off];
-        }
-#pragma unroll
-        for (int k = 0; k < kEvPerThread; ++k) {
-            const int xcr = static_cast<short>(lut[k] & 0xffff);
-            const int ycr = lut[k] >> 16;
-            const int disp = static_cast<short>(xp[k] - xcr - p.x_offset);  // int16 arithmetic wraps
-            const bool inl = y_ok[k] && disp >= 0;
-            n_inl += inl ? 1u : 0u;
-            // x_rect + disp = x_map - x_offset, in [0, rect_w) for verified tables
-            const int cell = p.view == 1 ? r.pix[k] : ycr * p.rect_w + (xp[k] - p.x_offset);
-            if (inl) atomicMax(p.map + cell, make_key32(p.epoch, idx_base + static_cast<unsigned>(k * kEvThreads), disp));
-        }
-    } else {
-#pragma unroll
-    for (int k = 0; k < kEvPerThread; ++k) {
-        if (r.col[k] < 0) continue;
-        const int lut = s_lut[k * kEvThreads + tid];
-        const int xcr = static_cast<short>(lut & 0xffff);
-        const int ycr = lut >> 16;
-        if (static_cast<unsigned>(ycr) >= y_lim) continue;  // x_maps_disparity.py:23: 0 <= y_rect < H - 1
-        int xp;
-        if (FROM_SMEM)
-            xp = s_cols[(r.col[k] - win_lo) * p.col_stride + ycr];
-        else
-            xp = __ldg(p.xmap_t + static_cast<long long>(r.col[k]) * p.col_stride + ycr);
-        const int disp = static_cast<short>(xp - xcr - p.x_offset);  // int16 arithmetic wraps
-        if (disp < 0) continue;
-        ++n_inl;
-        int cell;
-        if (p.view == 1) {
-            cell = r.pix[k];
-        } else if (SAFE) {
-            cell = ycr * p.rect_w + (xp - p.x_offset);  // = x_rect + disp, in [0, rect_w)
-        } else {
-            int xpr = static_cast<short>(xcr + disp);
-            if (xpr < 0) xpr += p.rect_w;  // NumPy negative index wraps once
-            if (xpr < 0 || xpr >= p.rect_w || ycr >= p.rect_h) {
-                flags |= kStatusScatterOob;  // the reference raises IndexError here
-                continue;
-            }
-            cell = ycr * p.rect_w + xpr;
-        }
-        atomicMax(p.map + cell, make_key32(p.epoch, idx_base + static_cast<unsigned>(k * kEvThreads), disp));
-    }
-    }
-}
-
-template <bool F64, bool SAFE>
-__global__ void __launch_bounds__(kEvThreads, 3) events_kernel(const EventParams p) {
-    extern __shared__ __align__(128) unsigned char ev_smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(ev_smem);         // [kMaxStages]
-    uint64_t* winbar = reinterpret_cast<uint64_t*>(ev_smem + 64);  // X-map window copy
-    unsigned* s_range = reinterpret_cast<unsigned*>(ev_smem + 128);  // [2][8] per-warp column range words
-    int* s_lut = reinterpret_cast<int*>(ev_smem + kEvSmemHeader);  // [2][kEvChunk]
-    unsigned char* ring = ev_smem + kEvSmemHeader + kEvLutBytes;
-    short* s_cols = reinterpret_cast<short*>(ring + p.stages * (kEvChunk * 16));
-
-    FrameState* st = p.state;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-
-    // span of this CTA: equal shares, boundaries on multiples of 32 events (512 B)
-    const long long per = ((p.n + gridDim.x - 1) / gridDim.x + 31) & ~31LL;
-    const long long span_lo = per * blockIdx.x < p.n ? per * blockIdx.x : p.n;
-    const long long span_hi = span_lo + per < p.n ? span_lo + per : p.n;
-    const int span_len = static_cast<int>(span_hi - span_lo);
-    const int n_chunks = (span_len + kEvChunk - 1) / kEvChunk;
-    const int4* span_ptr = p.events + span_lo;
-    const uint64_t pol = make_evict_first_policy();
-    const unsigned pol_mask = p.polarity ? 0xffffu : 0u;
-
-    auto issue_chunk = [&](int c, int slot) {  // thread 0 only
-        const unsigned bytes = static_cast<unsigned>(min(kEvChunk, span_len - c * kEvChunk)) * 16u;
-        mbar_expect_tx(full + slot, bytes);
-        tma_load_1d_hint(ring + slot * (kEvChunk * 16), span_ptr + c * kEvChunk, bytes, full + slot, pol);
-    };
-
-    if (p.use_pdl) pdl_launch_dependents();  // the epilogue may start its (table-only) prologue right away
-    long long* s_bounds = reinterpret_cast<long long*>(ev_smem + 80);  // [2]
-    if (tid == 0) {
-        for (int s = 0; s < p.stages; ++s) mbar_init(full + s, 1);
-        mbar_init(winbar, 1);
-        const int pre = n_chunks < p.stages ? n_chunks : p.stages;
-        for (int c = 0; c < pre; ++c) issue_chunk(c, c);  // prologue: fill the ring (inputs only)
-    }
-    // t.min() / t.max() of a time-sorted frame are its first / last valid event; every CTA looks them
-    // up itself (two cached 512-byte reads) instead of waiting for a separate kernel
-    if (p.bounds_mode == 0) scan_sorted_bounds(p.events, p.n, p.polarity, warp, lane, s_bounds);
-    __syncthreads();
-    // everything above only reads inputs; below this line the kernel touches the state block and the
-    // scatter map, which the previous frame's epilogue may still be using
-    if (p.use_pdl) pdl_wait();
-
-    long long t_lo, t_hi;
-    if (p.bounds_mode == 0) {
-        t_lo = s_bounds[0];
-        t_hi = s_bounds[1];
-    } else if (p.bounds_mode == 1) {
-        t_lo = p.given_lo;
-        t_hi = p.given_hi;
-    } else {
-        t_lo = st->t_lo_bits;
-        t_hi = st->t_hi_bits;
-    }
-    if (p.bounds_mode != 2 && blockIdx.x == 0 && tid == 0) {  // for xm_frame_status
-        st->t_lo_bits = t_lo;
-        st->t_hi_bits = t_hi;
-    }
-    TimeCol<F64> tc;
-    tc.init(t_lo, t_hi, p.t_px_scale);
-
-    unsigned n_valid = 0, n_inl = 0, flags = 0;
-    int win_lo = 0, win_n = 0;
-    unsigned win_phase = 0;
-    bool win_pending = false;
-    int f_slot = 0;            // ring slot / parity of the next chunk the FRONT half will take
-    unsigned f_phase = 0;
-
-    // FRONT half of chunk c: fills `r`, starts the LUT gathers, publishes the warp's column range
-    auto front = [&](int c, ChunkRegs& r) {
-        mbar_wait(full + f_slot, f_phase);
-        const int4* stage = reinterpret_cast<const int4*>(ring + f_slot * (kEvChunk * 16));
-        int* lut_dst = s_lut + (c & 1) * kEvChunk;
-        const int limit = span_len - c * kEvChunk;
-        ColRange range{0xffffffffu, -1};
-        if (limit >= kEvChunk) {
-            if (tc.fast)
-                front_half<F64, true, true>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, range, n_valid, flags);
-            else
-                front_half<F64, true, false>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, range, n_valid, flags);
-        } else {
-            if (tc.fast)
-                front_half<F64, false, true>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, range, n_valid, flags);
-            else
-                front_half<F64, false, false>(p, tc, stage, lut_dst, tid, limit, pol_mask, r, range, n_valid, flags);
-        }
-        const unsigned lo = __reduce_min_sync(0xffffffffu, range.lo);
-        const int hi = __reduce_max_sync(0xffffffffu, range.hi);
-        // one word per warp: (max << 16) | min; 0xffffffff = no valid event (columns are < 2^15)
-        if (lane == 0) s_range[(c & 1) * 8 + warp] = hi < 0 ? 0xffffffffu : ((static_cast<unsigned>(hi) << 16) | lo);
-    };
-
-    // after the block barrier that follows front(c): recycle the stage, decide how chunk c reads the X-map
-    // returns: 0 = chunk has no valid event, 1 = shared-memory window, 2 = through L2
-    auto after_barrier = [&](int c) -> int {
-        if (tid == 0 && c + p.stages < n_chunks) issue_chunk(c + p.stages, f_slot);
-        if (++f_slot == p.stages) {
-            f_slot = 0;
-            f_phase ^= 1u;
-        }
-        const unsigned w = s_range[(c & 1) * 8 + (lane & 7)];
-        const int cmin = static_cast<int>(__reduce_min_sync(0xffffffffu, w & 0xffffu));
-        const int cmax = __reduce_max_sync(0xffffffffu, w == 0xffffffffu ? -1 : static_cast<int>(w >> 16));
-        if (cmax < 0) return 0;
-        const int need = cmax - cmin + 1;
-        if (need > p.cap_cols) return 2;
-        if (cmin < win_lo || cmax >= win_lo + win_n) {
-            win_lo = cmin;
-            win_n = min(min(need + p.lookahead, p.cap_cols), p.xmap_w - cmin);
-            if (tid == 0) {
-                const unsigned bytes = static_cast<unsigned>(win_n) * p.col_stride * 2u;
-                mbar_expect_tx(winbar, bytes);
-                tma_load_1d(s_cols, p.xmap_t + static_cast<long long>(win_lo) * p.col_stride, bytes, winbar);
-            }
-            win_pending = true;
-        }
-        return 1;
-    };
-
-    ChunkRegs cur;
-    int mode = 0;
-    if (n_chunks > 0) {  // (uniform) a trailing CTA may own an empty span
-        front(0, cur);
-        __syncthreads();
-        mode = after_barrier(0);
-    }
-
-    for (int c = 0; c < n_chunks; ++c) {
-        ChunkRegs nxt;
-        const bool has_next = c + 1 < n_chunks;
-        if (has_next) {
-            front(c + 1, nxt);
-            cp_async_wait<1>();  // the gathers of chunk c have landed; those of chunk c+1 stay in flight
-        } else {
-            cp_async_wait<0>();
-        }
-        if (mode != 0) {
-            const unsigned idx_base = static_cast<unsigned>(span_lo) + static_cast<unsigned>(c * kEvChunk + tid);
-            const int* lut_src = s_lut + (c & 1) * kEvChunk;
-            if (mode == 1) {
-                if (win_pending) {  // the window copy was issued one chunk ago
-                    mbar_wait(winbar, win_phase);
-                    win_phase ^= 1u;
-                    win_pending = false;
-                }
-                back_half<SAFE, true>(p, cur, lut_src, s_cols, win_lo, tid, idx_base, n_inl, flags);
-            } else {
-                back_half<SAFE, false>(p, cur, lut_src, s_cols, win_lo, tid, idx_base, n_inl, flags);
-            }
-        }
-        if (!has_next) break;
-        __syncthreads();  // every thread has taken its events of chunk c+1 out of the ring and is done
-                          // with the X-map window of chunk c
-        mode = after_barrier(c + 1);
-#pragma unroll
-        for (int k = 0; k < kEvPerThread; ++k) {
-            cur.col[k] = nxt.col[k];
-            cur.pix[k] = nxt.pix[k];
-        }
-    }
-
-    // per-CTA statistics -> one atomic per warp
-    n_valid = __reduce_add_sync(0xffffffffu, n_valid);
-    n_inl = __reduce_add_sync(0xffffffffu, n_inl);
-    flags = __reduce_or_sync(0xffffffffu, flags);
-    if (lane == 0) {
-        if (n_valid) atomicAdd(&st->n_valid, static_cast<unsigned long long>(n_valid));
-        if (n_inl) atomicAdd(&st->n_inliers, static_cast<unsigned long long>(n_inl));
-        if (flags) atomicOr(&st->flags, flags);
-    }
-    if (p.arm_fixup) {
-        // last CTA: if any event violated the assumed bounds, arm the fix-up pass
-        __shared__ unsigned s_last;
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            s_last = (atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1);
-        }
-        __syncthreads();
-        if (s_last && tid == 0) {
-            __threadfence();
-            unsigned f = *reinterpret_cast<volatile unsigned*>(&st->flags);
-            st->blocks_done = 0;
-            if (f & kStatusTBounds) {
-                st->redo = 1;
-                st->flags = f & ~(kStatusPixelOob | kStatusScatterOob);
-                // Exact fix-up, launched from the device into the tail-launch stream (CUDA dynamic
-                // parallelism): both grids run, in this order, after this grid has drained and before
-                // the next kernel of the host stream (the epilogue) starts.  Costs nothing when the
-                // optimistic bounds hold.
-                bounds_reduce_kernel<F64><<<p.fix_reduce_grid, 256, 0, cudaStreamTailLaunch>>>(p.events, p.n, p.polarity, st);
-                EventParams q = p;
-                q.epoch = p.epoch + 1;
-                q.arm_fixup = 0;
-                q.use_pdl = 0;
-                q.bounds_mode = 2;
-                events_kernel<F64, SAFE><<<gridDim.x, kEvThreads, p.smem_bytes, cudaStreamTailLaunch>>>(q);
-            }
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
-// K1, warp-specialised variant (default).
+// K1, warp-specialised general variant (k1_variant = 1; the lean integer-time kernel below is the default).
 //
-// Same work per event as events_kernel, but without any CTA-wide barrier in the steady state:
+// The general per-event kernel (float64 or integer timestamps, verified or unverified tables), without any CTA-wide
+// barrier in the steady state:
 //   * warp 8 is the PRODUCER: one lane streams the CTA's span through a ring of event stages
 //     (TMA bulk copies, `full_ev` / `empty_ev` mbarriers) and, for every chunk, stages the X-map time
 //     columns between the columns of the chunk's first and last event into a ring of window buffers

@@ -37,7 +37,13 @@ EVENT_DTYPE_F64 = np.dtype(
 
 
 def pack_events(x, y, t, p=None) -> np.ndarray:
-    """Build a host EventCD array from columns.  A floating ``t`` yields the float64-time record."""
+    """Build a host EventCD array from columns.  A floating ``t`` yields the float64-time record.
+
+    Note on float32 timestamps: the reference's ``compute_disparity`` normalises time in ``t``'s own dtype
+    (x_maps_disparity.py:12-19), so a float32 ``t`` is subtracted / divided / scaled in float32 there; this record
+    stores float64 and the kernels normalise in float64 (bit-identical to the reference for int64 and float64
+    timestamps).  For float32 input the rounded time column can differ by one in rare ties; convert such data to
+    int64 microseconds (what the camera delivers) or float64 before comparing bit for bit."""
     t = np.asarray(t)
     n = len(t)
     dtype = EVENT_DTYPE_F64 if np.issubdtype(t.dtype, np.floating) else EVENT_DTYPE
