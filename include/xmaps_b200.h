@@ -64,6 +64,11 @@ enum {
 /* XmFrameArgs.flags */
 #define XM_FLAG_POLARITY 0x1u /* keep only p == 1 (PolarityFilterAlgorithm(1), ...pipe.py:43,114)  */
 #define XM_FLAG_TIME_F64 0x2u /* the 8-byte time field holds a float64                              */
+/* xm_frame only, opt-in, NOT reference behaviour (the reference's lookup is nearest, x_maps_disparity.py:19,25):
+ * bilinear X-map lookup at the un-rounded (y_rect, time column) of the float32 rectification LUT (needs
+ * XmTables.lut_x_f32 / lut_y_f32); undefined (0) cells are left out of the blend; float32 disparities, last event
+ * per cell wins; 7x7 dilate / remap / depth as usual on the float map.  Staged kernels, no batch path.  */
+#define XM_FLAG_BILINEAR 0x4u
 
 /* XmFrameStatus.flags (device-side findings of the last frame) */
 #define XM_STATUS_TBOUNDS_VIOLATED 0x1u /* an event lies outside the assumed [t_min, t_max]          */

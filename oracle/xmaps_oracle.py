@@ -261,6 +261,65 @@ def frame_depth(tables: OracleTables, events, view: int, apply_polarity: bool = 
 # --------------------------------------------------------------------------------------
 # N1  colourise (tail of process_ev_frame)
 # --------------------------------------------------------------------------------------
+def frame_disparity_map_bilinear(tables: OracleTables, lut_x_f32: np.ndarray, lut_y_f32: np.ndarray, events, view: int,
+                                 apply_polarity: bool = True, use_cv2: bool = True):
+    """Opt-in extension (BASELINE config 3, "bilinear X-map lookup"), NOT reference behaviour: the reference rounds the
+    rectified row and the time column and reads ONE X-map cell (python/x_maps_disparity.py:19,25).  Here the X-map is
+    sampled bilinearly at the un-rounded position:
+
+      (x_r, y_r) = float32 LUT (rectify_cam_coords_f32, cam_proj_calibration.py:272-275);  c = (t - min) / (max - min) * T
+      taps X[y0 + i, c0 + j] (y0 = floor(y_r), c0 = floor(c), c0 + 1 clipped to the last column), rows restricted to
+      0 <= y0, y0 + 1 <= H - 1 like the reference's `0 <= y < H - 1`; cells equal to 0 are undefined (x_map.py) and
+      are left out of the blend, the remaining weights renormalised; disparity = float32(x_p - x_r - X_OFFSET) >= 0;
+      last event per cell wins; cell = (rint(y_r), rint(x_p - X_OFFSET)) (projector view) or the camera pixel.
+
+    float64 throughout, in the same operation order as the CUDA kernel (bilinear_scatter_kernel).  Returns the float32
+    disparity map of the view (projector view: after the 7x7 dilate + nearest remap)."""
+    ev = polarity_mask(events) if apply_polarity else events
+    h_rows, w_cols = tables.x_map.shape
+    if len(ev) == 0:
+        rect = np.zeros((tables.rect_h, tables.rect_w) if view == 0 else (tables.cam_h, tables.cam_w), dtype=np.float32)
+        return dilate_remap(tables, rect, use_cv2) if view == 0 else rect
+    x, y = ev["x"].astype(np.int64), ev["y"].astype(np.int64)
+    t = ev["t"]
+    xr = lut_x_f32[y, x].astype(np.float64)
+    yr = lut_y_f32[y, x].astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        c = (t - t.min()) / (t.max() - t.min()) * tables.t_px_scale  # x_maps_disparity.py:12-19 without the rint
+    c = np.where(np.isnan(c), 0.0, c)
+    c0, y0 = np.floor(c), np.floor(yr)
+    ok = (y0 >= 0) & (y0 + 1 <= h_rows - 1) & (c0 >= 0) & (c0 <= tables.t_px_scale)
+    fc, fy = c - c0, yr - y0
+    ic0 = np.where(ok, c0, 0).astype(np.int64)
+    iy0 = np.where(ok, y0, 0).astype(np.int64)
+    ic1 = np.minimum(ic0 + 1, w_cols - 1)
+    xm = tables.x_map.astype(np.float64)
+    v = [xm[iy0, ic0], xm[iy0, ic1], xm[iy0 + 1, ic0], xm[iy0 + 1, ic1]]
+    gy, gc = 1.0 - fy, 1.0 - fc
+    w = [gy * gc, gy * fc, fy * gc, fy * fc]
+    num = np.zeros(len(ev))
+    den = np.zeros(len(ev))
+    for vi, wi in zip(v, w):
+        m = vi != 0
+        num = num + np.where(m, wi * vi, 0.0)
+        den = den + np.where(m, wi, 0.0)
+    good = ok & (den > 0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        xp = num / den
+    disp = ((xp - xr) - tables.x_offset).astype(np.float32)
+    inl = good & (disp >= 0)
+    if view == 1:
+        out = np.zeros((tables.cam_h, tables.cam_w), dtype=np.float32)
+        out[y[inl], x[inl]] = disp[inl]  # NumPy keeps the last duplicate
+        return out
+    rows = np.rint(yr)
+    cols = np.rint(xp - tables.x_offset)
+    inside = inl & (rows >= 0) & (rows < tables.rect_h) & (cols >= 0) & (cols < tables.rect_w)
+    rect = np.zeros((tables.rect_h, tables.rect_w), dtype=np.float32)
+    rect[rows[inside].astype(np.int64), cols[inside].astype(np.int64)] = disp[inside]
+    return dilate_remap(tables, rect, use_cv2)
+
+
 def clip_normalize_u8(depth: np.ndarray, z_near: float, z_far: float) -> np.ndarray:
     """python/disp_to_depth.py:7-21.  Numba types ``(val - min) / range`` in float32 and the
     following ``* 255`` (an int64 literal) in float64; the result is truncated to uint8."""

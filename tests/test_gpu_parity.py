@@ -388,6 +388,41 @@ def test_x_map_builder(small):
     assert np.array_equal(t_diffs.cpu().numpy(), want_diffs)
 
 
+def test_bilinear_lookup_matches_its_oracle(small):
+    """XM_FLAG_BILINEAR (opt-in, not reference behaviour): bilinear X-map lookup at the un-rounded rectified row / time
+    column, undefined cells left out of the blend.  The kernel evaluates the oracle's float64 expression operation by
+    operation, so the float32 maps are compared exactly; the stated tolerance of the feature is rtol = 1e-6."""
+    tables, z, eng = small
+    e = E()
+    lx, ly = z["lut_x_f32"], z["lut_y_f32"]
+    ev = orc.synth_events(41, 400_000, tables.cam_w, tables.cam_h)
+    for view in (0, 1):
+        want = orc.frame_disparity_map_bilinear(tables, lx, ly, ev, view)
+        got = eng.frame(ev, view=view, output=e.OUT_DISPARITY, time_bounds=e.TBOUNDS_REDUCE, bilinear=True).cpu().numpy()
+        assert (want > 0).sum() > 1000
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=0)
+        assert np.array_equal(got, want), f"view {view}: {np.count_nonzero(got != want)} pixels differ in the last bit"
+        depth = eng.frame(ev, view=view, output=e.OUT_DEPTH, bilinear=True).cpu().numpy()
+        assert np.array_equal(depth, orc.disparity_to_depth(want, tables.depth_scale))
+        st = eng.status()
+        assert st["n_valid"] == int((ev["p"] == 1).sum()) and not st["tbounds_violated"]
+    # it is a different estimator from the nearest lookup (sub-pixel disparities), yet close to it
+    near = orc.frame_disparity_map(tables, ev, 0)
+    bil = orc.frame_disparity_map_bilinear(tables, lx, ly, ev, 0)
+    both = (near > 0) & (bil > 0)
+    assert both.sum() > 1000 and np.any(bil[both] != np.rint(bil[both])) and np.median(np.abs(near[both] - bil[both])) < 2.0
+    # float64 timestamps, no polarity mask, empty frame
+    from xmaps_b200.events import pack_events
+
+    evf = pack_events(ev["x"], ev["y"], ev["t"].astype(np.float64) * 1e-6, ev["p"])
+    want = orc.frame_disparity_map_bilinear(tables, lx, ly, evf, 0, apply_polarity=False)
+    got = eng.frame(evf, view=0, output=e.OUT_DISPARITY, polarity=False, time_bounds=e.TBOUNDS_REDUCE, bilinear=True).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert not eng.frame(ev[:0], view=0, output=e.OUT_DISPARITY, bilinear=True).cpu().numpy().any()
+    # the nearest path is untouched by a bilinear frame before it
+    assert np.array_equal(eng.frame(ev, view=0).cpu().numpy(), orc.frame_depth(tables, ev, 0))
+
+
 def test_inverse_lut_builder_matches_reference_tables(manifest):
     """xm_build_inverse_lut = initUndistortRectifyMapInverse (cam_proj_calibration.py:31-41) on the device: the float32
     maps and the int16 tables of the default and the HD geometry carry the hashes of the REAL reference's tables, and

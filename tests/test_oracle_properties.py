@@ -68,3 +68,20 @@ def test_trigger_decision_is_invariant(seed):
     status, prev_idx, next_idx, _ = base
     if status == 1:
         assert orc.find_trigger(stream["t"][: next_idx + 2], 60)[:3] == (1, prev_idx, next_idx)
+
+
+def test_bilinear_lookup_reduces_to_nearest_on_integral_positions(tables_default):
+    """The opt-in bilinear X-map lookup (not reference behaviour) agrees with the reference's nearest lookup when
+    every event sits on integral rectified coordinates and integral time columns (up to the last-ulp cases where the
+    float64 column lands just below an integer next to an undefined cell)."""
+    tables = tables_default
+    ev = orc.synth_events(31, 200_000, tables.cam_w, tables.cam_h)
+    span = tables.t_px_scale * 16
+    rng = np.random.default_rng(2)
+    ev["t"] = np.sort(rng.integers(0, tables.t_px_scale + 1, len(ev))) * 16 + 1000
+    ev["t"][0], ev["t"][-1] = 1000, 1000 + span
+    near = orc.frame_disparity_map(tables, ev, 0)
+    bil = orc.frame_disparity_map_bilinear(tables, tables.lut_x.astype(np.float32), tables.lut_y.astype(np.float32), ev, 0)
+    assert near.shape == bil.shape
+    differ = np.abs(near - bil) > 1e-3
+    assert differ.mean() < 2e-3, differ.mean()

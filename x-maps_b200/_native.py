@@ -19,7 +19,7 @@ OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_XMAP, ERR_TABLE_RANGE, ERR_UNSUPPORTED = r
 VIEW_PROJECTOR, VIEW_CAMERA = 0, 1
 OUT_DEPTH, OUT_DISPARITY, OUT_BGR = 0, 1, 2
 TBOUNDS_REDUCE, TBOUNDS_SORTED, TBOUNDS_GIVEN = 0, 1, 2
-FLAG_POLARITY, FLAG_TIME_F64 = 0x1, 0x2
+FLAG_POLARITY, FLAG_TIME_F64, FLAG_BILINEAR = 0x1, 0x2, 0x4
 STATUS_TBOUNDS_VIOLATED, STATUS_PIXEL_OOB, STATUS_SCATTER_OOB = 0x1, 0x2, 0x4
 STATUS_FILTER_POLARITY, STATUS_FILTER_INDEX = 0x8, 0x10
 FILTER_FIRST_YT, FILTER_FIRST_XY, FILTER_LAST_XY, FILTER_MEAN_XY = 1, 2, 3, 4

@@ -82,6 +82,9 @@ struct XmCtx {
     int lut_x_min = 0;                  // smallest rectified x of the LUT (lut_safe = lut_x_min > -x_offset)
     float* d_lut_x_f32 = nullptr;
     float* d_lut_y_f32 = nullptr;
+    unsigned long long* d_bil_map = nullptr;  // XM_FLAG_BILINEAR: key map (kept cleared between frames), float rect / out maps
+    float* d_bil_rect = nullptr;
+    float* d_bil_out = nullptr;
     short* d_xmap_t = nullptr;
     short2* d_remap_xy = nullptr;
     short4* d_tile_box = nullptr;  // bounding box of the remap targets of every 32x32 output tile
@@ -479,7 +482,8 @@ int check_frame_args(const XmCtx* c, const XmFrameArgs* a) {
     if (a->view != XM_VIEW_PROJECTOR && a->view != XM_VIEW_CAMERA) return fail(XM_ERR_INVALID_ARG, "unknown view %d", a->view);
     if (a->time_bounds < XM_TBOUNDS_REDUCE || a->time_bounds > XM_TBOUNDS_GIVEN) return fail(XM_ERR_INVALID_ARG, "unknown time_bounds %d", a->time_bounds);
     if (a->output < XM_OUT_DEPTH || a->output > XM_OUT_BGR) return fail(XM_ERR_INVALID_ARG, "unknown output %d", a->output);
-    if (a->flags & ~(XM_FLAG_POLARITY | XM_FLAG_TIME_F64)) return fail(XM_ERR_INVALID_ARG, "unknown flags 0x%x", a->flags);
+    if (a->flags & ~(XM_FLAG_POLARITY | XM_FLAG_TIME_F64 | XM_FLAG_BILINEAR)) return fail(XM_ERR_INVALID_ARG, "unknown flags 0x%x", a->flags);
+    if ((a->flags & XM_FLAG_BILINEAR) && !c->d_lut_x_f32) return fail(XM_ERR_INVALID_ARG, "XM_FLAG_BILINEAR needs XmTables.lut_x_f32 / lut_y_f32");
     if (!c->d_xmap_t) return fail(XM_ERR_NO_XMAP, "no X-map: supply XmTables.x_map or call xm_ctx_set_xmap");
     if (a->view == XM_VIEW_PROJECTOR && !c->d_remap_xy) return fail(XM_ERR_INVALID_ARG, "projector view needs XmTables.remap_xy");
     if (a->output == XM_OUT_BGR && !c->have_turbo) return fail(XM_ERR_INVALID_ARG, "XM_OUT_BGR needs a colour map (xm_ctx_set_colormap)");
@@ -519,8 +523,69 @@ int profile_mark(XmCtx* c, cudaStream_t s) {
     return XM_OK;
 }
 
+// XM_FLAG_BILINEAR: bounds, bilinear scatter of float disparities, decode, [dilate + remap], convert
+int bilinear_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
+    const bool cam = a->view == XM_VIEW_CAMERA;
+    const long long cells = c->map_cells;
+    const long long out_px = cam ? static_cast<long long>(c->cam_w) * c->cam_h : static_cast<long long>(c->proj_w) * c->proj_h;
+    if (!c->d_bil_map) {
+        XM_CUDA(cudaMalloc(&c->d_bil_map, static_cast<size_t>(cells) * 8));
+        XM_CUDA(cudaMemset(c->d_bil_map, 0, static_cast<size_t>(cells) * 8));
+        XM_CUDA(cudaMalloc(&c->d_bil_rect, static_cast<size_t>(cells) * 4));
+        const long long mx = std::max(static_cast<long long>(c->cam_w) * c->cam_h, static_cast<long long>(c->proj_w) * c->proj_h);
+        XM_CUDA(cudaMalloc(&c->d_bil_out, static_cast<size_t>(mx > 0 ? mx : 1) * 4));
+    }
+    xm::FrameState* st;
+    int rc = staged_state(c, s, true, &st);
+    if (rc) return rc;
+    rc = launch_bounds(c, st, a->d_events, a->n_events, a->flags, a->time_bounds, a->t_min, a->t_max, c->epoch, s);
+    if (rc) return rc;
+    if (a->n_events > 0) {
+        xm::BilinearParams p;
+        p.events = static_cast<const int4*>(a->d_events);
+        p.n = a->n_events;
+        p.polarity = (a->flags & XM_FLAG_POLARITY) ? 1 : 0;
+        p.lut_x = c->d_lut_x_f32;
+        p.lut_y = c->d_lut_y_f32;
+        p.cam_w = c->cam_w;
+        p.cam_h = c->cam_h;
+        p.xmap_t = c->d_xmap_t;
+        p.xmap_w = c->xmap_w;
+        p.xmap_h = c->xmap_h;
+        p.col_stride = c->col_stride;
+        p.t_px_scale = c->t_px_scale;
+        p.x_offset = c->x_offset;
+        p.rect_w = c->rect_w;
+        p.rect_h = c->rect_h;
+        p.view = cam ? 1 : 0;
+        p.map = c->d_bil_map;
+        p.state = st;
+        p.verify = a->time_bounds != XM_TBOUNDS_REDUCE;
+        const int grid = grid_for(a->n_events, 256, 4, c->sm_count * 8);
+        if (a->flags & XM_FLAG_TIME_F64)
+            xm::bilinear_scatter_kernel<true><<<grid, 256, 0, s>>>(p);
+        else
+            xm::bilinear_scatter_kernel<false><<<grid, 256, 0, s>>>(p);
+        XM_LAUNCHED();
+    }
+    const long long src_cells = cam ? static_cast<long long>(c->cam_w) * c->cam_h : static_cast<long long>(c->rect_w) * c->rect_h;
+    float* disp_map = cam ? c->d_bil_out : c->d_bil_rect;
+    xm::bilinear_decode_kernel<<<grid_for(src_cells, 256, 4, c->sm_count * 8), 256, 0, s>>>(c->d_bil_map, src_cells, disp_map);
+    XM_LAUNCHED();
+    if (!cam) {
+        xm::dilate_remap_kernel<<<grid_for(out_px, 256, 1, c->sm_count * 16), 256, 0, s>>>(c->d_bil_rect, c->rect_w, c->rect_h, c->d_remap_xy, c->proj_w,
+                                                                                           c->proj_h, c->dilate / 2, c->d_bil_out);
+        XM_LAUNCHED();
+    }
+    const xm::OutputSpec o = make_output(c, a->output, c->depth_scale, a->z_near, a->z_far);
+    xm::convert_kernel<<<grid_for(out_px, 256, 4, c->sm_count * 8), 256, 0, s>>>(c->d_bil_out, out_px, o, a->d_out);
+    XM_LAUNCHED();
+    return XM_OK;
+}
+
 int frame_impl(XmCtx* c, const XmFrameArgs* a, cudaStream_t s) {
     if (!a->d_out) return fail(XM_ERR_INVALID_ARG, "d_out is NULL");
+    if (a->flags & XM_FLAG_BILINEAR) return bilinear_impl(c, a, s);
     const bool f64 = (a->flags & XM_FLAG_TIME_F64) != 0;
     const bool assumed = a->time_bounds != XM_TBOUNDS_REDUCE;
     const bool fixup = assumed && c->opt_auto_fixup;
@@ -715,7 +780,7 @@ bool batch_applies(const XmCtx* c, const XmFrameArgs* a, int n) {
     for (int i = 0; i < n; ++i) {
         if (a[i].view != a[0].view || a[i].output != a[0].output || a[i].flags != a[0].flags) return false;
         if (a[i].z_near != a[0].z_near || a[i].z_far != a[0].z_far) return false;
-        if ((a[i].flags & XM_FLAG_TIME_F64) || a[i].time_bounds == XM_TBOUNDS_REDUCE || !a[i].d_out) return false;
+        if ((a[i].flags & (XM_FLAG_TIME_F64 | XM_FLAG_BILINEAR)) || a[i].time_bounds == XM_TBOUNDS_REDUCE || !a[i].d_out) return false;
     }
     return true;
 }
@@ -1079,6 +1144,9 @@ int xm_ctx_destroy(XmCtx* c) {
     cudaFree(c->d_alive);
     cudaFree(c->d_alive_ones);
     cudaFree(c->d_lut_x_f32);
+    cudaFree(c->d_bil_map);
+    cudaFree(c->d_bil_rect);
+    cudaFree(c->d_bil_out);
     cudaFree(c->d_lut_y_f32);
     cudaFree(c->d_xmap_t);
     cudaFree(c->d_remap_xy);

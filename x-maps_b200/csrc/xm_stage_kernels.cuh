@@ -348,6 +348,108 @@ __global__ void __launch_bounds__(256) build_xmap_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// XM_FLAG_BILINEAR: bilinear X-map lookup (BASELINE config 3; NOT in the reference, whose lookup is nearest:
+// x_maps_disparity.py:19,25 round both coordinates).  Defined here and restated by the oracle's
+// frame_disparity_map_bilinear, float64 operation by operation:
+//   (x_r, y_r) = float32 rectification LUT (rectify_cam_coords_f32, cam_proj_calibration.py:272-275)
+//   c   = (t - t_min) / (t_max - t_min) * T_PX_SCALE            un-rounded (0 / 0 -> 0)
+//   c0 = floor(c), fc = c - c0, y0 = floor(y_r), fy = y_r - y0;  needs 0 <= y0, y0 + 1 <= H - 1, 0 <= c0 <= T_PX_SCALE
+//   taps X[y0, c0], X[y0, c1], X[y0 + 1, c0], X[y0 + 1, c1], c1 = min(c0 + 1, W - 1), weights (1 - fy)(1 - fc) ...;
+//   taps equal to 0 are undefined cells (x_map.py:5-55) and are left out, the remaining weights renormalised
+//   x_p = sum(w v) / sum(w);  disparity = float32((x_p - x_r) - X_OFFSET), inlier iff >= 0
+//   scatter cell: projector view (rint(y_r), rint(x_p - X_OFFSET)), camera view (y, x); last event wins; the map holds
+//   the float32 disparity.  Key = (event index + 1) << 32 | float bits, kept with atomicMax in a cleared map.
+// ---------------------------------------------------------------------------------------------
+struct BilinearParams {
+    const int4* events;
+    long long n;
+    int polarity;
+    const float* lut_x;
+    const float* lut_y;
+    int cam_w, cam_h;
+    const short* xmap_t;
+    int xmap_w, xmap_h, col_stride;
+    int t_px_scale, x_offset;
+    int rect_w, rect_h;
+    int view;  // 0 projector, 1 camera
+    unsigned long long* map;
+    FrameState* state;
+    int verify;
+};
+
+template <bool F64>
+__global__ void __launch_bounds__(256) bilinear_scatter_kernel(const BilinearParams p) {
+    TimeNorm<F64> tn;
+    tn.init(p.state->t_lo_bits, p.state->t_hi_bits, p.t_px_scale);
+    unsigned n_valid = 0, n_inl = 0, flags = 0;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const EventFields e = unpack_event(ld_event_plain(p.events + i));
+        if (!event_valid(e, p.polarity)) continue;
+        ++n_valid;
+        if (e.x >= static_cast<unsigned>(p.cam_w) || e.y >= static_cast<unsigned>(p.cam_h)) {
+            flags |= kStatusPixelOob;
+            continue;
+        }
+        if (p.verify && tn.outside(e.t_bits)) flags |= kStatusTBounds;
+        const int pix = static_cast<int>(e.y) * p.cam_w + static_cast<int>(e.x);
+        const double xr = static_cast<double>(__ldg(p.lut_x + pix)), yr = static_cast<double>(__ldg(p.lut_y + pix));
+        const double num_t = F64 ? __dsub_rn(__longlong_as_double(e.t_bits), tn.lo_f) : static_cast<double>(e.t_bits - tn.lo_i);
+        double c = __dmul_rn(__ddiv_rn(num_t, tn.den), tn.scale);
+        if (!(c == c)) c = 0.0;
+        const double c0 = floor(c), y0 = floor(yr);
+        if (!(y0 >= 0.0 && y0 + 1.0 <= static_cast<double>(p.xmap_h - 1) && c0 >= 0.0 && c0 <= static_cast<double>(p.t_px_scale))) continue;
+        const double fc = __dsub_rn(c, c0), fy = __dsub_rn(yr, y0);
+        const int ic0 = static_cast<int>(c0), iy0 = static_cast<int>(y0);
+        const int ic1 = min(ic0 + 1, p.xmap_w - 1);
+        const int v00 = __ldg(p.xmap_t + static_cast<long long>(ic0) * p.col_stride + iy0);
+        const int v01 = __ldg(p.xmap_t + static_cast<long long>(ic1) * p.col_stride + iy0);
+        const int v10 = __ldg(p.xmap_t + static_cast<long long>(ic0) * p.col_stride + iy0 + 1);
+        const int v11 = __ldg(p.xmap_t + static_cast<long long>(ic1) * p.col_stride + iy0 + 1);
+        const double gy = __dsub_rn(1.0, fy), gc = __dsub_rn(1.0, fc);
+        const double w00 = __dmul_rn(gy, gc), w01 = __dmul_rn(gy, fc), w10 = __dmul_rn(fy, gc), w11 = __dmul_rn(fy, fc);
+        double num = 0.0, den = 0.0;
+        if (v00) { num = __dadd_rn(num, __dmul_rn(w00, static_cast<double>(v00))); den = __dadd_rn(den, w00); }
+        if (v01) { num = __dadd_rn(num, __dmul_rn(w01, static_cast<double>(v01))); den = __dadd_rn(den, w01); }
+        if (v10) { num = __dadd_rn(num, __dmul_rn(w10, static_cast<double>(v10))); den = __dadd_rn(den, w10); }
+        if (v11) { num = __dadd_rn(num, __dmul_rn(w11, static_cast<double>(v11))); den = __dadd_rn(den, w11); }
+        if (!(den > 0.0)) continue;
+        const double xp = __ddiv_rn(num, den);
+        const float disp = __double2float_rn(__dsub_rn(__dsub_rn(xp, xr), static_cast<double>(p.x_offset)));
+        if (!(disp >= 0.0f)) continue;
+        long long cell;
+        if (p.view == 1) {
+            cell = pix;
+        } else {
+            const double row = rint(yr), col = rint(__dsub_rn(xp, static_cast<double>(p.x_offset)));
+            if (!(row >= 0.0 && row < static_cast<double>(p.rect_h) && col >= 0.0 && col < static_cast<double>(p.rect_w))) {
+                flags |= kStatusScatterOob;
+                continue;
+            }
+            cell = static_cast<long long>(row) * p.rect_w + static_cast<long long>(col);
+        }
+        ++n_inl;
+        atomicMax(p.map + cell, (static_cast<unsigned long long>(i + 1) << 32) | static_cast<unsigned>(__float_as_int(disp)));
+    }
+    n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+    n_inl = __reduce_add_sync(0xffffffffu, n_inl);
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if ((threadIdx.x & 31) == 0) {
+        if (n_valid) atomicAdd(&p.state->n_valid, static_cast<unsigned long long>(n_valid));
+        if (n_inl) atomicAdd(&p.state->n_inliers, static_cast<unsigned long long>(n_inl));
+        if (flags) atomicOr(&p.state->flags, flags);
+    }
+}
+
+// float32 disparity map out of the bilinear keys; clears the map for the next frame on the way
+__global__ void __launch_bounds__(256) bilinear_decode_kernel(unsigned long long* __restrict__ map, long long n, float* __restrict__ out) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const unsigned long long k = map[i];
+        out[i] = k ? __int_as_float(static_cast<int>(k & 0xffffffffULL)) : 0.f;
+        if (k) map[i] = 0ULL;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // N3 (second half): initUndistortRectifyMapInverse (python/cam_proj_calibration.py:31-41, used at :246-270)
 // = cv2.undistortPoints over the whole pixel grid.  OpenCV's point loop (cvUndistortPointsInternal, default
 // criteria = 5 iterations, no tilt model) restated operation by operation in float64 without contraction, so the

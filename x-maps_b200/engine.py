@@ -189,12 +189,16 @@ class DepthEngine:
         z_near: float = 0.1,
         z_far: float = 1.0,
         out: Optional[torch.Tensor] = None,
+        bilinear: bool = False,
     ) -> torch.Tensor:
         """One projector frame of events -> depth / disparity / BGR frame (asynchronous on the
-        current CUDA stream of the engine's device)."""
+        current CUDA stream of the engine's device).  ``bilinear``: opt-in bilinear X-map lookup at the un-rounded
+        rectified row / time column (``XM_FLAG_BILINEAR``; not reference behaviour, whose lookup is nearest)."""
         ev = self.events(events)
         out = self._alloc_out(view, output, out)
         a = self._args(ev, view, output, time_bounds, polarity, t_min, t_max, z_near, z_far, out.data_ptr())
+        if bilinear:
+            a.flags |= N.FLAG_BILINEAR
         N.check(N.lib.xm_frame(self._ctx, C.byref(a), self._stream()))
         return out
 
