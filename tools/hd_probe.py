@@ -45,6 +45,17 @@ def main():
         raw[:, 1] = (torch.rand(n, generator=g, device=dev) < 0.9).to(torch.int32)
         raw.view(torch.int64)[:, 1] = t
         frames.append(raw)
+    # the opt-in bilinear X-map lookup (XM_FLAG_BILINEAR; staged kernels, one frame per call) next to the nearest path
+    for mode in (True, False):
+        out1 = eng.frame(frames[0], view=0, bilinear=mode)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            for fr in frames:
+                eng.frame(fr, view=0, bilinear=mode, out=out1)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3 / a.frames
+        print(f"single frames, {'bilinear' if mode else 'nearest '} lookup: {dt * 1e6:8.1f} us / frame  {a.events / dt / 1e9:6.1f} G ev/s")
     for cells in (3072, 4608, 6144):
         for batch in (1, 0):
             eng.set_option("region_cells", cells)

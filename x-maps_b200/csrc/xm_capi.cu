@@ -19,6 +19,10 @@
 #include "xm_stage_kernels.cuh"
 #include "xm_fused_kernel.cuh"
 #include "xm_batch_kernel.cuh"
+
+#ifndef XM_BATCH_SMEM_CAP  // shared memory the resident batch-kernel CTAs of one SM may take together (above 196 KB the L1 shrinks to 28 KB)
+#define XM_BATCH_SMEM_CAP (196 * 1024)
+#endif
 #include "xm_stream_kernels.cuh"
 
 namespace {
@@ -309,7 +313,7 @@ int configure_event_kernels(XmCtx* c) {
             auto smem_for = [&](int k) {
                 return xm::batch_smem_bytes(c->opt_stages, c->opt_batch_win_stages, k * c->col_stride * 2, c->opt_region_cells, c->alive_words, cam != 0);
             };
-            while (bcols > 0 && xm::kBatchCtasPerSm * (smem_for(bcols) + 1024) > 196 * 1024) --bcols;
+            while (bcols > 0 && xm::kBatchCtasPerSm * (smem_for(bcols) + 1024) > XM_BATCH_SMEM_CAP) --bcols;
             c->batch_cols[cam] = bcols;
             c->batch_smem[cam] = smem_for(bcols);
             void (*k)(xm::BatchParams) = cam ? xm::batch_kernel<true> : xm::batch_kernel<false>;
