@@ -165,6 +165,10 @@ int xm_ctx_set_colormap(XmCtx* ctx, const uint8_t* h_bgr256);
  *   "batch"           xm_frame_batch on uniform batches: 1 = batch_kernel (one persistent kernel per <= 32
  *                     frames: staged event pipeline + epilogue warp groups), 0 = the per-frame kernels
  *                     back to back                                                              [1]
+ *   "scatter_aggregate" batch kernel, projector view: 1 = chunks in which nearly every event is live keep one RED per
+ *                     distinct cell and warp round (pays on a scanning projector's stream, where consecutive events
+ *                     share pixels; costs 25 % on a uniform stream), 0 = plain scatter, 2 = decide from the inlier
+ *                     fraction of the last batch whose statistics reached the host (asynchronous)       [2]
  *   "reserve_sms"     SMs the persistent batch kernel leaves free (e.g. for NCCL's copy kernels)  [0]
  *   "ctas_per_sm"     resident CTAs per SM for the event kernel, 0 = occupancy query            [0]
  *   "region_cells"    shared-memory cells per buffer of the projector-view epilogue [largest tile region of

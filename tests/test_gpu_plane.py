@@ -143,3 +143,30 @@ def test_hd_20m_events(manifest):
     assert sha(evp) == pcfg["events"]
     assert sha(eng.frame(evp, view=0).cpu().numpy()) == pcfg["depth_proj"]
     assert eng.status()["n_inliers"] == pcfg["n_inliers"]
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_warp_aggregated_scatter_is_bit_exact(default, time_map, mode):
+    """`scatter_aggregate`: dense chunks keep ONE RED per distinct cell and warp round (match.any; the highest lane of a
+    group holds the highest event index).  Forced on (1), off (0) and auto (2: decided from the previous batch's inlier
+    fraction) render the same frames: dense plane bursts, a heavy-collision frame, a uniform frame."""
+    tables, _, eng = default
+    burst = orc.synth_plane_events(tables, time_map, 0.5, repeat=156, jitter_us=12, seed=9)
+    plane = orc.synth_plane_events(tables, time_map, 0.4, repeat=10, jitter_us=8, seed=3)
+    uni = orc.synth_events(22, 1_500_000, 640, 480)
+    frames = [plane, burst, uni, plane]
+    want = [orc.frame_depth(tables, f, 0) for f in frames]
+    eng.set_option("scatter_aggregate", mode)
+    try:
+        for rep in range(3):  # (auto switches to the aggregating kernel after the first dense batch)
+            out = eng.frame_batch(frames, view=0).cpu().numpy()
+            for i, w in enumerate(want):
+                assert np.array_equal(out[i], w), f"mode {mode} pass {rep} frame {i}: {np.count_nonzero(out[i] != w)} pixels differ"
+        if mode == 2:
+            assert eng.get_option("scatter_aggregate_now") == 1
+            eng.frame_batch([uni, uni, uni], view=0)
+            torch.cuda.synchronize()
+            eng.frame_batch([uni, uni, uni], view=0)
+            assert eng.get_option("scatter_aggregate_now") == 0
+    finally:
+        eng.set_option("scatter_aggregate", 2)

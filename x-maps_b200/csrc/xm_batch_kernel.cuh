@@ -47,6 +47,9 @@ constexpr int kCamTilePx = 4096;  // camera-view epilogue item
 #define XM_POLL_NS0 200
 #define XM_POLL_NS1 1600
 #endif
+#ifndef XM_AGG_ABOVE
+#define XM_AGG_ABOVE 100
+#endif
 #ifndef XM_BATCH_CTAS
 #define XM_BATCH_CTAS 2
 #endif
@@ -246,10 +249,104 @@ __device__ __forceinline__ void batch_tile_groups(const BatchParams& bp, int grp
     }
 }
 
+// The back half's work on two list entries per lane, as one block of PTX (see `back` in batch_kernel): HEAD = lookup,
+// disparity, key; then the scatter -- PLAIN: one predicated RED per inlier; AGG: one RED per distinct cell of the warp
+// round (match.any on the cell, the highest lane of a group holds the highest event index), which pays when many
+// consecutive events share a cell (a scanning projector lights few pixels at a time) and costs 25 % on a uniform
+// stream -- and TAIL = counts.
+#define XM_BACK_PTX_HEAD \
+"{\n\t" \
+                    ".reg .pred pa0, pa1, ph0, ph1, pi0, pi1, pm0, pm1;\n\t" \
+                    ".reg .b32 m0, m1, l0, l1, y0, y1, c0, c1, r0, r1, a0, a1, x0, x1, xc0, xc1, d0, d1, cl0, cl1, k0, k1, j1;\n\t" \
+                    ".reg .s16 xs0, xs1;\n\t" \
+                    ".reg .b64 ad0, ad1, kk0, kk1;\n\t" \
+                    "ld.shared.u32 m0, [%2 + 8192];\n\t" \
+                    "ld.shared.u32 m1, [%2 + 8320];\n\t" \
+                    "ld.shared.u32 l0, [%2];\n\t" \
+                    "ld.shared.u32 l1, [%2 + 128];\n\t" \
+                    "add.u32 j1, %3, 32;\n\t" \
+                    "shr.s32 y0, l0, 16;\n\t" \
+                    "shr.s32 y1, l1, 16;\n\t" \
+                    "and.b32 c0, m0, 0xffff;\n\t" \
+                    "and.b32 c1, m1, 0xffff;\n\t" \
+                    "sub.u32 r0, c0, %5;\n\t" \
+                    "sub.u32 r1, c1, %5;\n\t" \
+                    "setp.lt.u32 pa0, y0, %7;\n\t" \
+                    "setp.lt.u32 pa1, y1, %7;\n\t" \
+                    "setp.lt.and.u32 pa0, %3, %4, pa0;\n\t" \
+                    "setp.lt.and.u32 pa1, j1, %4, pa1;\n\t" \
+                    "setp.lt.and.u32 ph0, r0, %6, pa0;\n\t" \
+                    "setp.lt.and.u32 ph1, r1, %6, pa1;\n\t" \
+                    "setp.ge.and.u32 pm0, r0, %6, pa0;\n\t" \
+                    "setp.ge.and.u32 pm1, r1, %6, pa1;\n\t" \
+                    "mad.lo.u32 a0, r0, %8, y0;\n\t" \
+                    "mad.lo.u32 a1, r1, %8, y1;\n\t" \
+                    "shl.b32 a0, a0, 1;\n\t" \
+                    "shl.b32 a1, a1, 1;\n\t" \
+                    "add.u32 a0, a0, %9;\n\t" \
+                    "add.u32 a1, a1, %9;\n\t" \
+                    "mov.b16 xs0, 0;\n\t" \
+                    "mov.b16 xs1, 0;\n\t" \
+                    "@ph0 ld.shared.s16 xs0, [a0];\n\t" \
+                    "@ph1 ld.shared.s16 xs1, [a1];\n\t" \
+                    "cvt.s32.s16 x0, xs0;\n\t" \
+                    "cvt.s32.s16 x1, xs1;\n\t" \
+                    "sub.s32 x0, x0, %10;\n\t" \
+                    "sub.s32 x1, x1, %10;\n\t" \
+                    "cvt.s32.s16 xc0, l0;\n\t" \
+                    "cvt.s32.s16 xc1, l1;\n\t" \
+                    "sub.s32 d0, x0, xc0;\n\t" \
+                    "sub.s32 d1, x1, xc1;\n\t" \
+                    "and.b32 k0, d0, 0x8000;\n\t" \
+                    "and.b32 k1, d1, 0x8000;\n\t" \
+                    "setp.eq.and.u32 pi0, k0, 0, ph0;\n\t" \
+                    "setp.eq.and.u32 pi1, k1, 0, ph1;\n\t" \
+                    "mad.lo.s32 cl0, y0, %11, x0;\n\t" \
+                    "mad.lo.s32 cl1, y1, %11, x1;\n\t" \
+                    "mad.wide.s32 ad0, cl0, 8, %12;\n\t" \
+                    "mad.wide.s32 ad1, cl1, 8, %12;\n\t" \
+                    "prmt.b32 k0, d0, m0, 0x7610;\n\t" \
+                    "prmt.b32 k1, d1, m1, 0x7610;\n\t" \
+                    "add.u32 k0, k0, %13;\n\t" \
+                    "add.u32 k1, k1, %13;\n\t" \
+                    "mov.b64 kk0, {k0, %14};\n\t" \
+                    "mov.b64 kk1, {k1, %14};\n\t"
+#define XM_BACK_PTX_RED_PLAIN \
+                    "@pi0 red.global.max.u64 [ad0], kk0;\n\t" \
+                    "@pi1 red.global.max.u64 [ad1], kk1;\n\t"
+#define XM_BACK_PTX_RED_AGG \
+                    "{\n\t" \
+                    ".reg .b32 g0, g1, q0, q1;\n\t" \
+                    ".reg .pred pl0, pl1;\n\t" \
+                    "sub.s32 q0, -1, %15;\n\t" \
+                    "selp.b32 g0, cl0, q0, pi0;\n\t" \
+                    "selp.b32 g1, cl1, q0, pi1;\n\t" \
+                    "match.any.sync.b32 g0, g0, 0xffffffff;\n\t" \
+                    "match.any.sync.b32 g1, g1, 0xffffffff;\n\t" \
+                    "shr.u32 g0, g0, %15;\n\t" \
+                    "shr.u32 g1, g1, %15;\n\t" \
+                    "setp.eq.and.u32 pl0, g0, 1, pi0;\n\t" \
+                    "setp.eq.and.u32 pl1, g1, 1, pi1;\n\t" \
+                    "@pl0 red.global.max.u64 [ad0], kk0;\n\t" \
+                    "@pl1 red.global.max.u64 [ad1], kk1;\n\t" \
+                    "}\n\t"
+#define XM_BACK_PTX_TAIL \
+                    "selp.u32 %0, 1, 0, pi0;\n\t" \
+                    "@pi1 add.u32 %0, %0, 1;\n\t" \
+                    "selp.u32 %1, 1, 0, pm0;\n\t" \
+                    "@pm1 or.b32 %1, %1, 2;\n\t" \
+                    "}"
+#define XM_BACK_PTX_OPERANDS \
+                    : "=r"(n_in), "=r"(n_miss) \
+                    : "r"(a_e), "r"(j0), "r"(count), "r"(win_lo), "r"(win_n), "r"(static_cast<unsigned>(bp.xmap_h) - 1u), "r"(static_cast<unsigned>(bp.col_stride)), \
+                      "r"(a_win_c), "r"(bp.x_offset), "r"(bp.rect_w), "l"(map), "r"(idx_lo), "r"(key_hi), "r"(lane) \
+                    : "memory"
+
 // What a chunk carries from its front half to its back half (one register):
 //   bit 0 constant slot | bits 1-3 events of this thread that pass the polarity mask | bit 4 a pixel outside the
 //   camera image | bit 5 a timestamp outside the assumed bounds | bits 8.. entries of the warp's live list
 constexpr unsigned kCarryOob = 1u << 4, kCarryTb = 1u << 5;
+constexpr unsigned kAggregateAbove = XM_AGG_ABOVE;  // live-list entries (of 128) above which a chunk's scatter is warp-aggregated
 constexpr unsigned kMetaSkip = 0x8000u;  // list entry of an event whose column is not usable (bounds violation)
 constexpr unsigned kMetaOff = 2 * kListBytes, kPixOff = 4 * kListBytes;  // (column | index << 16) / camera pixel lists behind the LUT words
 
@@ -302,7 +399,9 @@ static __device__ __noinline__ unsigned batch_front_general(const BatchParams& b
     return (kept << 1) | (oob ? kCarryOob : 0u) | (tb ? kCarryTb : 0u) | (count << 8);
 }
 
-template <bool CAM>
+// AGG: the instantiation whose dense chunks aggregate their scatter per warp round (see XM_BACK_PTX_*).  A second
+// instantiation rather than a run-time switch: the mere presence of the second PTX block costs the plain path 1.6 %.
+template <bool CAM, bool AGG = false>
 __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(const __grid_constant__ BatchParams bp) {
     extern __shared__ __align__(128) unsigned char ev_smem[];
     uint64_t* full_ev = reinterpret_cast<uint64_t*>(ev_smem);
@@ -665,80 +764,21 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(c
         const unsigned key_hi = static_cast<unsigned>(c2.z) | (static_cast<unsigned>(g) >> 6);
         const unsigned idx_lo = (static_cast<unsigned>(g) & 63u) << 26;  // bits 16.. of the key's low word
         unsigned missed = 0;  // entries whose column is not in the staged window (or that carry the skip flag)
+        // Dense chunk (nearly every event is live: what a scanning projector produces, consecutive events from the few
+        // pixels it lights) -> aggregate the scatter per warp round; a uniform stream (~40 % live) keeps the plain form.
+        const bool aggregate = AGG && count > kAggregateAbove;
 #pragma unroll 1
-        for (unsigned j0 = lane; j0 < count; j0 += 64u) {
+        for (unsigned jb = 0; jb < count; jb += 64u) {  // (warp-uniform trip count)
+            const unsigned j0 = jb + lane;
             // Two list entries per lane and round, everything for entries whose column is in the window, in one block of
             // PTX: predicates stay predicates (no masks in registers), the scatter is a predicated RED.
-            const unsigned a_e = a_list_c + (j0 - lane) * 4u;
+            const unsigned a_e = a_list_c + jb * 4u;
             unsigned n_in, n_miss;
             if (!CAM) {
-                asm volatile(
-                    "{\n\t"
-                    ".reg .pred pa0, pa1, ph0, ph1, pi0, pi1, pm0, pm1;\n\t"
-                    ".reg .b32 m0, m1, l0, l1, y0, y1, c0, c1, r0, r1, a0, a1, x0, x1, xc0, xc1, d0, d1, cl0, cl1, k0, k1, j1;\n\t"
-                    ".reg .s16 xs0, xs1;\n\t"
-                    ".reg .b64 ad0, ad1, kk0, kk1;\n\t"
-                    "ld.shared.u32 m0, [%2 + 8192];\n\t"
-                    "ld.shared.u32 m1, [%2 + 8320];\n\t"
-                    "ld.shared.u32 l0, [%2];\n\t"
-                    "ld.shared.u32 l1, [%2 + 128];\n\t"
-                    "add.u32 j1, %3, 32;\n\t"
-                    "shr.s32 y0, l0, 16;\n\t"
-                    "shr.s32 y1, l1, 16;\n\t"
-                    "and.b32 c0, m0, 0xffff;\n\t"
-                    "and.b32 c1, m1, 0xffff;\n\t"
-                    "sub.u32 r0, c0, %5;\n\t"
-                    "sub.u32 r1, c1, %5;\n\t"
-                    "setp.lt.u32 pa0, y0, %7;\n\t"                 // 0 <= y_rect < H - 1 (x_maps_disparity.py:23)
-                    "setp.lt.u32 pa1, y1, %7;\n\t"
-                    "setp.lt.and.u32 pa1, j1, %4, pa1;\n\t"        // entry exists (entry 0 always does: j0 < count)
-                    "setp.lt.and.u32 ph0, r0, %6, pa0;\n\t"        // column inside the staged window
-                    "setp.lt.and.u32 ph1, r1, %6, pa1;\n\t"
-                    "setp.ge.and.u32 pm0, r0, %6, pa0;\n\t"
-                    "setp.ge.and.u32 pm1, r1, %6, pa1;\n\t"
-                    "mad.lo.u32 a0, r0, %8, y0;\n\t"
-                    "mad.lo.u32 a1, r1, %8, y1;\n\t"
-                    "shl.b32 a0, a0, 1;\n\t"
-                    "shl.b32 a1, a1, 1;\n\t"
-                    "add.u32 a0, a0, %9;\n\t"
-                    "add.u32 a1, a1, %9;\n\t"
-                    "mov.b16 xs0, 0;\n\t"
-                    "mov.b16 xs1, 0;\n\t"
-                    "@ph0 ld.shared.s16 xs0, [a0];\n\t"
-                    "@ph1 ld.shared.s16 xs1, [a1];\n\t"
-                    "cvt.s32.s16 x0, xs0;\n\t"
-                    "cvt.s32.s16 x1, xs1;\n\t"
-                    "sub.s32 x0, x0, %10;\n\t"                     // x_map - X_OFFSET = x_rect + disparity
-                    "sub.s32 x1, x1, %10;\n\t"
-                    "cvt.s32.s16 xc0, l0;\n\t"
-                    "cvt.s32.s16 xc1, l1;\n\t"
-                    "sub.s32 d0, x0, xc0;\n\t"
-                    "sub.s32 d1, x1, xc1;\n\t"
-                    "and.b32 k0, d0, 0x8000;\n\t"                  // int16 arithmetic wraps: sign of the low half
-                    "and.b32 k1, d1, 0x8000;\n\t"
-                    "setp.eq.and.u32 pi0, k0, 0, ph0;\n\t"
-                    "setp.eq.and.u32 pi1, k1, 0, ph1;\n\t"
-                    "mad.lo.s32 cl0, y0, %11, x0;\n\t"
-                    "mad.lo.s32 cl1, y1, %11, x1;\n\t"
-                    "mad.wide.s32 ad0, cl0, 8, %12;\n\t"
-                    "mad.wide.s32 ad1, cl1, 8, %12;\n\t"
-                    "prmt.b32 k0, d0, m0, 0x7610;\n\t"             // disparity (low half) | index inside the chunk << 16
-                    "prmt.b32 k1, d1, m1, 0x7610;\n\t"
-                    "add.u32 k0, k0, %13;\n\t"
-                    "add.u32 k1, k1, %13;\n\t"
-                    "mov.b64 kk0, {k0, %14};\n\t"
-                    "mov.b64 kk1, {k1, %14};\n\t"
-                    "@pi0 red.global.max.u64 [ad0], kk0;\n\t"
-                    "@pi1 red.global.max.u64 [ad1], kk1;\n\t"
-                    "selp.u32 %0, 1, 0, pi0;\n\t"
-                    "@pi1 add.u32 %0, %0, 1;\n\t"
-                    "selp.u32 %1, 1, 0, pm0;\n\t"
-                    "@pm1 or.b32 %1, %1, 2;\n\t"
-                    "}"
-                    : "=r"(n_in), "=r"(n_miss)
-                    : "r"(a_e), "r"(j0), "r"(count), "r"(win_lo), "r"(win_n), "r"(XM_B_YLIM), "r"(static_cast<unsigned>(bp.col_stride)),
-                      "r"(a_win_c), "r"(bp.x_offset), "r"(bp.rect_w), "l"(map), "r"(idx_lo), "r"(key_hi)
-                    : "memory");
+                if (AGG && aggregate)
+                    asm volatile(XM_BACK_PTX_HEAD XM_BACK_PTX_RED_AGG XM_BACK_PTX_TAIL XM_BACK_PTX_OPERANDS);
+                else
+                    asm volatile(XM_BACK_PTX_HEAD XM_BACK_PTX_RED_PLAIN XM_BACK_PTX_TAIL XM_BACK_PTX_OPERANDS);
                 n_inl += n_in;
                 missed |= n_miss;
             } else {

@@ -94,6 +94,10 @@ struct XmCtx {
     short4* d_tile_box = nullptr;  // bounding box of the remap targets of every 32x32 output tile
     unsigned short* d_tile_off = nullptr;  // per output pixel: its cell inside the tile's shared-memory region (EpilogueParams::tile_off)
     int opt_tile_off = 1;
+    int opt_scatter_aggregate = 2;  // batch kernel: 0 plain scatter, 1 aggregate dense chunks per warp round, 2 auto (from the last batch's inlier fraction)
+    bool agg_dense = false, agg_pending = false;
+    cudaEvent_t agg_event = nullptr;
+    unsigned long long* h_agg_stats = nullptr;  // pinned: n_valid, n_inliers of the last sampled batch frame
     unsigned char* d_turbo = nullptr;
     unsigned long long* d_dbg = nullptr;  // per-CTA phase timestamps (option debug & 8)
     float* d_depth_lut = nullptr;  // [32768], exact depth of every integer disparity
@@ -210,6 +214,11 @@ unsigned next_epoch(XmCtx* c, unsigned count, cudaStream_t s, cudaError_t* err) 
     return e;
 }
 
+size_t fa_static_bytes(void (*k)(xm::BatchParams)) {
+    cudaFuncAttributes fa;
+    return cudaFuncGetAttributes(&fa, k) == cudaSuccess ? fa.sharedSizeBytes : 0;
+}
+
 using EvKernel = void (*)(xm::EventParams);
 EvKernel ev_kernel(bool f64, bool safe, int variant = 1, bool cam = false) {
     // 2: the lean integer-time kernel (verified tables); float64 timestamps and unverified tables take the general one
@@ -317,6 +326,8 @@ int configure_event_kernels(XmCtx* c) {
             c->batch_cols[cam] = bcols;
             c->batch_smem[cam] = smem_for(bcols);
             void (*k)(xm::BatchParams) = cam ? xm::batch_kernel<true> : xm::batch_kernel<false>;
+            XM_CUDA(cudaFuncSetAttribute(xm::batch_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         optin - static_cast<int>(fa_static_bytes(xm::batch_kernel<false, true>))));
             cudaFuncAttributes fa;
             XM_CUDA(cudaFuncGetAttributes(&fa, k));
             const int dyn = optin - static_cast<int>(fa.sharedSizeBytes);
@@ -901,11 +912,31 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
         int rc = profile_mark(c, s);
         if (rc) return rc;
     }
+    // Dense streams (nearly every event an inlier: what a scanning projector produces) take the instantiation that
+    // aggregates the scatter of dense chunks per warp round.  "scatter_aggregate" = 2 (auto) decides from the inlier
+    // fraction of the last batch whose statistics have arrived on the host (read back asynchronously, never waited for).
+    if (c->agg_event && c->agg_pending && cudaEventQuery(c->agg_event) == cudaSuccess) {
+        c->agg_pending = false;
+        c->agg_dense = c->h_agg_stats[0] > 0 && c->h_agg_stats[1] * 10ULL > c->h_agg_stats[0] * 6ULL;
+    }
+    const bool agg = !cam && (c->opt_scatter_aggregate == 1 || (c->opt_scatter_aggregate == 2 && c->agg_dense));
     if (cam)
         xm::batch_kernel<true><<<grid, xm::kBatchThreads, c->batch_smem[1], s>>>(bp);
+    else if (agg)
+        xm::batch_kernel<false, true><<<grid, xm::kBatchThreads, c->batch_smem[0], s>>>(bp);
     else
         xm::batch_kernel<false><<<grid, xm::kBatchThreads, c->batch_smem[0], s>>>(bp);
     XM_LAUNCHED();
+    if (c->opt_scatter_aggregate == 2 && !cam && !c->agg_pending) {
+        if (!c->agg_event) {
+            XM_CUDA(cudaEventCreateWithFlags(&c->agg_event, cudaEventDisableTiming));
+            XM_CUDA(cudaMallocHost(&c->h_agg_stats, 2 * sizeof(unsigned long long)));
+        }
+        // n_valid, n_inliers of the batch's first frame (adjacent 64-bit counters of its state block)
+        XM_CUDA(cudaMemcpyAsync(c->h_agg_stats, &c->d_bstate[0].n_valid, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        XM_CUDA(cudaEventRecord(c->agg_event, s));
+        c->agg_pending = true;
+    }
     if (c->opt_profile) {
         int rc = profile_mark(c, s);
         if (rc) return rc;
@@ -1156,6 +1187,8 @@ int xm_ctx_destroy(XmCtx* c) {
     cudaFree(c->d_remap_xy);
     cudaFree(c->d_tile_box);
     cudaFree(c->d_tile_off);
+    if (c->agg_event) cudaEventDestroy(c->agg_event);
+    if (c->h_agg_stats) cudaFreeHost(c->h_agg_stats);
     cudaFree(c->d_turbo);
     cudaFree(c->d_depth_lut);
     cudaFree(c->d_dbg);
@@ -1256,6 +1289,11 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         c->opt_coop = v != 0;
         return XM_OK;
     }
+    if (!strcmp(key, "scatter_aggregate")) { /* 0 / 1 / 2 = auto: warp-aggregated scatter of dense chunks in the batch kernel */
+        if (v < 0 || v > 2) return fail(XM_ERR_INVALID_ARG, "scatter_aggregate must be 0, 1 or 2");
+        c->opt_scatter_aggregate = v;
+        return XM_OK;
+    }
     if (!strcmp(key, "tile_off")) { /* 1: projector epilogue reads each pixel's region cell from the precomputed table */
         c->opt_tile_off = v != 0;
         return XM_OK;
@@ -1326,6 +1364,8 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     else if (!strcmp(key, "fused")) *value = c->opt_fused;
     else if (!strcmp(key, "alive")) *value = c->opt_alive;
     else if (!strcmp(key, "tile_off")) *value = c->opt_tile_off;
+    else if (!strcmp(key, "scatter_aggregate")) *value = c->opt_scatter_aggregate;
+    else if (!strcmp(key, "scatter_aggregate_now")) *value = c->agg_dense ? 1 : 0;  /* read-only: what "auto" currently selects */
     else if (!strcmp(key, "coop")) *value = c->opt_coop;
     else if (!strcmp(key, "alive_px")) *value = c->alive_px;          /* read-only: camera pixels inside alive blocks */
     else if (!strcmp(key, "batch")) *value = c->opt_batch;
