@@ -90,6 +90,8 @@ struct BatchParams {
     EpilogueParams ep;
     int tiles_x, tile_items;  // items per frame epilogue
     int n_frames;
+    unsigned long long* dbg;  // XM_DEBUG_HOOKS + debug & 8: per frame [0] first consumer enters, [1] last chunk count published,
+                              // [2] first tile group sees the frame complete, [3] last tile finished (global timer, ns)
     int debug;  // timing experiments only (results WRONG): 16 = skip the epilogue work of tile items
     int hard_frames;  // 1: publish a frame's chunk count before touching the next frame (few chunks per CTA and frame:
                       //    the tiles would otherwise wait for every CTA's NEXT chunk)
@@ -228,6 +230,9 @@ __device__ __forceinline__ void batch_tile_groups(const BatchParams& bp, int grp
             // (back-off: a group leader polls every 0.2 ... 1.6 us; the 3-map ring gives the tiles two frames of slack)
             for (unsigned ns = XM_POLL_NS0; ld_acquire_u32(&st->blocks_done) < need; ns = min(ns * 2u, static_cast<unsigned>(XM_POLL_NS1))) __nanosleep(ns);
             next_ticket = static_cast<int>(atomicAdd(&st->fix_chunk, 1u));
+#ifdef XM_DEBUG_HOOKS
+            if (bp.dbg) atomicMin(bp.dbg + f * 4 + 2, global_timer_ns());
+#endif
         }
         for (;;) {
             group_sync<kTileGroupThreads>(bar_id);  // the previous tile is done with the buffers / the frame is complete
@@ -244,6 +249,9 @@ __device__ __forceinline__ void batch_tile_groups(const BatchParams& bp, int grp
             if (gtid == 0) {
                 fence_acq_rel_gpu();
                 atomicAdd(&st->next_tile, 1u);  // this tile no longer needs the frame's scatter map
+#ifdef XM_DEBUG_HOOKS
+                if (bp.dbg) atomicMax(bp.dbg + f * 4 + 3, global_timer_ns());
+#endif
             }
         }
     }
@@ -600,6 +608,9 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(c
                 if (fl) atomicOr(&st->flags, fl);
                 fence_acq_rel_gpu();
                 atomicAdd(&st->blocks_done, my_chunks);
+#ifdef XM_DEBUG_HOOKS
+                if (bp.dbg) atomicMax(bp.dbg + cur_f * 4 + 1, global_timer_ns());
+#endif
             }
         }
         __syncwarp();
@@ -622,6 +633,9 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(c
         }
         const FrameState* st = bp.states + f;
         if (lane == 0) {
+#ifdef XM_DEBUG_HOOKS
+            if (bp.dbg) atomicMin(bp.dbg + f * 4 + 0, global_timer_ns());
+#endif
             const unsigned a = a_fc + fslot * 48;
             IntCol ic;
             ic.init(__ldcg(&st->t_lo_bits), __ldcg(&st->t_hi_bits), bp.t_px_scale);

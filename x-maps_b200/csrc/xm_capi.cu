@@ -883,6 +883,16 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     bp.tile_items = cam ? (c->cam_w * c->cam_h + xm::kCamTilePx - 1) / xm::kCamTilePx : tiles_x * tiles_y;
     bp.n_frames = n;
     bp.debug = c->opt_debug;
+    bp.dbg = nullptr;
+    if ((c->opt_debug & 8) && c->d_dbg) {  // per-frame hand-off timestamps (XM_DEBUG_HOOKS builds): min slots start at ~0, max slots at 0
+        bp.dbg = c->d_dbg;
+        std::vector<unsigned long long> init(xm::kBatchMax * 4);
+        for (int f = 0; f < xm::kBatchMax; ++f) {
+            init[f * 4 + 0] = init[f * 4 + 2] = ~0ULL;
+            init[f * 4 + 1] = init[f * 4 + 3] = 0ULL;
+        }
+        XM_CUDA(cudaMemcpyAsync(c->d_dbg, init.data(), init.size() * 8, cudaMemcpyHostToDevice, s));
+    }
     unsigned long long items64 = 0;
     for (int f = 0; f < n; ++f) {
         bp.first_item[f] = static_cast<unsigned>(items64);
