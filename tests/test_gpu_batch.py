@@ -13,24 +13,30 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-BATCH_KERNELS = [1]  # 1: batch_kernel (the persistent batch kernel)
+# batch_kernel (the persistent batch kernel) with both projector epilogues: the two-pass strip epilogue (default) and
+# the shared-memory tile epilogue
+BATCH_KERNELS = [(1, 1), (1, 0)]
+BATCH_IDS = ["strips", "tiles"]
 
 
-@pytest.fixture(scope="module", params=BATCH_KERNELS, ids=["staged"])
+@pytest.fixture(scope="module", params=BATCH_KERNELS, ids=BATCH_IDS)
 def small(request):
     tables, z = load_golden_tables("small")
     eng = make_engine(tables, z)
-    eng.set_option("batch", request.param)
-    assert eng.get_option("batch") == request.param and eng.get_option("batch_occ") >= 1
+    eng.set_option("batch", request.param[0])
+    eng.set_option("batch_strips", request.param[1])
+    assert eng.get_option("batch") == request.param[0] and eng.get_option("batch_occ") >= 1
+    assert eng.get_option("batch_strips") == request.param[1]
     yield tables, z, eng
     eng.close()
 
 
-@pytest.fixture(scope="module", params=BATCH_KERNELS, ids=["staged"])
+@pytest.fixture(scope="module", params=BATCH_KERNELS, ids=BATCH_IDS)
 def default(request):
     tables, z = load_golden_tables("default")
     eng = make_engine(tables)
-    eng.set_option("batch", request.param)
+    eng.set_option("batch", request.param[0])
+    eng.set_option("batch_strips", request.param[1])
     yield tables, z, eng
     eng.close()
 

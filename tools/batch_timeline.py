@@ -27,9 +27,10 @@ for _ in range(3):
     eng.frame_batch(frames, output=OUT_DEPTH)
 torch.cuda.synchronize()
 ptr = eng.get_option("debug_ptr")
-buf = torch.empty(32 * 4, dtype=torch.int64, device=dev)
-ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(buf.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(32 * 4 * 8), 3)
-x = buf.cpu().numpy().reshape(32, 4)[: a.frames].astype(np.float64)
+buf = torch.empty(32 * 4 + 256, dtype=torch.int64, device=dev)
+ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(buf.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t((32 * 4 + 256) * 8), 3)
+raw = buf.cpu().numpy()
+x = raw[:128].reshape(32, 4)[: a.frames].astype(np.float64)
 t0 = x[:, 0].min()
 r = (x - t0) / 1e3
 print("frame  enter  events-done  tiles-start  tiles-done   (us)   | events  publish->seen  tiles   frame-to-frame")
@@ -38,3 +39,9 @@ for f in range(a.frames):
     ff = r[f, 3] - r[f - 1, 3] if f else 0.0
     print(f"{f:5d} {d[0]:7.2f} {d[1]:10.2f} {d[2]:11.2f} {d[3]:11.2f}          | {d[1]-d[0]:6.2f} {d[2]-d[1]:10.2f} {d[3]-d[2]:9.2f} {ff:10.2f}")
 print("total %.2f us = %.2f us per frame" % (r[:, 3].max(), r[:, 3].max() / a.frames))
+acc = raw[256:266].astype(np.float64)
+if acc[8] + acc[9] > 0:  # strip epilogue: lane 0's cycles per phase (launches of the warm-up included: only the ratios and per-item means matter)
+    for ps, name in ((0, "pass 1"), (1, "pass 2")):
+        n = max(acc[8 + ps], 1.0)
+        print("%s: %d items, per item (us at 1.965 GHz): ticket %.2f  wait %.2f  work %.2f  publish %.2f" % (
+            name, acc[8 + ps], *(acc[ps * 4 + k] / n / 1965.0 for k in range(4))))

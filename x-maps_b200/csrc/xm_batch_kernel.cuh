@@ -37,7 +37,9 @@ constexpr int kBatchMax = 32;    // frames per launch (the frame table travels i
 #ifndef XM_BATCH_MAPS
 #define XM_BATCH_MAPS 3
 #endif
-constexpr int kBatchMaps = XM_BATCH_MAPS;  // scatter maps in rotation
+constexpr int kBatchMaps = XM_BATCH_MAPS;  // scatter maps in rotation (default; BatchParams::n_maps is what a launch uses)
+constexpr int kBatchMapsMax = 8;
+constexpr int kBatchDilMaps = 4;           // strip epilogue: dilated maps in rotation
 constexpr int kBatchHeader = 1152;  // mbarriers, ring descriptors, CTA accumulators, per-warp frame constants (2 slots)
 constexpr int kCamTilePx = 4096;  // camera-view epilogue item
 #ifndef XM_TILE_WARPS
@@ -83,12 +85,19 @@ struct BatchParams {
     const unsigned* alive;
     int alive_row_bytes, alive_words;
     unsigned alive_mask;  // alive_words * 4 - 4
-    unsigned long long* maps[kBatchMaps];
+    unsigned long long* maps[kBatchMapsMax];
+    int n_maps;             // maps in rotation: frame f scatters into maps[f % n_maps]
     unsigned epoch0;        // frame f scatters with epoch0 + f
     FrameState* states;     // [n_frames + 1]; block n_frames is the control block (next_chunk = item counter)
     // epilogue (ep.map / ep.dst / ep.state are set per tile)
     EpilogueParams ep;
-    int tiles_x, tile_items;  // items per frame epilogue
+    int tiles_x, tile_items;  // items per frame epilogue (strip epilogue: pass-1 items)
+    // strip epilogue (projector view; see xm_frame_kernels.cuh): every epilogue WARP works on its own, no shared memory
+    int strips;               // 1: on
+    int p2_items;             // pass-2 items per frame
+    StripWindow win;          // window of the rectified image pass 1 produces (bounding box of the remap targets)
+    const unsigned* pix_cell;  // per output pixel: its remap target's cell in the rectified image, 0xffffffff = none
+    unsigned short* dil[kBatchDilMaps];  // dilated disparity maps in rotation (frame f uses f % kBatchDilMaps)
     int n_frames;
     unsigned long long* dbg;  // XM_DEBUG_HOOKS + debug & 8: per frame [0] first consumer enters, [1] last chunk count published,
                               // [2] first tile group sees the frame complete, [3] last tile finished (global timer, ns)
@@ -141,6 +150,8 @@ __global__ void __launch_bounds__(64) batch_bounds_kernel(const __grid_constant_
         st->next_chunk = 0;
         st->next_tile = 0;
         st->fix_chunk = 0;
+        st->p2_ticket = 0;
+        st->p2_done = 0;
     }
     if (f >= p.n_frames) {
         if (threadIdx.x == 0) st->t_lo_bits = st->t_hi_bits = 0;
@@ -200,14 +211,14 @@ static __device__ __noinline__ void batch_tile(const BatchParams& bp, int f, int
 #endif
         // timing experiment: no epilogue work (results WRONG)
     } else if (CAM) {
-        const unsigned long long* mp = bp.maps[f % kBatchMaps];
+        const unsigned long long* mp = bp.maps[f % bp.n_maps];
         const int n_px = bp.ep.out_w * bp.ep.out_h;
         const int end = min(n_px, (t + 1) * kCamTilePx);
         for (int i = t * kCamTilePx + tid; i < end; i += kTileGroupThreads)
             emit_pixel_int(bp.ep.out, bp.frames[f].dst, i, key_disparity(__ldcg(mp + i), epoch));
     } else {
         EpilogueParams q = bp.ep;
-        q.map = bp.maps[f % kBatchMaps];
+        q.map = bp.maps[f % bp.n_maps];
         q.dst = bp.frames[f].dst;
         const int by = t / bp.tiles_x;
         proj7_tile_late<kTileGroupThreads, 6, 8>(q, t - by * bp.tiles_x, by, bp.tiles_x, epoch, bufA, bufB, tid, bar_id);
@@ -255,6 +266,122 @@ __device__ __forceinline__ void batch_tile_groups(const BatchParams& bp, int grp
             }
         }
     }
+}
+
+// The loop of one epilogue WARP with the strip epilogue (projector view).  The pass-1 items (strip x row segment: decode
+// + 7x7 dilation into the frame's dilated map) and pass-2 items (kRemapItemPx output pixels) of ALL frames form one
+// ordered list -- frame 0 pass 1, frame 0 pass 2, frame 1 pass 1, ... -- handed out by a global counter, so warps do not
+// march through the frames in step: with small frames the items of several frames are in flight at the same time.
+// A pass-1 item waits for its frame's chunks (and for pass 2 of the frame that used the same dilated map), a pass-2
+// item for the frame's finished pass-1 count.  The scatter map is free as soon as pass 1 is complete (`next_tile`
+// counts finished pass-1 items: what the event warps of frame f + n_maps wait for).  Every wait is for items that
+// come earlier in the list (or for event work that only depends on such items), an item is only ever held by a warp
+// that will run it, and the look-ahead ticket is run right after the current item, so this cannot deadlock.
+template <int CHUNK>
+__device__ __forceinline__ void batch_strip_warps(const BatchParams& bp, int lane) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int n_p1 = bp.tile_items, n_p2 = bp.p2_items;
+    const unsigned per_frame = static_cast<unsigned>(n_p1 + n_p2);
+    const unsigned total = per_frame * static_cast<unsigned>(bp.n_frames);
+    const int n_strips = bp.win.strips;
+    const int n_px = bp.ep.out_w * bp.ep.out_h;
+    unsigned* const counter = &bp.states[bp.n_frames].next_tile;
+    auto wait_for = [&](const unsigned* c, unsigned need) {
+        for (unsigned ns = XM_POLL_NS0; ld_acquire_u32(c) < need; ns = min(ns * 2u, static_cast<unsigned>(XM_POLL_NS1))) __nanosleep(ns);
+    };
+#ifdef XM_DEBUG_HOOKS  // lane 0's cycles per phase and pass: [pass * 4 + {ticket, wait, work, publish}], [8 + pass] items
+    long long acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#define XM_STRIP_CLK(v) v = clock64()
+#else
+#define XM_STRIP_CLK(v)
+#endif
+#ifndef XM_STRIP_LOOKAHEAD
+#define XM_STRIP_LOOKAHEAD 0
+#endif
+    // List order: pass 1 of frame 0, then blocks of (pass 1 of frame g, pass 2 of frame g - 1), then pass 2 of the last
+    // frame: by the time a warp reaches the pass-2 items of a frame, that frame's pass 1 has had a block's worth of
+    // items to complete, so warps spend their time on items that can run instead of holding items that cannot.
+    unsigned ticket = 0;
+    if (XM_STRIP_LOOKAHEAD && lane == 0) ticket = atomicAdd(counter, 1u);
+    for (;;) {
+        XM_STRIP_CLK(c0);
+        if (!XM_STRIP_LOOKAHEAD && lane == 0) ticket = atomicAdd(counter, 1u);
+        const unsigned t = __shfl_sync(kFull, ticket, 0);
+        if (t >= total) break;
+        if (XM_STRIP_LOOKAHEAD && lane == 0) ticket = atomicAdd(counter, 1u);
+        XM_STRIP_CLK(c1);
+        int f, j;  // frame, item (j < n_p1: pass 1, else pass 2 item j - n_p1)
+        if (t < static_cast<unsigned>(n_p1)) {
+            f = 0;
+            j = static_cast<int>(t);
+        } else {
+            const unsigned k = t - static_cast<unsigned>(n_p1);
+            const int g = static_cast<int>(k / per_frame) + 1;
+            const int r = static_cast<int>(k - static_cast<unsigned>(g - 1) * per_frame);
+            if (g < bp.n_frames && r < n_p1) {
+                f = g;
+                j = r;
+            } else {
+                f = g - 1;
+                j = g < bp.n_frames ? r : r + n_p1;
+            }
+        }
+        FrameState* st = bp.states + f;
+        unsigned short* const dil = bp.dil[f % kBatchDilMaps];
+        if (j < n_p1) {
+            if (lane == 0) {
+                wait_for(&st->blocks_done, static_cast<unsigned>((bp.frames[f].n + CHUNK - 1) / CHUNK));
+                if (f >= kBatchDilMaps) wait_for(&bp.states[f - kBatchDilMaps].p2_done, static_cast<unsigned>(n_p2));
+#ifdef XM_DEBUG_HOOKS
+                if (bp.dbg) atomicMin(bp.dbg + f * 4 + 2, global_timer_ns());
+#endif
+            }
+            __syncwarp();
+            XM_STRIP_CLK(c2);
+            const int seg = j / n_strips;
+            if (!(bp.debug & 16))
+                strip_dilate_item(bp.maps[f % bp.n_maps], dil, bp.rect_w, bp.rect_h, bp.epoch0 + static_cast<unsigned>(f),
+                                  bp.win.x0 + (j - seg * n_strips) * kStripCols, bp.win.y0 + seg * kStripRows, bp.win.y1, lane);
+            __syncwarp();
+            XM_STRIP_CLK(c3);
+            if (lane == 0) {
+                fence_acq_rel_gpu();
+                atomicAdd(&st->next_tile, 1u);
+            }
+        } else {
+            RemapPipe rp;
+            strip_remap_begin(rp, bp.pix_cell, n_px, j - n_p1, lane);  // (static table: requested before the wait)
+            if (lane == 0) wait_for(&st->next_tile, static_cast<unsigned>(n_p1));
+            __syncwarp();
+            XM_STRIP_CLK(c2);
+            if (!(bp.debug & 16)) strip_remap_run(rp, bp.ep.out, bp.frames[f].dst, bp.pix_cell, dil, n_px, j - n_p1, lane);
+            __syncwarp();
+            XM_STRIP_CLK(c3);
+            if (lane == 0) {
+                fence_acq_rel_gpu();
+                atomicAdd(&st->p2_done, 1u);
+#ifdef XM_DEBUG_HOOKS
+                if (bp.dbg) atomicMax(bp.dbg + f * 4 + 3, global_timer_ns());
+#endif
+            }
+        }
+#ifdef XM_DEBUG_HOOKS
+        {
+            const long long c4 = clock64();
+            const int ps = j < n_p1 ? 0 : 1;
+            acc[ps * 4 + 0] += c1 - c0;
+            acc[ps * 4 + 1] += c2 - c1;
+            acc[ps * 4 + 2] += c3 - c2;
+            acc[ps * 4 + 3] += c4 - c3;
+            acc[8 + ps] += 1;
+        }
+#endif
+    }
+#ifdef XM_DEBUG_HOOKS
+    if (bp.dbg && lane == 0)
+        for (int i = 0; i < 10; ++i) atomicAdd(bp.dbg + 256 + i, static_cast<unsigned long long>(acc[i]));
+#endif
 }
 
 // The back half's work on two list entries per lane, as one block of PTX (see `back` in batch_kernel): HEAD = lookup,
@@ -447,6 +574,10 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(c
 
     if (warp > kEvThreads / 32) {
         // ---- epilogue groups ----------------------------------------------------------------------
+        if (!CAM && bp.strips) {
+            batch_strip_warps<kEvChunk>(bp, lane);
+            return;
+        }
         const int grp = (tid - kWsThreads) / kTileGroupThreads, gtid = (tid - kWsThreads) % kTileGroupThreads;
         unsigned short* bufA = reinterpret_cast<unsigned short*>(win_ring + bp.win_stages * win_bytes) + grp * (2 * bp.ep.region_cap);
         unsigned short* bufB = bufA + bp.ep.region_cap;
@@ -622,10 +753,10 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(c
     auto prepare_frame = [&](int f) {
         front_f = f;
         fslot ^= 1u;
-        if (f >= kBatchMaps) {
-            // this frame scatters into the map frame f - kBatchMaps used: all of that frame's tiles must have read it
+        if (f >= bp.n_maps) {
+            // this frame scatters into the map frame f - n_maps used: all of that frame's tiles must have read it
             if (lane == 0) {
-                const unsigned* done = &bp.states[f - kBatchMaps].next_tile;
+                const unsigned* done = &bp.states[f - bp.n_maps].next_tile;
                 const unsigned need = static_cast<unsigned>(bp.tile_items);
                 while (ld_acquire_u32(done) < need) __nanosleep(64);
             }
@@ -639,7 +770,7 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(c
             const unsigned a = a_fc + fslot * 48;
             IntCol ic;
             ic.init(__ldcg(&st->t_lo_bits), __ldcg(&st->t_hi_bits), bp.t_px_scale);
-            const unsigned long long mp = reinterpret_cast<unsigned long long>(bp.maps[f % kBatchMaps]);
+            const unsigned long long mp = reinterpret_cast<unsigned long long>(bp.maps[f % bp.n_maps]);
             sts128_a(a, make_int4(static_cast<int>(ic.lo), static_cast<int>(ic.lo >> 32), static_cast<int>(ic.range), static_cast<int>(ic.scale2)));
             sts128_a(a + 16, make_int4(static_cast<int>(ic.d), static_cast<int>(ic.M), ic.sh, ic.ok ? 1 : 0));
             sts128_a(a + 32, make_int4(static_cast<int>(mp), static_cast<int>(mp >> 32),
@@ -878,15 +1009,15 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(c
     for (;;) {
         const int2 m = peek();  // (does not consume the stage: front() releases it)
         const bool more = m.x >= 0;
-        // Entering frame F waits for the tiles of frame F - kBatchMaps, which wait for every warp's count
+        // Entering frame F waits for the tiles of frame F - n_maps, which wait for every warp's count
         // of that frame's chunks.  This warp publishes a frame's count only in the BACK half of a later
         // frame's chunk, so if one of its two unpublished frames (cur_f: back half, f_cur: front half done)
         // is that old, the pipeline is drained first (tiny frames / many more CTAs than chunks per frame).
         bool drain = false;
         if (more && have_cur && m.x != f_cur) {
             drain = bp.hard_frames != 0;
-            if (!drain && m.x != front_f && m.x >= kBatchMaps) {
-                const int must_be_out = m.x - kBatchMaps;
+            if (!drain && m.x != front_f && m.x >= bp.n_maps) {
+                const int must_be_out = m.x - bp.n_maps;
                 drain = f_cur <= must_be_out || (cur_f >= 0 && cur_f <= must_be_out);
             }
         }

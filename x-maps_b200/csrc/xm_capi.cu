@@ -94,6 +94,11 @@ struct XmCtx {
     short4* d_tile_box = nullptr;  // bounding box of the remap targets of every 32x32 output tile
     unsigned short* d_tile_off = nullptr;  // per output pixel: its cell inside the tile's shared-memory region (EpilogueParams::tile_off)
     int opt_tile_off = 1;
+    // strip epilogue of the batch kernel (projector view): per-pixel cell index table and the dilated-map ring
+    unsigned* d_pix_cell = nullptr;
+    unsigned short* d_dil = nullptr;  // kBatchDilMaps x rect_w x rect_h
+    xm::StripWindow strip_win = {};
+    int opt_batch_strips = 1;
     int opt_scatter_aggregate = 2;  // batch kernel: 0 plain scatter, 1 aggregate dense chunks per warp round, 2 auto (from the last batch's inlier fraction)
     bool agg_dense = false, agg_pending = false;
     cudaEvent_t agg_event = nullptr;
@@ -142,7 +147,8 @@ struct XmCtx {
     int opt_batch = 1;        // 1: xm_frame_batch renders uniform batches with one persistent kernel per <= 32 frames
                               //    (event warps + dedicated epilogue warps; 47 vs 57 us per 5 M-event frame, EXPERIMENTS_r01.md)
     int batch_occ = 0, batch_smem[2] = {0, 0}, batch_cols[2] = {0, 0};  // launch configuration of batch_kernel ([view])
-    unsigned long long* d_map_ring[xm::kBatchMaps] = {};  // [0] = d_map
+    unsigned long long* d_map_ring[xm::kBatchMapsMax] = {};  // [0] = d_map; the others are allocated when a batch first uses them
+    int opt_batch_maps = 0;  // scatter maps in rotation (0 = auto: kBatchMaps, more for batches of small frames)
     xm::FrameState* d_bstate = nullptr;  // [kBatchMax + 1] state blocks of the current batch
     const xm::FrameState* status_src = nullptr;  // state block xm_frame_status reports (NULL: d_state + last_slot)
     int opt_pdl = 1;          // programmatic dependent launch between K1 / K2 / next K1
@@ -205,7 +211,7 @@ unsigned next_epoch(XmCtx* c, unsigned count, cudaStream_t s, cudaError_t* err) 
     *err = cudaSuccess;
     if (c->epoch + count > 0xffffu) {
         *err = cudaMemsetAsync(c->d_map, 0, static_cast<size_t>(c->map_cells) * 8, s);
-        for (int i = 1; i < xm::kBatchMaps && *err == cudaSuccess; ++i)
+        for (int i = 1; i < xm::kBatchMapsMax && *err == cudaSuccess; ++i)
             if (c->d_map_ring[i]) *err = cudaMemsetAsync(c->d_map_ring[i], 0, static_cast<size_t>(c->map_cells) * 8, s);
         c->epoch = 0;
     }
@@ -264,6 +270,9 @@ cudaError_t launch_pdl(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cu
     return e;
 }
 
+// shared-memory tile regions of the batch kernel's epilogue groups: none for the camera view and the strip epilogue
+int batch_region_cells(const XmCtx* c, bool cam) { return (cam || (c->opt_batch_strips && c->d_pix_cell)) ? 0 : c->opt_region_cells; }
+
 int configure_event_kernels(XmCtx* c) {
     int cols = 0;
     if (c->opt_stage_xmap && c->col_stride > 0) cols = c->opt_smem_cols_bytes / (c->col_stride * 2);
@@ -320,7 +329,7 @@ int configure_event_kernels(XmCtx* c) {
         for (int cam = 0; cam < 2; ++cam) {
             int bcols = cols;
             auto smem_for = [&](int k) {
-                return xm::batch_smem_bytes(c->opt_stages, c->opt_batch_win_stages, k * c->col_stride * 2, c->opt_region_cells, c->alive_words, cam != 0);
+                return xm::batch_smem_bytes(c->opt_stages, c->opt_batch_win_stages, k * c->col_stride * 2, batch_region_cells(c, cam != 0), c->alive_words, cam != 0);
             };
             while (bcols > 0 && xm::kBatchCtasPerSm * (smem_for(bcols) + 1024) > XM_BATCH_SMEM_CAP) --bcols;
             c->batch_cols[cam] = bcols;
@@ -807,11 +816,6 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
         XM_CUDA(cudaMemset(c->d_bstate, 0, (xm::kBatchMax + 1) * sizeof(xm::FrameState)));
     }
     c->d_map_ring[0] = c->d_map;
-    for (int i = 1; i < xm::kBatchMaps; ++i)
-        if (!c->d_map_ring[i]) {
-            XM_CUDA(cudaMalloc(&c->d_map_ring[i], static_cast<size_t>(c->map_cells) * 8));
-            XM_CUDA(cudaMemset(c->d_map_ring[i], 0, static_cast<size_t>(c->map_cells) * 8));
-        }
     const bool cam = a[0].view == XM_VIEW_CAMERA;
     const int polarity = (a[0].flags & XM_FLAG_POLARITY) ? 1 : 0;
     const bool fixup = c->opt_auto_fixup != 0;
@@ -858,7 +862,6 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     bp.alive_row_bytes = c->alive_wpr * 4;
     bp.alive_mask = static_cast<unsigned>(c->alive_words) * 4u - 4u;
     bp.alive_words = c->alive_words;
-    for (int i = 0; i < xm::kBatchMaps; ++i) bp.maps[i] = c->d_map_ring[i];
     bp.epoch0 = epoch0;
     bp.states = c->d_bstate;
     xm::EpilogueParams& q = bp.ep;
@@ -873,7 +876,7 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     q.rect_w = c->rect_w;
     q.rect_h = c->rect_h;
     q.radius = c->dilate / 2;
-    q.region_cap = c->opt_region_cells;
+    q.region_cap = batch_region_cells(c, cam);
     q.out = make_output(c, a[0].output, c->depth_scale, a[0].z_near, a[0].z_far);
     q.dst = nullptr;
     q.out_w = cam ? c->cam_w : c->proj_w;
@@ -881,12 +884,23 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     const int tiles_x = (c->proj_w + xm::kTile - 1) / xm::kTile, tiles_y = (c->proj_h + xm::kTile - 1) / xm::kTile;
     bp.tiles_x = tiles_x;
     bp.tile_items = cam ? (c->cam_w * c->cam_h + xm::kCamTilePx - 1) / xm::kCamTilePx : tiles_x * tiles_y;
+    long long epi_items = (static_cast<long long>(bp.tile_items) + xm::kTileGroups - 1) / xm::kTileGroups;  // per CTA and round
+    if (!cam && c->opt_batch_strips && c->d_pix_cell) {
+        if (!c->d_dil) XM_CUDA(cudaMalloc(&c->d_dil, static_cast<size_t>(xm::kBatchDilMaps) * c->rect_w * c->rect_h * sizeof(unsigned short)));
+        bp.strips = 1;
+        bp.pix_cell = c->d_pix_cell;
+        for (int i = 0; i < xm::kBatchDilMaps; ++i) bp.dil[i] = c->d_dil + static_cast<size_t>(i) * c->rect_w * c->rect_h;
+        bp.win = c->strip_win;
+        bp.tile_items = c->strip_win.items;
+        bp.p2_items = static_cast<int>((static_cast<long long>(c->proj_w) * c->proj_h + xm::kRemapItemPx - 1) / xm::kRemapItemPx);
+        epi_items = (bp.tile_items + bp.p2_items + xm::kTileWarps - 1) / xm::kTileWarps;
+    }
     bp.n_frames = n;
     bp.debug = c->opt_debug;
     bp.dbg = nullptr;
     if ((c->opt_debug & 8) && c->d_dbg) {  // per-frame hand-off timestamps (XM_DEBUG_HOOKS builds): min slots start at ~0, max slots at 0
         bp.dbg = c->d_dbg;
-        std::vector<unsigned long long> init(xm::kBatchMax * 4);
+        std::vector<unsigned long long> init(xm::kBatchMax * 4 + 256, 0ULL);  // [256 ..): phase cycle counters of the strip epilogue
         for (int f = 0; f < xm::kBatchMax; ++f) {
             init[f * 4 + 0] = init[f * 4 + 2] = ~0ULL;
             init[f * 4 + 1] = init[f * 4 + 3] = 0ULL;
@@ -911,13 +925,22 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     const int occ = c->opt_ctas_per_sm > 0 && c->opt_ctas_per_sm < kocc ? c->opt_ctas_per_sm : kocc;
     // no more CTAs than there is work: a CTA takes chunks in pairs and runs kTileGroups tiles at a time
     long long want = (static_cast<long long>(items) + 1) / 2;
-    const long long want_tiles = (static_cast<long long>(bp.tile_items) + xm::kTileGroups - 1) / xm::kTileGroups;
+    const long long want_tiles = epi_items;
     if (want_tiles > want) want = want_tiles;
     int grid = (c->sm_count - c->opt_reserve_sms) * occ;
     if (want < grid) grid = static_cast<int>(want < 1 ? 1 : want);
     // pipelining across frame boundaries pays when a CTA has many chunks per frame; with few, the late
     // publication of a frame's count (in the back half of the NEXT frame's first chunk) delays its tiles
     bp.hard_frames = static_cast<long long>(items) < 8LL * n * grid ? 1 : 0;
+    // scatter maps in rotation: a frame holds its map from its first chunk to the end of its epilogue's reads; with small
+    // frames that latency, not the work, sets the pace, so more frames are kept in flight
+    bp.n_maps = c->opt_batch_maps > 0 ? c->opt_batch_maps : (bp.hard_frames ? 6 : xm::kBatchMaps);
+    for (int i = 1; i < bp.n_maps; ++i)
+        if (!c->d_map_ring[i]) {
+            XM_CUDA(cudaMalloc(&c->d_map_ring[i], static_cast<size_t>(c->map_cells) * 8));
+            XM_CUDA(cudaMemsetAsync(c->d_map_ring[i], 0, static_cast<size_t>(c->map_cells) * 8, s));
+        }
+    for (int i = 0; i < bp.n_maps; ++i) bp.maps[i] = c->d_map_ring[i];
     if (c->opt_profile) {
         int rc = profile_mark(c, s);
         if (rc) return rc;
@@ -980,6 +1003,7 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
         p.smem_bytes = c->ev_smem;
         rp.ep = bp.ep;
         rp.ep.map = c->d_map;
+        rp.ep.region_cap = c->opt_region_cells;
         rp.epoch_redo0 = epoch0 + static_cast<unsigned>(n);
         rp.n_frames = n;
         rp.sm_count = c->sm_count;
@@ -1139,6 +1163,25 @@ int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
                 cudaMemcpy(c->d_tile_off, offs.data(), offs.size() * sizeof(unsigned short), cudaMemcpyHostToDevice) != cudaSuccess)
                 return bail(fail(XM_ERR_CUDA, "uploading the tile offsets failed: %s", cudaGetErrorString(cudaGetLastError())));
         }
+        // strip epilogue: every output pixel's cell in the rectified image (even rect_w only: cell pairs are read as one 16-byte word)
+        if (!(t->rect_w & 1) && static_cast<long long>(t->rect_w) * t->rect_h < 0x7fffffffLL) {
+            std::vector<unsigned> cells(static_cast<size_t>(t->proj_w) * t->proj_h, 0xffffffffu);
+            int bx0 = 1 << 30, by0 = 1 << 30, bx1 = -1, by1 = -1;
+            for (size_t i = 0; i < cells.size(); ++i) {
+                const int mx = t->remap_xy[i * 2], my = t->remap_xy[i * 2 + 1];
+                if (mx < 0 || mx >= t->rect_w || my < 0 || my >= t->rect_h) continue;
+                cells[i] = static_cast<unsigned>(my) * static_cast<unsigned>(t->rect_w) + static_cast<unsigned>(mx);
+                bx0 = mx < bx0 ? mx : bx0;
+                bx1 = mx > bx1 ? mx : bx1;
+                by0 = my < by0 ? my : by0;
+                by1 = my > by1 ? my : by1;
+            }
+            if (bx1 < 0) bx0 = by0 = bx1 = by1 = 0;  // no pixel maps into the rectified image: one (empty) item
+            c->strip_win = xm::strip_window(bx0, by0, bx1, by1);
+            if (cudaMalloc(&c->d_pix_cell, cells.size() * sizeof(unsigned)) != cudaSuccess ||
+                cudaMemcpy(c->d_pix_cell, cells.data(), cells.size() * sizeof(unsigned), cudaMemcpyHostToDevice) != cudaSuccess)
+                return bail(fail(XM_ERR_CUDA, "uploading the pixel cell table failed: %s", cudaGetErrorString(cudaGetLastError())));
+        }
     }
     c->map_cells = static_cast<long long>(t->rect_w) * t->rect_h;
     if (static_cast<long long>(cam_px) > c->map_cells) c->map_cells = static_cast<long long>(cam_px);
@@ -1197,13 +1240,15 @@ int xm_ctx_destroy(XmCtx* c) {
     cudaFree(c->d_remap_xy);
     cudaFree(c->d_tile_box);
     cudaFree(c->d_tile_off);
+    cudaFree(c->d_pix_cell);
+    cudaFree(c->d_dil);
     if (c->agg_event) cudaEventDestroy(c->agg_event);
     if (c->h_agg_stats) cudaFreeHost(c->h_agg_stats);
     cudaFree(c->d_turbo);
     cudaFree(c->d_depth_lut);
     cudaFree(c->d_dbg);
     cudaFree(c->d_map);
-    for (int i = 1; i < xm::kBatchMaps; ++i) cudaFree(c->d_map_ring[i]);
+    for (int i = 1; i < xm::kBatchMapsMax; ++i) cudaFree(c->d_map_ring[i]);
     cudaFree(c->d_bstate);
     cudaFree(c->d_state);
     cudaFree(c->d_counts);
@@ -1308,6 +1353,15 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         c->opt_tile_off = v != 0;
         return XM_OK;
     }
+    if (!strcmp(key, "batch_strips")) { /* 1: the batch kernel's projector epilogue runs as two barrier-free passes (strip dilation, then remap) */
+        c->opt_batch_strips = v != 0;
+        return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;  // the batch kernel's shared memory depends on it
+    }
+    if (!strcmp(key, "batch_maps")) { /* scatter maps the batch kernel rotates through (0 = auto) */
+        if (v < 0 || v == 1 || v > xm::kBatchMapsMax) return fail(XM_ERR_INVALID_ARG, "batch_maps must be 0 or 2 ... %d", xm::kBatchMapsMax);
+        c->opt_batch_maps = v;
+        return XM_OK;
+    }
     if (!strcmp(key, "alive")) { /* 1: the batch kernel skips the look-ups of events whose pixel block can never yield an inlier */
         c->opt_alive = v != 0;
         return XM_OK;
@@ -1374,6 +1428,8 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     else if (!strcmp(key, "fused")) *value = c->opt_fused;
     else if (!strcmp(key, "alive")) *value = c->opt_alive;
     else if (!strcmp(key, "tile_off")) *value = c->opt_tile_off;
+    else if (!strcmp(key, "batch_strips")) *value = c->opt_batch_strips;
+    else if (!strcmp(key, "batch_maps")) *value = c->opt_batch_maps;
     else if (!strcmp(key, "scatter_aggregate")) *value = c->opt_scatter_aggregate;
     else if (!strcmp(key, "scatter_aggregate_now")) *value = c->agg_dense ? 1 : 0;  /* read-only: what "auto" currently selects */
     else if (!strcmp(key, "coop")) *value = c->opt_coop;

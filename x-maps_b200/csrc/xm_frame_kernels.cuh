@@ -33,6 +33,8 @@ struct FrameState {
     unsigned int next_chunk;  // dynamic chunk scheduler of the lean K1
     unsigned int next_tile;   // fused kernel: epilogue tile scheduler
     unsigned int fix_chunk;   // fused kernel: chunk scheduler of the fix-up pass
+    unsigned int p2_ticket;   // batch kernel, strip epilogue: pass-2 item scheduler
+    unsigned int p2_done;     //   ... and finished pass-2 items
 };
 
 constexpr unsigned kStatusTBounds = 0x1u;
@@ -1464,6 +1466,160 @@ __device__ __forceinline__ void proj7_tile_late(const EpilogueParams& p, int bx,
             idx[j] = pix0 + (k0 + j) * step;
         }
         emit_pixels_int<PXB>(p.out, p.dst, idx, val, live);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Strip epilogue (projector view, 7x7 dilation, even rect_w): the same result in two passes WITHOUT shared memory or
+// barriers, each item done by ONE warp.
+//   pass 1 (rectified domain, every cell decoded once): a warp walks down kStripRows + 6 rows of a strip of 64 cells
+//     (lane l holds cells 2l, 2l+1 as a u16 pair; lanes 0, 1, 30, 31 are the halo), decodes the keys, takes the
+//     horizontal 7-max with four shuffles and the vertical 7-max with a register sliding window (three SIMD max per
+//     row), and stores the dilated u16 disparities of its 56 x kStripRows cells into a small map (rect_w x rect_h x 2 B);
+//   pass 2 (output domain): per output pixel one streamed 32-bit load of the pixel's cell index (table built with the
+//     remap table), one 16-bit gather from the dilated map (L2), one depth-table look-up, one store.
+// cv2.dilate ignores taps outside the image and disparities are >= 0, so "outside" and "undefined" are both 0.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStripCols = 56;   // cells a strip produces per row
+#ifndef XM_STRIP_ROWS
+#define XM_STRIP_ROWS 42
+#endif
+#ifndef XM_STRIP_BATCH
+#define XM_STRIP_BATCH 8
+#endif
+#ifndef XM_REMAP_PX
+#define XM_REMAP_PX 8
+#endif
+#ifndef XM_REMAP_BLOCKS
+#define XM_REMAP_BLOCKS 8
+#endif
+constexpr int kStripRows = XM_STRIP_ROWS;    // rows a pass-1 item produces (it reads kStripRows + 6)
+constexpr int kStripBatch = XM_STRIP_BATCH;  // rows whose key loads are in flight together: an item costs (kStripRows + 6) / kStripBatch L2 round trips
+constexpr int kRemapPx = XM_REMAP_PX;        // output pixels per lane and block of a pass-2 item
+constexpr int kRemapBlocks = XM_REMAP_BLOCKS;  // blocks per pass-2 item (software-pipelined: cell indices two blocks ahead, gathers one)
+constexpr int kRemapItemPx = 32 * kRemapPx * kRemapBlocks;  // output pixels of a pass-2 item
+static_assert((kStripRows + 6) % kStripBatch == 0, "a pass-1 item is a whole number of row batches");
+
+// The window of the rectified image pass 1 has to produce: the bounding box of the remap targets (x0 rounded down to even).
+struct StripWindow {
+    int x0, y0, x1, y1;  // cells [x0, x1) x [y0, y1); x0 even
+    int strips, items;   // strips across, pass-1 items (strips x row segments)
+};
+inline StripWindow strip_window(int bx0, int by0, int bx1, int by1) {  // inclusive bounding box
+    StripWindow w;
+    w.x0 = bx0 & ~1;
+    w.y0 = by0;
+    w.x1 = bx1 + 1;
+    w.y1 = by1 + 1;
+    w.strips = (w.x1 - w.x0 + kStripCols - 1) / kStripCols;
+    w.items = w.strips * ((w.y1 - w.y0 + kStripRows - 1) / kStripRows);
+    return w;
+}
+
+__device__ __forceinline__ unsigned ldg_stream_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// pass 1, one item: output cells [x_out, x_out + 56) x [y_out, min(y_out + kStripRows, y_end)); x_out even
+__device__ __forceinline__ void strip_dilate_item(const unsigned long long* __restrict__ map, unsigned short* __restrict__ dil, int rect_w,
+                                                  int rect_h, unsigned epoch, int x_out, int y_out, int y_end, int lane) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const unsigned ep16 = epoch & 0xffffu;
+    const int gx = x_out - 4 + 2 * lane;  // first cell of this lane's pair (even; rect_w is even)
+    const bool col_in = gx >= 0 && gx < rect_w;
+    const bool store_lane = lane >= 2 && lane < 30 && col_in;
+    const int y_first = y_out - 3;  // first row read
+    unsigned h1 = 0u, m2a = 0u, m2b = 0u, m4a = 0u, m4b = 0u, m4c = 0u;  // sliding window: rows i-1 (h, m2, m4), i-2 (m2, m4), i-3 (m4)
+#pragma unroll 1
+    for (int i0 = 0; i0 < kStripRows + 6; i0 += kStripBatch) {
+        if (y_first + i0 - 3 >= y_end) break;  // nothing left to produce
+        uint4 cur[kStripBatch];
+#pragma unroll
+        for (int j = 0; j < kStripBatch; ++j) {
+            const int gy = y_first + i0 + j;
+            cur[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (col_in && gy >= 0 && gy < rect_h) cur[j] = __ldcg(reinterpret_cast<const uint4*>(map + static_cast<long long>(gy) * rect_w + gx));
+        }
+#pragma unroll
+        for (int j = 0; j < kStripBatch; ++j) {
+            // key = epoch:16 | index:32 | disparity:16 -> the epoch is the top half of the high word
+            const unsigned d0 = (cur[j].y >> 16) == ep16 ? (cur[j].x & 0xffffu) : 0u;
+            const unsigned d1 = (cur[j].w >> 16) == ep16 ? (cur[j].z & 0xffffu) : 0u;
+            const unsigned pr = d0 | (d1 << 16);
+            // horizontal: cells 2l-3 .. 2l+3 = hi(l-2), pair(l-1), pair(l), pair(l+1); cells 2l-2 .. 2l+4 = pair(l-1 .. l+1), lo(l+2)
+            const unsigned m = max(d0, d1);
+            const unsigned common = max(max(__shfl_up_sync(kFull, m, 1), m), __shfl_down_sync(kFull, m, 1));
+            const unsigned ha = max(common, __shfl_up_sync(kFull, pr, 2) >> 16);
+            const unsigned hb = max(common, __shfl_down_sync(kFull, pr, 2) & 0xffffu);
+            const unsigned h = ha | (hb << 16);
+            // vertical: max of rows i-6 .. i  (m2_i = rows i-1..i, m4_i = rows i-3..i)
+            const unsigned m2 = __vmaxu2(h, h1);
+            const unsigned m4 = __vmaxu2(m2, m2b);
+            const unsigned out = __vmaxu2(m4, m4c);
+            h1 = h;
+            m2b = m2a;
+            m2a = m2;
+            m4c = m4b;
+            m4b = m4a;
+            m4a = m4;
+            const int gy = y_first + i0 + j - 3;  // the row whose window ends with row i
+            if (store_lane && i0 + j >= 6 && gy < y_end)
+                *reinterpret_cast<unsigned*>(dil + static_cast<long long>(gy) * rect_w + gx) = out;
+        }
+    }
+}
+
+// pass 2, one item = output pixels [item * kRemapItemPx, (item + 1) * kRemapItemPx) in kRemapBlocks blocks of 32 x kRemapPx,
+// as a three-stage software pipeline: cell indices of block b + 2 (static table, streamed), gathers from the dilated
+// map for block b + 1, depth-table look-ups and stores of block b.  strip_remap_begin() only touches the static table,
+// so it can run before the frame's dilated map is complete.
+struct RemapPipe {
+    unsigned c0[kRemapPx], c1[kRemapPx];  // cell indices of the next two blocks
+};
+__device__ __forceinline__ void strip_remap_cells(unsigned (&cell)[kRemapPx], const unsigned* __restrict__ pix_cell, int n_px, int first) {
+#pragma unroll
+    for (int j = 0; j < kRemapPx; ++j) {
+        cell[j] = 0xffffffffu;
+        if (first + j * 32 < n_px) cell[j] = ldg_stream_u32(pix_cell + first + j * 32);
+    }
+}
+__device__ __forceinline__ void strip_remap_begin(RemapPipe& rp, const unsigned* __restrict__ pix_cell, int n_px, int item, int lane) {
+    const int base = item * kRemapItemPx + lane;
+    strip_remap_cells(rp.c0, pix_cell, n_px, base);
+    strip_remap_cells(rp.c1, pix_cell, n_px, base + 32 * kRemapPx);
+}
+__device__ __forceinline__ void strip_remap_run(RemapPipe& rp, const OutputSpec& o, void* dst, const unsigned* __restrict__ pix_cell,
+                                                const unsigned short* __restrict__ dil, int n_px, int item, int lane) {
+    const int base = item * kRemapItemPx + lane;
+    int val[kRemapPx];
+#pragma unroll
+    for (int j = 0; j < kRemapPx; ++j) val[j] = rp.c0[j] != 0xffffffffu ? static_cast<int>(__ldcg(dil + rp.c0[j])) : 0;
+#pragma unroll 1
+    for (int b = 0; b < kRemapBlocks; ++b) {
+        // gathers of block b + 1, cell indices of block b + 3 (c0 is free once its gathers are issued)
+        int nxt[kRemapPx];
+#pragma unroll
+        for (int j = 0; j < kRemapPx; ++j) nxt[j] = (b + 1 < kRemapBlocks && rp.c1[j] != 0xffffffffu) ? static_cast<int>(__ldcg(dil + rp.c1[j])) : 0;
+#pragma unroll
+        for (int j = 0; j < kRemapPx; ++j) rp.c0[j] = rp.c1[j];
+        if (b + 2 < kRemapBlocks)
+            strip_remap_cells(rp.c1, pix_cell, n_px, base + (b + 2) * 32 * kRemapPx);
+        else {
+#pragma unroll
+            for (int j = 0; j < kRemapPx; ++j) rp.c1[j] = 0xffffffffu;
+        }
+        int idx[kRemapPx];
+        bool live[kRemapPx];
+#pragma unroll
+        for (int j = 0; j < kRemapPx; ++j) {
+            idx[j] = base + b * 32 * kRemapPx + j * 32;
+            live[j] = idx[j] < n_px;
+        }
+        emit_pixels_int<kRemapPx>(o, dst, idx, val, live);
+#pragma unroll
+        for (int j = 0; j < kRemapPx; ++j) val[j] = nxt[j];
     }
 }
 
