@@ -269,7 +269,7 @@ __device__ __forceinline__ void batch_tile_groups(const BatchParams& bp, int grp
 }
 
 // The loop of one epilogue WARP with the strip epilogue (projector view).  The pass-1 items (strip x row segment: decode
-// + 7x7 dilation into the frame's dilated map) and pass-2 items (kRemapItemPx output pixels) of ALL frames form one
+// + 7x7 dilation into the frame's dilated map) and pass-2 items (a run of output pixels) of ALL frames form one
 // ordered list -- frame 0 pass 1, frame 0 pass 2, frame 1 pass 1, ... -- handed out by a global counter, so warps do not
 // march through the frames in step: with small frames the items of several frames are in flight at the same time.
 // A pass-1 item waits for its frame's chunks (and for pass 2 of the frame that used the same dilated map), a pass-2
@@ -342,7 +342,8 @@ __device__ __forceinline__ void batch_strip_warps(const BatchParams& bp, int lan
             const int seg = j / n_strips;
             if (!(bp.debug & 16))
                 strip_dilate_item(bp.maps[f % bp.n_maps], dil, bp.rect_w, bp.rect_h, bp.epoch0 + static_cast<unsigned>(f),
-                                  bp.win.x0 + (j - seg * n_strips) * kStripCols, bp.win.y0 + seg * kStripRows, bp.win.y1, lane);
+                                  bp.win.x0 + (j - seg * n_strips) * kStripCols, bp.win.y0 + seg * bp.win.rows,
+                                  min(bp.win.y0 + (seg + 1) * bp.win.rows, bp.win.y1), lane);
             __syncwarp();
             XM_STRIP_CLK(c3);
             if (lane == 0) {
@@ -351,11 +352,11 @@ __device__ __forceinline__ void batch_strip_warps(const BatchParams& bp, int lan
             }
         } else {
             RemapPipe rp;
-            strip_remap_begin(rp, bp.pix_cell, n_px, j - n_p1, lane);  // (static table: requested before the wait)
+            strip_remap_begin(rp, bp.pix_cell, n_px, (j - n_p1) * bp.win.blocks * kRemapBlockPx, lane);  // (static table: requested before the wait)
             if (lane == 0) wait_for(&st->next_tile, static_cast<unsigned>(n_p1));
             __syncwarp();
             XM_STRIP_CLK(c2);
-            if (!(bp.debug & 16)) strip_remap_run(rp, bp.ep.out, bp.frames[f].dst, bp.pix_cell, dil, n_px, j - n_p1, lane);
+            if (!(bp.debug & 16)) strip_remap_run(rp, bp.ep.out, bp.frames[f].dst, bp.pix_cell, dil, n_px, (j - n_p1) * bp.win.blocks * kRemapBlockPx, bp.win.blocks, lane);
             __syncwarp();
             XM_STRIP_CLK(c3);
             if (lane == 0) {
@@ -536,8 +537,13 @@ static __device__ __noinline__ unsigned batch_front_general(const BatchParams& b
 
 // AGG: the instantiation whose dense chunks aggregate their scatter per warp round (see XM_BACK_PTX_*).  A second
 // instantiation rather than a run-time switch: the mere presence of the second PTX block costs the plain path 1.6 %.
-template <bool CAM, bool AGG = false>
-__global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(const __grid_constant__ BatchParams bp) {
+// TW: epilogue warps per CTA.  The strip epilogue of large frames needs only two (it waits most of the time), which
+// leaves the per-event loop 80 registers instead of 72; small frames, whose pace the epilogue sets, take four.
+constexpr int kTileWarpsLarge = 2;
+template <bool CAM, bool AGG = false, int TW = kTileWarps>
+__global__ void __launch_bounds__(kWsThreads + TW * 32, kBatchCtasPerSm) batch_kernel(const __grid_constant__ BatchParams bp) {
+    constexpr int kGroups = TW * 32 / kTileGroupThreads;
+    constexpr int kThreads = kWsThreads + TW * 32;
     extern __shared__ __align__(128) unsigned char ev_smem[];
     uint64_t* full_ev = reinterpret_cast<uint64_t*>(ev_smem);
     uint64_t* empty_ev = reinterpret_cast<uint64_t*>(ev_smem + 32);
@@ -568,8 +574,8 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm) batch_kernel(c
         }
     }
     if (tid < 32) s_acc[tid] = 0u;
-    unsigned* const s_alive = reinterpret_cast<unsigned*>(win_ring + bp.win_stages * win_bytes + kTileGroups * bp.ep.region_cap * 4);
-    for (int i = tid; i < bp.alive_words; i += kBatchThreads) s_alive[i] = __ldg(bp.alive + i);
+    unsigned* const s_alive = reinterpret_cast<unsigned*>(win_ring + bp.win_stages * win_bytes + kGroups * bp.ep.region_cap * 4);
+    for (int i = tid; i < bp.alive_words; i += kThreads) s_alive[i] = __ldg(bp.alive + i);
     __syncthreads();
 
     if (warp > kEvThreads / 32) {

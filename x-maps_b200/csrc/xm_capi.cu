@@ -97,7 +97,9 @@ struct XmCtx {
     // strip epilogue of the batch kernel (projector view): per-pixel cell index table and the dilated-map ring
     unsigned* d_pix_cell = nullptr;
     unsigned short* d_dil = nullptr;  // kBatchDilMaps x rect_w x rect_h
-    xm::StripWindow strip_win = {};
+    int strip_box[4] = {0, 0, 0, 0};  // bounding box of the remap targets (inclusive): the window pass 1 produces
+    int opt_tile_warps = 0;  // epilogue warps per CTA of the strip epilogue: 0 = auto, 2 or 4
+    int opt_strip_rows = 0, opt_strip_blocks = 0;  // item sizes of the strip epilogue (0 = auto: by events per frame)
     int opt_batch_strips = 1;
     int opt_scatter_aggregate = 2;  // batch kernel: 0 plain scatter, 1 aggregate dense chunks per warp round, 2 auto (from the last batch's inlier fraction)
     bool agg_dense = false, agg_pending = false;
@@ -337,6 +339,10 @@ int configure_event_kernels(XmCtx* c) {
             void (*k)(xm::BatchParams) = cam ? xm::batch_kernel<true> : xm::batch_kernel<false>;
             XM_CUDA(cudaFuncSetAttribute(xm::batch_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          optin - static_cast<int>(fa_static_bytes(xm::batch_kernel<false, true>))));
+            XM_CUDA(cudaFuncSetAttribute(xm::batch_kernel<false, false, xm::kTileWarpsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         optin - static_cast<int>(fa_static_bytes(xm::batch_kernel<false, false, xm::kTileWarpsLarge>))));
+            XM_CUDA(cudaFuncSetAttribute(xm::batch_kernel<false, true, xm::kTileWarpsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         optin - static_cast<int>(fa_static_bytes(xm::batch_kernel<false, true, xm::kTileWarpsLarge>))));
             cudaFuncAttributes fa;
             XM_CUDA(cudaFuncGetAttributes(&fa, k));
             const int dyn = optin - static_cast<int>(fa.sharedSizeBytes);
@@ -885,15 +891,24 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     bp.tiles_x = tiles_x;
     bp.tile_items = cam ? (c->cam_w * c->cam_h + xm::kCamTilePx - 1) / xm::kCamTilePx : tiles_x * tiles_y;
     long long epi_items = (static_cast<long long>(bp.tile_items) + xm::kTileGroups - 1) / xm::kTileGroups;  // per CTA and round
+    int tile_warps = xm::kTileWarps;  // epilogue warps per CTA (strip epilogue of large frames: kTileWarpsLarge)
     if (!cam && c->opt_batch_strips && c->d_pix_cell) {
         if (!c->d_dil) XM_CUDA(cudaMalloc(&c->d_dil, static_cast<size_t>(xm::kBatchDilMaps) * c->rect_w * c->rect_h * sizeof(unsigned short)));
         bp.strips = 1;
         bp.pix_cell = c->d_pix_cell;
         for (int i = 0; i < xm::kBatchDilMaps; ++i) bp.dil[i] = c->d_dil + static_cast<size_t>(i) * c->rect_w * c->rect_h;
-        bp.win = c->strip_win;
-        bp.tile_items = c->strip_win.items;
-        bp.p2_items = static_cast<int>((static_cast<long long>(c->proj_w) * c->proj_h + xm::kRemapItemPx - 1) / xm::kRemapItemPx);
+        // item sizes: large frames leave the epilogue warps plenty of slack -> few large items; small frames are a latency chain
+        long long ev_total = 0;
+        for (int f = 0; f < n; ++f) ev_total += a[f].n_events;
+        const bool large = ev_total > 3000000LL * n;
+        const int rows = c->opt_strip_rows > 0 ? c->opt_strip_rows : (large ? 2 * xm::kStripRows + 6 : xm::kStripRows);
+        const int blocks = c->opt_strip_blocks > 0 ? c->opt_strip_blocks : (large ? 2 * xm::kRemapBlocks : xm::kRemapBlocks);
+        bp.win = xm::strip_window(c->strip_box[0], c->strip_box[1], c->strip_box[2], c->strip_box[3], rows, blocks);
+        bp.tile_items = bp.win.items;
+        const long long item_px = static_cast<long long>(blocks) * xm::kRemapBlockPx;
+        bp.p2_items = static_cast<int>((static_cast<long long>(c->proj_w) * c->proj_h + item_px - 1) / item_px);
         epi_items = (bp.tile_items + bp.p2_items + xm::kTileWarps - 1) / xm::kTileWarps;
+        tile_warps = c->opt_tile_warps > 0 ? c->opt_tile_warps : (large ? xm::kTileWarpsLarge : xm::kTileWarps);
     }
     bp.n_frames = n;
     bp.debug = c->opt_debug;
@@ -934,7 +949,12 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     bp.hard_frames = static_cast<long long>(items) < 8LL * n * grid ? 1 : 0;
     // scatter maps in rotation: a frame holds its map from its first chunk to the end of its epilogue's reads; with small
     // frames that latency, not the work, sets the pace, so more frames are kept in flight
-    bp.n_maps = c->opt_batch_maps > 0 ? c->opt_batch_maps : (bp.hard_frames ? 6 : xm::kBatchMaps);
+    {
+        long long ev_total = 0;
+        for (int f = 0; f < n; ++f) ev_total += a[f].n_events;
+        const int auto_maps = ev_total <= 1500000LL * n ? 6 : (bp.hard_frames ? 4 : xm::kBatchMaps);  // (measured: profiles/EXPERIMENTS_r02.md)
+        bp.n_maps = c->opt_batch_maps > 0 ? c->opt_batch_maps : auto_maps;
+    }
     for (int i = 1; i < bp.n_maps; ++i)
         if (!c->d_map_ring[i]) {
             XM_CUDA(cudaMalloc(&c->d_map_ring[i], static_cast<size_t>(c->map_cells) * 8));
@@ -955,6 +975,10 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     const bool agg = !cam && (c->opt_scatter_aggregate == 1 || (c->opt_scatter_aggregate == 2 && c->agg_dense));
     if (cam)
         xm::batch_kernel<true><<<grid, xm::kBatchThreads, c->batch_smem[1], s>>>(bp);
+    else if (tile_warps == xm::kTileWarpsLarge && agg)
+        xm::batch_kernel<false, true, xm::kTileWarpsLarge><<<grid, xm::kWsThreads + xm::kTileWarpsLarge * 32, c->batch_smem[0], s>>>(bp);
+    else if (tile_warps == xm::kTileWarpsLarge)
+        xm::batch_kernel<false, false, xm::kTileWarpsLarge><<<grid, xm::kWsThreads + xm::kTileWarpsLarge * 32, c->batch_smem[0], s>>>(bp);
     else if (agg)
         xm::batch_kernel<false, true><<<grid, xm::kBatchThreads, c->batch_smem[0], s>>>(bp);
     else
@@ -1177,7 +1201,10 @@ int xm_ctx_create(const XmTables* t, int device, XmCtx** out) {
                 by1 = my > by1 ? my : by1;
             }
             if (bx1 < 0) bx0 = by0 = bx1 = by1 = 0;  // no pixel maps into the rectified image: one (empty) item
-            c->strip_win = xm::strip_window(bx0, by0, bx1, by1);
+            c->strip_box[0] = bx0;
+            c->strip_box[1] = by0;
+            c->strip_box[2] = bx1;
+            c->strip_box[3] = by1;
             if (cudaMalloc(&c->d_pix_cell, cells.size() * sizeof(unsigned)) != cudaSuccess ||
                 cudaMemcpy(c->d_pix_cell, cells.data(), cells.size() * sizeof(unsigned), cudaMemcpyHostToDevice) != cudaSuccess)
                 return bail(fail(XM_ERR_CUDA, "uploading the pixel cell table failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -1357,6 +1384,16 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         c->opt_batch_strips = v != 0;
         return c->d_xmap_t ? configure_event_kernels(c) : XM_OK;  // the batch kernel's shared memory depends on it
     }
+    if (!strcmp(key, "strip_rows") || !strcmp(key, "strip_blocks")) { /* item sizes of the strip epilogue (0 = auto) */
+        if (v < 0 || v > 4096) return fail(XM_ERR_INVALID_ARG, "%s out of range", key);
+        (key[6] == 'r' ? c->opt_strip_rows : c->opt_strip_blocks) = v;
+        return XM_OK;
+    }
+    if (!strcmp(key, "tile_warps")) { /* epilogue warps per CTA of the batch kernel's strip epilogue: 0 = auto (2 for large frames), 2, 4 */
+        if (v != 0 && v != xm::kTileWarpsLarge && v != xm::kTileWarps) return fail(XM_ERR_INVALID_ARG, "tile_warps must be 0, %d or %d", xm::kTileWarpsLarge, xm::kTileWarps);
+        c->opt_tile_warps = v;
+        return XM_OK;
+    }
     if (!strcmp(key, "batch_maps")) { /* scatter maps the batch kernel rotates through (0 = auto) */
         if (v < 0 || v == 1 || v > xm::kBatchMapsMax) return fail(XM_ERR_INVALID_ARG, "batch_maps must be 0 or 2 ... %d", xm::kBatchMapsMax);
         c->opt_batch_maps = v;
@@ -1430,6 +1467,9 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     else if (!strcmp(key, "tile_off")) *value = c->opt_tile_off;
     else if (!strcmp(key, "batch_strips")) *value = c->opt_batch_strips;
     else if (!strcmp(key, "batch_maps")) *value = c->opt_batch_maps;
+    else if (!strcmp(key, "strip_rows")) *value = c->opt_strip_rows;
+    else if (!strcmp(key, "tile_warps")) *value = c->opt_tile_warps;
+    else if (!strcmp(key, "strip_blocks")) *value = c->opt_strip_blocks;
     else if (!strcmp(key, "scatter_aggregate")) *value = c->opt_scatter_aggregate;
     else if (!strcmp(key, "scatter_aggregate_now")) *value = c->agg_dense ? 1 : 0;  /* read-only: what "auto" currently selects */
     else if (!strcmp(key, "coop")) *value = c->opt_coop;

@@ -1493,26 +1493,30 @@ constexpr int kStripCols = 56;   // cells a strip produces per row
 #ifndef XM_REMAP_BLOCKS
 #define XM_REMAP_BLOCKS 8
 #endif
-constexpr int kStripRows = XM_STRIP_ROWS;    // rows a pass-1 item produces (it reads kStripRows + 6)
-constexpr int kStripBatch = XM_STRIP_BATCH;  // rows whose key loads are in flight together: an item costs (kStripRows + 6) / kStripBatch L2 round trips
+// Item sizes are chosen per launch (StripWindow::rows / ::blocks): small items for small frames, whose epilogue is a
+// latency chain (more items in flight), large ones for large frames (fewer tickets, waits and fences).
+constexpr int kStripRows = XM_STRIP_ROWS;    // default rows a pass-1 item produces (it reads rows + 6)
+constexpr int kStripBatch = XM_STRIP_BATCH;  // rows whose key loads are in flight together: an item costs (rows + 6) / kStripBatch L2 round trips
 constexpr int kRemapPx = XM_REMAP_PX;        // output pixels per lane and block of a pass-2 item
-constexpr int kRemapBlocks = XM_REMAP_BLOCKS;  // blocks per pass-2 item (software-pipelined: cell indices two blocks ahead, gathers one)
-constexpr int kRemapItemPx = 32 * kRemapPx * kRemapBlocks;  // output pixels of a pass-2 item
-static_assert((kStripRows + 6) % kStripBatch == 0, "a pass-1 item is a whole number of row batches");
+constexpr int kRemapBlocks = XM_REMAP_BLOCKS;  // default blocks per pass-2 item (software-pipelined: cell indices two blocks ahead, gathers one)
+constexpr int kRemapBlockPx = 32 * kRemapPx;   // output pixels of a block
 
 // The window of the rectified image pass 1 has to produce: the bounding box of the remap targets (x0 rounded down to even).
 struct StripWindow {
     int x0, y0, x1, y1;  // cells [x0, x1) x [y0, y1); x0 even
+    int rows, blocks;    // rows per pass-1 item, blocks per pass-2 item
     int strips, items;   // strips across, pass-1 items (strips x row segments)
 };
-inline StripWindow strip_window(int bx0, int by0, int bx1, int by1) {  // inclusive bounding box
+inline StripWindow strip_window(int bx0, int by0, int bx1, int by1, int rows, int blocks) {  // inclusive bounding box
     StripWindow w;
     w.x0 = bx0 & ~1;
     w.y0 = by0;
     w.x1 = bx1 + 1;
     w.y1 = by1 + 1;
+    w.rows = rows;
+    w.blocks = blocks;
     w.strips = (w.x1 - w.x0 + kStripCols - 1) / kStripCols;
-    w.items = w.strips * ((w.y1 - w.y0 + kStripRows - 1) / kStripRows);
+    w.items = w.strips * ((w.y1 - w.y0 + rows - 1) / rows);
     return w;
 }
 
@@ -1522,7 +1526,7 @@ __device__ __forceinline__ unsigned ldg_stream_u32(const unsigned* p) {
     return v;
 }
 
-// pass 1, one item: output cells [x_out, x_out + 56) x [y_out, min(y_out + kStripRows, y_end)); x_out even
+// pass 1, one item: output cells [x_out, x_out + 56) x [y_out, y_end); x_out even
 __device__ __forceinline__ void strip_dilate_item(const unsigned long long* __restrict__ map, unsigned short* __restrict__ dil, int rect_w,
                                                   int rect_h, unsigned epoch, int x_out, int y_out, int y_end, int lane) {
     constexpr unsigned kFull = 0xffffffffu;
@@ -1533,8 +1537,7 @@ __device__ __forceinline__ void strip_dilate_item(const unsigned long long* __re
     const int y_first = y_out - 3;  // first row read
     unsigned h1 = 0u, m2a = 0u, m2b = 0u, m4a = 0u, m4b = 0u, m4c = 0u;  // sliding window: rows i-1 (h, m2, m4), i-2 (m2, m4), i-3 (m4)
 #pragma unroll 1
-    for (int i0 = 0; i0 < kStripRows + 6; i0 += kStripBatch) {
-        if (y_first + i0 - 3 >= y_end) break;  // nothing left to produce
+    for (int i0 = 0; y_first + i0 - 3 < y_end; i0 += kStripBatch) {  // (the batch's last row is the window end of output row y_first + i0 + kStripBatch - 4)
         uint4 cur[kStripBatch];
 #pragma unroll
         for (int j = 0; j < kStripBatch; ++j) {
@@ -1571,7 +1574,7 @@ __device__ __forceinline__ void strip_dilate_item(const unsigned long long* __re
     }
 }
 
-// pass 2, one item = output pixels [item * kRemapItemPx, (item + 1) * kRemapItemPx) in kRemapBlocks blocks of 32 x kRemapPx,
+// pass 2, one item = output pixels [first, first + blocks * kRemapBlockPx) in blocks of 32 x kRemapPx,
 // as a three-stage software pipeline: cell indices of block b + 2 (static table, streamed), gathers from the dilated
 // map for block b + 1, depth-table look-ups and stores of block b.  strip_remap_begin() only touches the static table,
 // so it can run before the frame's dilated map is complete.
@@ -1585,27 +1588,27 @@ __device__ __forceinline__ void strip_remap_cells(unsigned (&cell)[kRemapPx], co
         if (first + j * 32 < n_px) cell[j] = ldg_stream_u32(pix_cell + first + j * 32);
     }
 }
-__device__ __forceinline__ void strip_remap_begin(RemapPipe& rp, const unsigned* __restrict__ pix_cell, int n_px, int item, int lane) {
-    const int base = item * kRemapItemPx + lane;
+__device__ __forceinline__ void strip_remap_begin(RemapPipe& rp, const unsigned* __restrict__ pix_cell, int n_px, int first, int lane) {
+    const int base = first + lane;
     strip_remap_cells(rp.c0, pix_cell, n_px, base);
-    strip_remap_cells(rp.c1, pix_cell, n_px, base + 32 * kRemapPx);
+    strip_remap_cells(rp.c1, pix_cell, n_px, base + kRemapBlockPx);
 }
 __device__ __forceinline__ void strip_remap_run(RemapPipe& rp, const OutputSpec& o, void* dst, const unsigned* __restrict__ pix_cell,
-                                                const unsigned short* __restrict__ dil, int n_px, int item, int lane) {
-    const int base = item * kRemapItemPx + lane;
+                                                const unsigned short* __restrict__ dil, int n_px, int first, int blocks, int lane) {
+    const int base = first + lane;
     int val[kRemapPx];
 #pragma unroll
     for (int j = 0; j < kRemapPx; ++j) val[j] = rp.c0[j] != 0xffffffffu ? static_cast<int>(__ldcg(dil + rp.c0[j])) : 0;
 #pragma unroll 1
-    for (int b = 0; b < kRemapBlocks; ++b) {
+    for (int b = 0; b < blocks; ++b) {
         // gathers of block b + 1, cell indices of block b + 3 (c0 is free once its gathers are issued)
         int nxt[kRemapPx];
 #pragma unroll
-        for (int j = 0; j < kRemapPx; ++j) nxt[j] = (b + 1 < kRemapBlocks && rp.c1[j] != 0xffffffffu) ? static_cast<int>(__ldcg(dil + rp.c1[j])) : 0;
+        for (int j = 0; j < kRemapPx; ++j) nxt[j] = (b + 1 < blocks && rp.c1[j] != 0xffffffffu) ? static_cast<int>(__ldcg(dil + rp.c1[j])) : 0;
 #pragma unroll
         for (int j = 0; j < kRemapPx; ++j) rp.c0[j] = rp.c1[j];
-        if (b + 2 < kRemapBlocks)
-            strip_remap_cells(rp.c1, pix_cell, n_px, base + (b + 2) * 32 * kRemapPx);
+        if (b + 2 < blocks)
+            strip_remap_cells(rp.c1, pix_cell, n_px, base + (b + 2) * kRemapBlockPx);
         else {
 #pragma unroll
             for (int j = 0; j < kRemapPx; ++j) rp.c1[j] = 0xffffffffu;
@@ -1614,7 +1617,7 @@ __device__ __forceinline__ void strip_remap_run(RemapPipe& rp, const OutputSpec&
         bool live[kRemapPx];
 #pragma unroll
         for (int j = 0; j < kRemapPx; ++j) {
-            idx[j] = base + b * 32 * kRemapPx + j * 32;
+            idx[j] = base + b * kRemapBlockPx + j * 32;
             live[j] = idx[j] < n_px;
         }
         emit_pixels_int<kRemapPx>(o, dst, idx, val, live);
