@@ -270,13 +270,13 @@ __device__ __forceinline__ void batch_tile_groups(const BatchParams& bp, int grp
 
 // The loop of one epilogue WARP with the strip epilogue (projector view).  The pass-1 items (strip x row segment: decode
 // + 7x7 dilation into the frame's dilated map) and pass-2 items (a run of output pixels) of ALL frames form one
-// ordered list -- frame 0 pass 1, frame 0 pass 2, frame 1 pass 1, ... -- handed out by a global counter, so warps do not
-// march through the frames in step: with small frames the items of several frames are in flight at the same time.
-// A pass-1 item waits for its frame's chunks (and for pass 2 of the frame that used the same dilated map), a pass-2
-// item for the frame's finished pass-1 count.  The scatter map is free as soon as pass 1 is complete (`next_tile`
-// counts finished pass-1 items: what the event warps of frame f + n_maps wait for).  Every wait is for items that
-// come earlier in the list (or for event work that only depends on such items), an item is only ever held by a warp
-// that will run it, and the look-ahead ticket is run right after the current item, so this cannot deadlock.
+// ordered list handed out by a global counter, so warps do not march through the frames in step: with small frames
+// the items of several frames are in flight at the same time.  A pass-1 item waits for its frame's chunks (and for
+// pass 2 of the frame that used the same dilated map), a pass-2 item for the frame's finished pass-1 count.  The
+// scatter map is free as soon as pass 1 is complete (`next_tile` counts finished pass-1 items: what the event warps of
+// frame f + n_maps wait for).  Every wait is for items that come earlier in the list (or for event work that only
+// depends on such items) and an item is only ever held by a warp that is running it or waiting to, so this cannot
+// deadlock (tests/test_batch_protocol_model.py models it, with a negative control).
 template <int CHUNK>
 __device__ __forceinline__ void batch_strip_warps(const BatchParams& bp, int lane) {
     constexpr unsigned kFull = 0xffffffffu;
@@ -296,20 +296,18 @@ __device__ __forceinline__ void batch_strip_warps(const BatchParams& bp, int lan
 #else
 #define XM_STRIP_CLK(v)
 #endif
-#ifndef XM_STRIP_LOOKAHEAD
-#define XM_STRIP_LOOKAHEAD 0
-#endif
     // List order: pass 1 of frame 0, then blocks of (pass 1 of frame g, pass 2 of frame g - 1), then pass 2 of the last
     // frame: by the time a warp reaches the pass-2 items of a frame, that frame's pass 1 has had a block's worth of
     // items to complete, so warps spend their time on items that can run instead of holding items that cannot.
+    // (No look-ahead ticket: a warp that held its next item while working on the current one kept that item from every
+    // other warp -- with small frames a serial chain pass 2 (f) -> pass 1 (f + 1) through the warps, 31 us per frame
+    // instead of 14.)
     unsigned ticket = 0;
-    if (XM_STRIP_LOOKAHEAD && lane == 0) ticket = atomicAdd(counter, 1u);
     for (;;) {
         XM_STRIP_CLK(c0);
-        if (!XM_STRIP_LOOKAHEAD && lane == 0) ticket = atomicAdd(counter, 1u);
+        if (lane == 0) ticket = atomicAdd(counter, 1u);
         const unsigned t = __shfl_sync(kFull, ticket, 0);
         if (t >= total) break;
-        if (XM_STRIP_LOOKAHEAD && lane == 0) ticket = atomicAdd(counter, 1u);
         XM_STRIP_CLK(c1);
         int f, j;  // frame, item (j < n_p1: pass 1, else pass 2 item j - n_p1)
         if (t < static_cast<unsigned>(n_p1)) {

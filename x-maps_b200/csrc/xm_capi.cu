@@ -900,7 +900,11 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
         // item sizes: large frames leave the epilogue warps plenty of slack -> few large items; small frames are a latency chain
         long long ev_total = 0;
         for (int f = 0; f < n; ++f) ev_total += a[f].n_events;
-        const bool large = ev_total > 3000000LL * n;
+        // "large": the event stream of a frame outweighs its epilogue (window cells + output pixels) -- measured cross-over
+        // on the default geometry (1.7 M cells + pixels) at ~3 M events per frame
+        const long long epi_units = static_cast<long long>(c->strip_box[2] - c->strip_box[0] + 1) * (c->strip_box[3] - c->strip_box[1] + 1) +
+                                    static_cast<long long>(c->proj_w) * c->proj_h;
+        const bool large = 4 * ev_total > 7 * epi_units * n;
         const int rows = c->opt_strip_rows > 0 ? c->opt_strip_rows : (large ? 2 * xm::kStripRows + 6 : xm::kStripRows);
         const int blocks = c->opt_strip_blocks > 0 ? c->opt_strip_blocks : (large ? 2 * xm::kRemapBlocks : xm::kRemapBlocks);
         bp.win = xm::strip_window(c->strip_box[0], c->strip_box[1], c->strip_box[2], c->strip_box[3], rows, blocks);
