@@ -169,6 +169,13 @@ int xm_ctx_set_colormap(XmCtx* ctx, const uint8_t* h_bgr256);
  *                     distinct cell and warp round (pays on a scanning projector's stream, where consecutive events
  *                     share pixels; costs 25 % on a uniform stream), 0 = plain scatter, 2 = decide from the inlier
  *                     fraction of the last batch whose statistics reached the host (asynchronous)       [2]
+ *   "batch_strips"    batch kernel, projector view: 1 = strip epilogue (two barrier-free passes, one warp per item:
+ *                     decode + 7x7 dilation of the remap targets' window into a u16 map, then one gather per output
+ *                     pixel), 0 = tile epilogue (32x32 output tiles through shared memory).  Identical results    [1]
+ *   "batch_maps"      scatter maps the batch kernel rotates through, 2 ... 8; 0 = by events per frame (3 / 4 / 6)  [0]
+ *   "tile_warps"      epilogue warps per CTA of the strip epilogue: 2, 4; 0 = two for large frames, four for small [0]
+ *   "strip_rows", "strip_blocks"  item sizes of the strip epilogue (rows per pass-1 item, 256-pixel blocks per pass-2
+ *                     item); 0 = 42 / 8 for small frames, 90 / 16 for large ones                                [0]
  *   "reserve_sms"     SMs the persistent batch kernel leaves free (e.g. for NCCL's copy kernels)  [0]
  *   "ctas_per_sm"     resident CTAs per SM for the event kernel, 0 = occupancy query            [0]
  *   "region_cells"    shared-memory cells per buffer of the projector-view epilogue [largest tile region of
