@@ -33,6 +33,12 @@ FILES = [
     ("python/proj_time_map.py", "proj_time_map.py"),
     ("python/x_map.py", "x_map.py"),
     ("data/ESL_calib_hhi.yaml", "ESL_calib_hhi.yaml"),
+    # The reference's per-frame driver and the two helper modules it imports, in a directory of their own
+    # (oracle/_ref/pipe): tests/test_gpu_pipeline.py puts the drop-in modules AHEAD of it on sys.path and runs the
+    # unmodified DepthReprojectionPipe.process_ev_frame / process_events body over the CUDA path.
+    ("python/depth_reprojection_pipe.py", "pipe/depth_reprojection_pipe.py"),
+    ("python/timing_watchdog.py", "pipe/timing_watchdog.py"),
+    ("python/event_buf_pool.py", "pipe/event_buf_pool.py"),
 ]
 
 
@@ -46,6 +52,7 @@ def build(verbose=False):
     digest = {}
     for src, dst in FILES:
         a, b = os.path.join(REF_ROOT, src), os.path.join(OUT, dst)
+        os.makedirs(os.path.dirname(b), exist_ok=True)
         shutil.copyfile(a, b)
         os.chmod(b, 0o644)
         with open(b, "rb") as fh:

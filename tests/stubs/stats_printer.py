@@ -36,7 +36,10 @@ class StatsPrinter:
         pass
 
     def reset(self):
-        pass
+        self._t0 = time.perf_counter_ns()
+
+    def start_time_ns(self):
+        return getattr(self, "_t0", time.perf_counter_ns())
 
 
 class SingleTimer:

@@ -51,6 +51,70 @@ def test_process_ev_frame_matches_reference(pipes):
     assert np.array_equal(depth, golden_frame("default_100k_proj")["depth"])
 
 
+def test_unmodified_reference_pipe_renders_on_the_gpu():
+    """The reference's OWN `DepthReprojectionPipe` (python/depth_reprojection_pipe.py, copied unmodified to
+    oracle/_ref/pipe by oracle/build_ref.py) with the drop-in modules ahead of it on sys.path: its `__post_init__`
+    builds the calibration / X-map / depth objects through our classes, its `process_ev_frame` body (:121-167) renders
+    on the CUDA path, and its `process_events` (:108-119) feeds our trigger finder, which calls back into it.  Runs in a
+    subprocess so that the reference's module names do not leak into the test session."""
+    import subprocess
+    import sys
+
+    pipe_dir = os.path.join(ROOT, "oracle", "_ref", "pipe")
+    if not os.path.exists(os.path.join(pipe_dir, "depth_reprojection_pipe.py")):
+        pytest.skip("oracle/_ref/pipe not built (python -c 'import __graft_entry__ as g; g.build()' where /root/reference exists)")
+    code = f"""
+import numpy as np
+from types import SimpleNamespace
+import depth_reprojection_pipe as D
+assert D.__file__.startswith({pipe_dir!r}), D.__file__
+import xmaps_b200.calibration as C, xmaps_b200.disparity as X, xmaps_b200.depth as Z, xmaps_b200.trigger_finder as T
+assert D.CamProjMaps is C.CamProjMaps and D.XMapsDisparity is X.XMapsDisparity and D.DisparityToDepth is Z.DisparityToDepth
+assert D.RobustTriggerFinder is T.RobustTriggerFinder
+from stats_printer import StatsPrinter
+from oracle import xmaps_oracle as orc
+from xm_helpers import golden_frame
+from xmaps_b200 import _native
+evs = orc.polarity_mask(orc.synth_events(0, 100_000, 640, 480))
+for cam, key in ((False, "default_100k_proj"), (True, "default_100k_cam")):
+    params = SimpleNamespace(camera_width=640, camera_height=480, projector_width=720, projector_height=1280, projector_fps=60,
+                             z_near=0.1, z_far=1.0, calib={CALIB!r}, projector_time_map=None, no_frame_dropping=True,
+                             camera_perspective=cam, should_drop_frames=False)
+    got = []
+    pipe = D.DepthReprojectionPipe(params=params, stats_printer=StatsPrinter(), frame_callback=got.append)
+    n0 = _native.launch_count()
+    pipe.process_ev_frame(evs)
+    assert _native.launch_count() > n0, "no kernel of the library was launched"
+    assert len(got) == 1 and np.array_equal(np.asarray(got[0]), golden_frame(key)["bgr"]), key
+# the de-duplication filters the pipe rotates through (:164-166): NoFilter -> FirstEventPerYT -> FirstEventPerXY
+# (`ev_filter_proc` is a CLASS attribute of the reference's pipe, shared by all instances; the YT filter's key image
+# does not cover every pixel of a uniform frame, in the reference neither)
+pipe.select_next_frame_event_filter()
+pipe.select_next_frame_event_filter()
+pipe.process_ev_frame(evs)
+assert len(got) == 2 and np.asarray(got[1]).shape == np.asarray(got[0]).shape
+# the stream entry point (:108-119): a projector stream with pauses between the frames, in packets -> polarity and
+# activity filter (Metavision stand-ins), our trigger finder, which calls the reference's process_ev_frame per frame
+from stream_cases import chunked
+stream = orc.synth_projector_stream(5, 12, 20_000, 640, 480)
+frames = []
+otf = orc.TriggerFinderOracle(60, frames.append)
+got.clear()
+pipe.reset()
+for part in chunked(stream, [23_000, 12_000, 28_000]):
+    otf.process_events(part)
+    pipe.process_events(part)
+assert len(got) == len(frames) >= 8, (len(got), len(frames))
+assert all(np.asarray(g).shape == (480, 640, 3) for g in got)  # (the last pipe renders the camera view)
+print("rendered", len(got))
+"""
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([ROOT, os.path.join(ROOT, "x-maps_b200", "dropin"), os.path.join(ROOT, "tests", "stubs"), pipe_dir,
+                                         os.path.join(ROOT, "tests")])
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "rendered" in out.stdout, (out.stdout[-500:], out.stderr[-3000:])
+
+
 def test_lazy_handles_materialise(pipes):
     proj, _ = pipes
     g = golden_frame("default_100k_proj")
