@@ -537,7 +537,10 @@ static __device__ __noinline__ unsigned batch_front_general(const BatchParams& b
 // instantiation rather than a run-time switch: the mere presence of the second PTX block costs the plain path 1.6 %.
 // TW: epilogue warps per CTA.  The strip epilogue of large frames needs only two (it waits most of the time), which
 // leaves the per-event loop 80 registers instead of 72; small frames, whose pace the epilogue sets, take four.
-constexpr int kTileWarpsLarge = 2;
+#ifndef XM_TILE_WARPS_LARGE
+#define XM_TILE_WARPS_LARGE 2
+#endif
+constexpr int kTileWarpsLarge = XM_TILE_WARPS_LARGE;
 template <bool CAM, bool AGG = false, int TW = kTileWarps>
 __global__ void __launch_bounds__(kWsThreads + TW * 32, kBatchCtasPerSm) batch_kernel(const __grid_constant__ BatchParams bp) {
     constexpr int kGroups = TW * 32 / kTileGroupThreads;
