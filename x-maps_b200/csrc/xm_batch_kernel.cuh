@@ -8,22 +8,26 @@
 //         consumer warps, mbarrier ring fed by TMA bulk copies of the chunks and of their X-map windows).
 //         All chunks of the batch form ONE ordered list handed out by a global counter; the producer takes
 //         its chunks TWO ahead and reads a chunk's first / last timestamp ONE ahead;
-//       - kTileWarps epilogue warps in groups of kTileGroupThreads threads.  A group takes 32x32 output
-//         tiles (camera view: 4096 pixels) of frame f from that frame's ticket counter as soon as every
-//         chunk of frame f has been scattered, then moves on to frame f+1.
+//       - the epilogue warps (two for large frames, four for small ones).  Projector view, default: the STRIP
+//         epilogue -- two barrier-free passes per frame, one warp per item (pass 1: decode + 7x7 dilation of the
+//         remap targets' window into a small u16 map; pass 2: one gather per output pixel), the items of all
+//         frames in one ordered list handed out by a global counter (batch_strip_warps).  Otherwise (camera view,
+//         `batch_strips = 0`): groups of kTileGroupThreads threads take 32x32 output tiles (camera view: 4096
+//         pixels) of frame f from that frame's ticket counter, then move on to frame f+1 (batch_tile_groups).
+//         Either way an item of frame f starts as soon as every chunk of frame f has been scattered.
 //     So the epilogue of a frame runs on the same SMs, at the same time, as the event stream of the next
-//     frames: HBM streaming, L2 gathers and the shared-memory dilation overlap instead of alternating, and
-//     there is no launch, drain or pipeline fill per frame.  (A first version let the eight consumer warps
-//     execute the tiles in line: a tile is a chain of four barrier-separated phases, ~8 us during which
-//     the CTA's event stream stood still -- slower than separate kernels, see EXPERIMENTS_r01.md.)
+//     frames: HBM streaming, L2 gathers and the dilation overlap instead of alternating, and there is no
+//     launch, drain or pipeline fill per frame.  (A first version let the eight consumer warps execute the
+//     tiles in line: a tile is a chain of four barrier-separated phases, ~8 us during which the CTA's event
+//     stream stood still -- slower than separate kernels, see EXPERIMENTS_r01.md.)
 //   * A tile of frame f may only read the scatter map once every chunk of frame f has been scattered.
 //     Each CTA counts the chunks it finished per frame and publishes the count (after a fence) when its
 //     consumers leave the frame; the tile groups spin on the frame's count.  A chunk only ever waits for
 //     tiles of an earlier frame and a tile only for chunks of its own frame, and chunks are handed out in
 //     frame order, so this cannot deadlock.
-//   * Frames rotate through kBatchMaps scatter maps (epoch-tagged keys as everywhere else), so the
-//     events of frame f+1 and f+2 never disturb the cells frame f's tiles still have to read; the
-//     first chunk of frame f+3 a warp sees waits for frame f's finished-tile count.
+//   * Frames rotate through n_maps scatter maps (3 ... 6, chosen per launch; epoch-tagged keys as everywhere
+//     else), so the events of the next frames never disturb the cells frame f's epilogue still has to read; the
+//     first chunk of frame f + n_maps a warp sees waits for frame f's finished-tile (strips: pass-1) count.
 //   * Time bounds: batch_bounds_kernel (one tiny launch per batch) looks up first / last valid event
 //     of every frame.  Events outside the assumed bounds flag their frame; batch_redo_kernel (one tiny
 //     launch per batch) re-renders flagged frames exactly (device-side tail launches of the two-pass
