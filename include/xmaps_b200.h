@@ -176,6 +176,8 @@ int xm_ctx_set_colormap(XmCtx* ctx, const uint8_t* h_bgr256);
  *   "tile_warps"      epilogue warps per CTA of the strip epilogue: 2, 4; 0 = two for large frames, four for small [0]
  *   "strip_rows", "strip_blocks"  item sizes of the strip epilogue (rows per pass-1 item, 256-pixel blocks per pass-2
  *                     item); 0 = 42 / 8 for small frames, 90 / 16 for large ones                                [0]
+ *   "strip_lag"       blocks by which the pass-2 items of a frame trail its pass-1 items in the strip epilogue's
+ *                     item list, 1 ... 3                                                                       [1]
  *   "reserve_sms"     SMs the persistent batch kernel leaves free (e.g. for NCCL's copy kernels)  [0]
  *   "ctas_per_sm"     resident CTAs per SM for the event kernel, 0 = occupancy query            [0]
  *   "region_cells"    shared-memory cells per buffer of the projector-view epilogue [largest tile region of

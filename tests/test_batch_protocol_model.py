@@ -18,7 +18,7 @@ kernel relies on:
   3. every schedule terminates (no deadlock), with every chunk scattered and every tile processed once.
 
 The strip epilogue (the projector view's default: two passes per frame, one warp per item, every item of the batch in
-ONE ordered list handed out by a global counter, pass 2 of a frame one block behind its pass 1) is modelled the same
+ONE ordered list handed out by a global counter, pass 2 of a frame `lag` blocks behind its pass 1) is modelled the same
 way: pass 1 of frame f waits for the frame's chunks and for pass 2 of frame f - 4 (four dilated maps in rotation), pass
 2 for the frame's finished pass-1 count; the finished pass-1 count is what frees the scatter map.
 
@@ -144,17 +144,23 @@ def tile_group(w: World):
             w.tiles_done[f] += 1
 
 
-def strip_decode(w: World, t: int):
-    """Position t of the strip epilogue's item list -> (frame, pass, item).  Order: pass 1 of frame 0, then blocks of
-    (pass 1 of frame g, pass 2 of frame g - 1), then pass 2 of the last frame (batch_strip_warps)."""
+STRIP_LAG = 1  # option "strip_lag": 1 (default) ... DIL_MAPS - 1
+
+
+def strip_decode(w: World, t: int, lag=None):
+    """Position t of the strip epilogue's item list -> (frame, pass, item).  Block b of the list = pass 1 of frame b
+    (b < B) followed by pass 2 of frame b - lag (b >= lag) (batch_strip_warps)."""
+    lag = STRIP_LAG if lag is None else lag
     per_frame = w.P + w.P2
-    if t < w.P:
-        return 0, 1, t
-    k = t - w.P
-    g, r = k // per_frame + 1, k % per_frame
-    if g < w.B and r < w.P:
-        return g, 1, r
-    return g - 1, 2, (r - w.P if g < w.B else r)
+    head = min(lag, w.B) * w.P
+    mixed = max(w.B - lag, 0)
+    if t < head:
+        return t // w.P, 1, t % w.P
+    if t - head < mixed * per_frame:
+        b, r = (t - head) // per_frame, (t - head) % per_frame
+        return (b + lag, 1, r) if r < w.P else (b, 2, r - w.P)
+    k = t - head - mixed * per_frame
+    return mixed + k // w.P2, 2, k % w.P2
 
 
 def strip_warp(w: World, decode=strip_decode):
@@ -252,24 +258,27 @@ STRIP_SHAPES = [
 @pytest.mark.parametrize("shape", range(len(STRIP_SHAPES)))
 @pytest.mark.parametrize("hard_frames", [0, 1])
 @pytest.mark.parametrize("maps", [2, 3, 6])
-def test_strip_epilogue_protocol_is_safe_and_live(shape, hard_frames, maps):
+@pytest.mark.parametrize("lag", [1, 2, 3])
+def test_strip_epilogue_protocol_is_safe_and_live(shape, hard_frames, maps, lag):
     chunks, p1, p2, ctas, warps = STRIP_SHAPES[shape]
-    for seed in range(25):
+    for seed in range(12):
         rng = random.Random(seed * 104729 + shape)
         w = World(chunks, p1, hard_frames, maps=maps, p2_items=p2)
-        assert run(w, ctas, warps, 2, rng, epilogue=strip_warp) == "done", (shape, hard_frames, maps, seed)
+        assert run(w, ctas, warps, 2, rng, epilogue=lambda w: strip_warp(w, lambda w, t: strip_decode(w, t, lag))) == "done", (shape, hard_frames, maps, lag, seed)
         assert not w.violations, w.violations[:3]
         assert w.scattered == list(chunks) and w.blocks_done == list(chunks)
         assert w.tiles_processed == [p1] * len(chunks) and w.p2_processed == [p2] * len(chunks)
 
 
-def test_strip_decode_enumerates_every_item_once():
-    w = World([1] * 5, 3, 0, p2_items=4)
-    seen = [strip_decode(w, t) for t in range((3 + 4) * 5)]
-    assert sorted(seen) == sorted([(f, 1, j) for f in range(5) for j in range(3)] + [(f, 2, j) for f in range(5) for j in range(4)])
+@pytest.mark.parametrize("lag", [1, 2, 3])
+@pytest.mark.parametrize("frames", [1, 2, 3, 5, 9])
+def test_strip_decode_enumerates_every_item_once(lag, frames):
+    w = World([1] * frames, 3, 0, p2_items=4)
+    seen = [strip_decode(w, t, lag) for t in range((3 + 4) * frames)]
+    assert sorted(seen) == sorted([(f, 1, j) for f in range(frames) for j in range(3)] + [(f, 2, j) for f in range(frames) for j in range(4)])
     # an item only ever waits for items that come earlier in the list
     pos = {it: t for t, it in enumerate(seen)}
-    for f in range(5):
+    for f in range(frames):
         assert max(pos[(f, 1, j)] for j in range(3)) < min(pos[(f, 2, j)] for j in range(4))
         if f >= DIL_MAPS:
             assert max(pos[(f - DIL_MAPS, 2, j)] for j in range(4)) < min(pos[(f, 1, j)] for j in range(3))

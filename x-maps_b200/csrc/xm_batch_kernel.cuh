@@ -100,6 +100,7 @@ struct BatchParams {
     int strips;               // 1: on
     int p2_items;             // pass-2 items per frame
     StripWindow win;          // window of the rectified image pass 1 produces (bounding box of the remap targets)
+    int strip_lag;            // blocks the pass-2 items of a frame trail its pass-1 items by in the item list (1 ... kBatchDilMaps - 1)
     const unsigned* pix_cell;  // per output pixel: its remap target's cell in the rectified image, 0xffffffff = none
     unsigned short* dil[kBatchDilMaps];  // dilated disparity maps in rotation (frame f uses f % kBatchDilMaps)
     int n_frames;
@@ -300,9 +301,10 @@ __device__ __forceinline__ void batch_strip_warps(const BatchParams& bp, int lan
 #else
 #define XM_STRIP_CLK(v)
 #endif
-    // List order: pass 1 of frame 0, then blocks of (pass 1 of frame g, pass 2 of frame g - 1), then pass 2 of the last
-    // frame: by the time a warp reaches the pass-2 items of a frame, that frame's pass 1 has had a block's worth of
-    // items to complete, so warps spend their time on items that can run instead of holding items that cannot.
+    // List order: blocks of (pass 1 of frame b, pass 2 of frame b - lag): by the time a warp reaches the pass-2 items
+    // of a frame, that frame's pass 1 has had `lag` blocks' worth of items to complete, so warps spend their time on
+    // items that can run instead of holding items that cannot (lag < kBatchDilMaps: pass 1 of frame f waits for pass
+    // 2 of frame f - kBatchDilMaps, which must come earlier in the list).
     // (No look-ahead ticket: a warp that held its next item while working on the current one kept that item from every
     // other warp -- with small frames a serial chain pass 2 (f) -> pass 1 (f + 1) through the warps, 31 us per frame
     // instead of 14.)
@@ -314,19 +316,25 @@ __device__ __forceinline__ void batch_strip_warps(const BatchParams& bp, int lan
         if (t >= total) break;
         XM_STRIP_CLK(c1);
         int f, j;  // frame, item (j < n_p1: pass 1, else pass 2 item j - n_p1)
-        if (t < static_cast<unsigned>(n_p1)) {
-            f = 0;
-            j = static_cast<int>(t);
-        } else {
-            const unsigned k = t - static_cast<unsigned>(n_p1);
-            const int g = static_cast<int>(k / per_frame) + 1;
-            const int r = static_cast<int>(k - static_cast<unsigned>(g - 1) * per_frame);
-            if (g < bp.n_frames && r < n_p1) {
-                f = g;
+        {
+            // block b of the list = pass 1 of frame b (b < n) followed by pass 2 of frame b - lag (b >= lag)
+            const int n = bp.n_frames, lag = bp.strip_lag;
+            const unsigned head = static_cast<unsigned>(min(lag, n)) * static_cast<unsigned>(n_p1);  // pass-1-only blocks
+            const int mixed = max(n - lag, 0);
+            if (t < head) {
+                f = static_cast<int>(t / static_cast<unsigned>(n_p1));
+                j = static_cast<int>(t - static_cast<unsigned>(f) * static_cast<unsigned>(n_p1));
+            } else if (t - head < static_cast<unsigned>(mixed) * per_frame) {
+                const unsigned k = t - head;
+                const int b = static_cast<int>(k / per_frame);
+                const int r = static_cast<int>(k - static_cast<unsigned>(b) * per_frame);
+                f = r < n_p1 ? b + lag : b;
                 j = r;
-            } else {
-                f = g - 1;
-                j = g < bp.n_frames ? r : r + n_p1;
+            } else {  // pass-2-only blocks of the last frames
+                const unsigned k = t - head - static_cast<unsigned>(mixed) * per_frame;
+                const int b = static_cast<int>(k / static_cast<unsigned>(n_p2));
+                f = mixed + b;
+                j = n_p1 + static_cast<int>(k - static_cast<unsigned>(b) * static_cast<unsigned>(n_p2));
             }
         }
         FrameState* st = bp.states + f;

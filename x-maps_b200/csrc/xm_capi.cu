@@ -99,6 +99,7 @@ struct XmCtx {
     unsigned short* d_dil = nullptr;  // kBatchDilMaps x rect_w x rect_h
     int strip_box[4] = {0, 0, 0, 0};  // bounding box of the remap targets (inclusive): the window pass 1 produces
     int opt_tile_warps = 0;  // epilogue warps per CTA of the strip epilogue: 0 = auto, 2 or 4
+    int opt_strip_lag = 1;  // (2, 3 measured: no difference, EXPERIMENTS_r02.md #36)
     int opt_strip_rows = 0, opt_strip_blocks = 0;  // item sizes of the strip epilogue (0 = auto: by events per frame)
     int opt_batch_strips = 1;
     int opt_scatter_aggregate = 2;  // batch kernel: 0 plain scatter, 1 aggregate dense chunks per warp round, 2 auto (from the last batch's inlier fraction)
@@ -909,6 +910,7 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
         const int blocks = c->opt_strip_blocks > 0 ? c->opt_strip_blocks : (large ? 2 * xm::kRemapBlocks : xm::kRemapBlocks);
         bp.win = xm::strip_window(c->strip_box[0], c->strip_box[1], c->strip_box[2], c->strip_box[3], rows, blocks);
         bp.tile_items = bp.win.items;
+        bp.strip_lag = c->opt_strip_lag;
         const long long item_px = static_cast<long long>(blocks) * xm::kRemapBlockPx;
         bp.p2_items = static_cast<int>((static_cast<long long>(c->proj_w) * c->proj_h + item_px - 1) / item_px);
         epi_items = (bp.tile_items + bp.p2_items + xm::kTileWarps - 1) / xm::kTileWarps;
@@ -1398,6 +1400,11 @@ int xm_ctx_set_option(XmCtx* c, const char* key, int64_t value) {
         c->opt_tile_warps = v;
         return XM_OK;
     }
+    if (!strcmp(key, "strip_lag")) { /* blocks the pass-2 items of a frame trail its pass-1 items by in the strip epilogue's item list */
+        if (v < 1 || v >= xm::kBatchDilMaps) return fail(XM_ERR_INVALID_ARG, "strip_lag must be 1 ... %d", xm::kBatchDilMaps - 1);
+        c->opt_strip_lag = v;
+        return XM_OK;
+    }
     if (!strcmp(key, "batch_maps")) { /* scatter maps the batch kernel rotates through (0 = auto) */
         if (v < 0 || v == 1 || v > xm::kBatchMapsMax) return fail(XM_ERR_INVALID_ARG, "batch_maps must be 0 or 2 ... %d", xm::kBatchMapsMax);
         c->opt_batch_maps = v;
@@ -1472,6 +1479,7 @@ int xm_ctx_get_option(XmCtx* c, const char* key, int64_t* value) {
     else if (!strcmp(key, "batch_strips")) *value = c->opt_batch_strips;
     else if (!strcmp(key, "batch_maps")) *value = c->opt_batch_maps;
     else if (!strcmp(key, "strip_rows")) *value = c->opt_strip_rows;
+    else if (!strcmp(key, "strip_lag")) *value = c->opt_strip_lag;
     else if (!strcmp(key, "tile_warps")) *value = c->opt_tile_warps;
     else if (!strcmp(key, "strip_blocks")) *value = c->opt_strip_blocks;
     else if (!strcmp(key, "scatter_aggregate")) *value = c->opt_scatter_aggregate;
