@@ -258,3 +258,39 @@ def test_dead_pixel_event_outside_bounds_still_triggers_the_redo(small):
     got = eng.frame_batch([ev, ev], view=0).cpu().numpy()
     assert np.array_equal(got[1], orc.frame_depth(tables, ev, 0))
     assert eng.status()["fixup_ran"]
+
+
+@pytest.mark.parametrize("strips", [1, 0], ids=BATCH_IDS)
+def test_ragged_projector_image(strips):
+    """A projector image whose pixel count is not a multiple of the strip epilogue's 256-pixel blocks (nor of the tile
+    size), with remap targets that leave the rectified image and a window that touches its border: every pixel of every
+    frame must still equal the oracle's."""
+    import dataclasses
+
+    tables, z = load_golden_tables("small")
+    remap = np.ascontiguousarray(tables.remap_xy[3:310, 5:178]).copy()  # 307 rows x 173 columns
+    remap[:9, :, 0] = -5  # pixels whose targets lie outside the rectified image (left / below)
+    remap[-7:, :, 1] = tables.rect_h
+    remap[20:24, :, 0] = 0  # ... and on its first / last column and last row: the window's halo leaves the image
+    remap[40:44, :, 0] = tables.rect_w - 1
+    remap[30:34, :, 1] = tables.rect_h - 1
+    remap[50:52, :, 1] = 0
+    t2 = dataclasses.replace(tables, remap_xy=remap)
+    eng = make_engine(t2, z)
+    try:
+        eng.set_option("batch_strips", strips)
+        frames = [orc.synth_events(700 + i, n, 160, 120) for i, n in enumerate([30_000, 1, 0, 12_345, 64, 50_000, 2_047])]
+        out = eng.frame_batch(frames, view=0).cpu().numpy()
+        assert out.shape[1:] == (307, 173)
+        for i, f in enumerate(frames):
+            assert np.array_equal(out[i], orc.frame_depth(t2, f, 0)), f"frame {i}"
+        # item sizes the launch would not pick by itself
+        eng.set_option("strip_rows", 5)
+        eng.set_option("strip_blocks", 3)
+        eng.set_option("tile_warps", 2)
+        eng.set_option("batch_maps", 2)
+        out = eng.frame_batch(frames, view=0).cpu().numpy()
+        for i, f in enumerate(frames):
+            assert np.array_equal(out[i], orc.frame_depth(t2, f, 0)), f"frame {i} (odd item sizes)"
+    finally:
+        eng.close()
