@@ -186,10 +186,10 @@ int xm_ctx_set_colormap(XmCtx* ctx, const uint8_t* h_bgr256);
  *                     epilogue) of every frame; -1 resets the accumulators.  Read back with
  *                     "profile_k1_ns", "profile_k2_ns", "profile_frames", "profile_launches" (these
  *                     synchronise; a batch launch counts once in profile_launches, its frames in profile_frames)
- *   "alive"           1: the batch kernel consults a shared-memory bitmap (one bit per 4x4 camera-pixel block,
- *                     derived exactly from the LUT and the X-map at upload: can ANY time column make an
- *                     event of the block an inlier?) and only counts / bounds-checks events of dead
- *                     blocks -- no LUT gather, X-map lookup or scatter for them; 0: every event is looked up [1]
+ *   "alive"           1: the batch kernel consults a shared-memory table (per 8x8 block of camera pixels the hull of
+ *                     the time columns at which an event of the block can be an inlier, derived exactly from the LUT
+ *                     and the X-map at upload) and only counts / bounds-checks events outside it -- no LUT gather,
+ *                     X-map lookup or scatter for them; 0: every event is looked up                             [1]
  *   "epoch"           test hook: clear the scatter map and set its 16-bit frame counter
  * read-only (xm_ctx_get_option): "cap_cols", "occupancy", "sm_count", "event_smem_bytes", "batch_occ",
  * "batch_smem", "batch_cols", "alive_px" (camera pixels inside alive blocks).  The environment variable XMAPS_B200_OPTS="key=value,key=value" applies options to

@@ -196,10 +196,14 @@ def test_default_geometry_1m_events(default):
 
 
 # ------------------------------------------------------------------------------------------------
-# the "alive" bitmap (events whose 4x4 pixel block can never yield an inlier are only counted / bounds-checked)
+# the "alive" table (events whose pixel block cannot yield an inlier at their time column are only counted / bounds-checked)
 # ------------------------------------------------------------------------------------------------
+ALIVE_BLOCK = 8  # xm_capi.cu:build_alive picks 8 x 8 pixels for the golden geometries (<= 6144 blocks)
+
+
 def alive_blocks(tables):
-    """Host restatement of xm_capi.cu:build_alive: per camera pixel, can ANY time column make it an inlier?"""
+    """Host restatement of the first half of xm_capi.cu:build_alive: per camera pixel, can ANY time column make it an
+    inlier?  (The table also keeps, per block, the hull of those columns; the parity tests cover that part.)"""
     xm = tables.x_map.astype(np.int32)
     ly, lx = tables.lut_y.astype(np.int32), tables.lut_x.astype(np.int32)
     h, w = ly.shape
@@ -211,17 +215,18 @@ def alive_blocks(tables):
                 continue
             d = (xm[ly[y, x]] - lx[y, x] - tables.x_offset).astype(np.int16)
             alive[y, x] = bool((d >= 0).any())
-    bh, bw = (h + 3) // 4, (w + 3) // 4
-    pad = np.zeros((bh * 4, bw * 4), bool)
+    b = ALIVE_BLOCK
+    bh, bw = (h + b - 1) // b, (w + b - 1) // b
+    pad = np.zeros((bh * b, bw * b), bool)
     pad[:h, :w] = alive
-    blocks = pad.reshape(bh, 4, bw, 4).any(axis=(1, 3))
+    blocks = pad.reshape(bh, b, bw, b).any(axis=(1, 3))
     return alive, blocks
 
 
 def test_alive_bitmap_is_exact_and_invisible(small):
     tables, _, eng = small
     alive, blocks = alive_blocks(tables)
-    px_in_alive_blocks = int(np.kron(blocks, np.ones((4, 4), bool))[: tables.cam_h, : tables.cam_w].sum())
+    px_in_alive_blocks = int(np.kron(blocks, np.ones((ALIVE_BLOCK, ALIVE_BLOCK), bool))[: tables.cam_h, : tables.cam_w].sum())
     assert eng.get_option("alive_px") == px_in_alive_blocks
     assert 0 < px_in_alive_blocks < tables.cam_h * tables.cam_w  # the small geometry has dead blocks
     frames = [orc.synth_events(700 + i, 30_000 + 1000 * i, 160, 120) for i in range(5)]
@@ -248,7 +253,7 @@ def test_dead_pixel_event_outside_bounds_still_triggers_the_redo(small):
     ev = orc.synth_events(41, 40_000, 160, 120)
     ev["p"] = 1
     k = 20_000
-    ev["x"][k], ev["y"][k] = bx * 4, by * 4
+    ev["x"][k], ev["y"][k] = bx * ALIVE_BLOCK, by * ALIVE_BLOCK
     ev["t"][k] = ev["t"].min() - 500  # earlier than the first event: the sorted-bounds assumption is wrong
     other = orc.synth_events(42, 10_000, 160, 120)
     out = eng.frame_batch([other, ev, other], view=0).cpu().numpy()
@@ -294,3 +299,24 @@ def test_ragged_projector_image(strips):
             assert np.array_equal(out[i], orc.frame_depth(t2, f, 0)), f"frame {i} (odd item sizes)"
     finally:
         eng.close()
+
+
+def test_exact_rounding_ties_in_every_chunk(small):
+    """t range = 2 * T_PX_SCALE: every odd timestamp sits exactly half-way between two time columns (round half to even
+    in the reference's float64 expression).  The integer fast pass only detects those; every chunk is redone by the
+    general front half, whose live list (which depends on the time column) is laid out anew."""
+    tables, _, eng = small
+    frames = []
+    for i in range(4):
+        ev = orc.synth_events(900 + i, 25_000 + 3_000 * i, 160, 120)
+        rng = np.random.default_rng(i)
+        t = np.sort(rng.integers(0, 2 * tables.t_px_scale + 1, len(ev))).astype(np.int64)
+        t[0], t[-1] = 0, 2 * tables.t_px_scale
+        ev["t"] = t + 1000 * i
+        ev["p"][0] = ev["p"][-1] = 1  # the bounds are the first / last KEPT event
+        frames.append(ev)
+    for view in (0, 1):
+        out = eng.frame_batch(frames, view=view).cpu().numpy()
+        for i, f in enumerate(frames):
+            assert np.array_equal(out[i], orc.frame_depth(tables, f, view)), f"view {view} frame {i}"
+    assert not eng.status()["fixup_ran"]

@@ -81,14 +81,18 @@ struct BatchParams {
     int t_px_scale, x_offset;
     int rect_w, rect_h;
     int cap_cols, stages, win_stages;
-    // "alive" bitmap: one bit per 4x4 block of camera pixels, set if ANY time column can make an event of a pixel of
-    // the block an inlier (derived from the LUT and the X-map at table upload, exact).  Events of dead blocks are
-    // only counted and bounds-checked: no LUT gather, no X-map lookup, no scatter.
-    // Layout: block (bx, by) = bit (bx & 31) of word by * (alive_row_bytes / 4) + (bx >> 5); the table is padded to a
-    // power of two of words and the kernel masks the byte address, so that any 16-bit coordinate pair reads inside it.
-    const unsigned* alive;
-    int alive_row_bytes, alive_words;
-    unsigned alive_mask;  // alive_words * 4 - 4
+    // "alive" table: per block of 2^s x 2^s camera pixels the range of (quantised) time columns in which an event of a
+    // pixel of the block CAN be an inlier (derived exactly from the LUT and the X-map at table upload: the union over
+    // the block's pixels of [first, last] column with disparity >= 0; a pixel's inlier columns are one interval for any
+    // monotonic X-map row, and a conservative hull otherwise).  Events outside their block's range -- 69 % of a uniform
+    // stream, of which 70 % are no inliers -- are only counted and bounds-checked: no LUT gather, no X-map lookup, no
+    // scatter.  Entry (u16) = lo | (hi - lo) << 8 in units of 2^alive_qs columns, dead block = 255 | 0 << 8 (no column
+    // reaches 255 units); entry (bx, by) at by * alive_pitch + bx, the index clamped so that any 16-bit coordinate
+    // pair reads inside the table.
+    const unsigned* alive;   // the table, as 32-bit words for the copy into shared memory
+    int alive_words;         // words to copy
+    int alive_shift, alive_pitch, alive_qs;
+    unsigned alive_last;     // last entry (index clamp)
     unsigned long long* maps[kBatchMapsMax];
     int n_maps;             // maps in rotation: frame f scatters into maps[f % n_maps]
     unsigned epoch0;        // frame f scatters with epoch0 + f
@@ -496,17 +500,20 @@ constexpr unsigned kAggregateAbove = XM_AGG_ABOVE;  // live-list entries (of 128
 constexpr unsigned kMetaSkip = 0x8000u;  // list entry of an event whose column is not usable (bounds violation)
 constexpr unsigned kMetaOff = 2 * kListBytes, kPixOff = 4 * kListBytes;  // (column | index << 16) / camera pixel lists behind the LUT words
 
-// "alive" bit of the 4x4 pixel block of a record's first word (x | y << 16): masked address, any coordinates are safe
-__device__ __forceinline__ unsigned batch_alive_bit(const BatchParams& bp, unsigned a_alive, unsigned xy) {
-    const unsigned addr = ((xy >> 18) * static_cast<unsigned>(bp.alive_row_bytes) + ((xy >> 5) & 0x7fcu)) & bp.alive_mask;
-    return __funnelshift_r(static_cast<unsigned>(lds32_a(a_alive + addr)), 0u, xy >> 2) & 1u;
+// Can an event of this record's pixel block (first word x | y << 16) be an inlier at time column q?  (alive table,
+// see BatchParams; clamped index: any coordinates are safe)
+__device__ __forceinline__ bool batch_alive(const BatchParams& bp, unsigned a_alive, unsigned xy, unsigned q) {
+    const unsigned idx = min((xy >> 16 >> bp.alive_shift) * static_cast<unsigned>(bp.alive_pitch) + ((xy & 0xffffu) >> bp.alive_shift), bp.alive_last);
+    const unsigned e = lds_u16_a(a_alive + idx * 2u);
+    return (q >> bp.alive_qs) - (e & 0xffu) <= (e >> 8);
 }
 
 // GENERAL front half of a chunk (whole warp, out of line): partial chunks, frames the integer time column does not
 // cover, and chunks in which the fast pass found an exact rounding tie or a timestamp outside the assumed bounds.
-// Evaluates the reference's own float64 expression for every event and (re)writes the warp's live list; the list
-// positions only depend on the live flags, so gathers the fast pass already started land in the same slots with the
-// same words.  Returns the chunk's carry (without the constant slot).
+// Evaluates the reference's own float64 expression for every event and (re)writes the warp's live list.  The live
+// flags depend on the time column, so the list a fast pass left behind may be laid out differently: the caller waits
+// for the gathers that pass started (cp.async.wait_all) before this one reuses the slots.  Returns the chunk's carry
+// (without the constant slot).
 template <bool CAM>
 static __device__ __noinline__ unsigned batch_front_general(const BatchParams& bp, int f, unsigned a_stage, unsigned a_list_c, int limit,
                                                             unsigned a_alive, int tid) {
@@ -522,23 +529,26 @@ static __device__ __noinline__ unsigned batch_front_general(const BatchParams& b
         const unsigned ex = static_cast<unsigned>(rec.x) & 0xffffu, ey = static_cast<unsigned>(rec.x) >> 16;
         const bool valid = ((static_cast<unsigned>(rec.y) ^ 1u) & pol_mask) == 0u && (k * kEvThreads + tid < limit);
         const bool ok = valid && ex < static_cast<unsigned>(bp.cam_w) && ey < static_cast<unsigned>(bp.cam_h);
-        const bool live = ok && batch_alive_bit(bp, a_alive, static_cast<unsigned>(rec.x)) != 0u;
+        bool viol = false;
+        int cc = 0;
+        if (ok) {  // (not kept, or not inside the image: no time column)
+            const long long t_bits = (static_cast<long long>(rec.w) << 32) | static_cast<unsigned>(rec.z);
+            cc = tc.column(t_bits, viol);    // exact for every event (== the integer form wherever that is valid)
+            if (cc < 0) cc += bp.xmap_w;     // NumPy negative index (only reachable with wrong bounds)
+            viol = viol || cc < 0 || cc >= bp.xmap_w;
+        }
+        // (an event whose column is not usable flags the frame below and needs no list entry)
+        const bool live = ok && !viol && batch_alive(bp, a_alive, static_cast<unsigned>(rec.x), static_cast<unsigned>(cc));
         const unsigned mask = __ballot_sync(0xffffffffu, live);
         const unsigned pos = count + __popc(mask & lt_mask);
         count += __popc(mask);
         kept += valid ? 1u : 0u;
         oob = oob || (valid && !ok);  // the reference raises IndexError here
-        if (!ok) continue;            // not kept, or not inside the image: no time column
-        const long long t_bits = (static_cast<long long>(rec.w) << 32) | static_cast<unsigned>(rec.z);
-        bool viol;
-        int cc = tc.column(t_bits, viol);  // exact for every event (== the integer form wherever that is valid)
-        if (cc < 0) cc += bp.xmap_w;       // NumPy negative index (only reachable with wrong bounds)
-        viol = viol || cc < 0 || cc >= bp.xmap_w;
         tb = tb || viol;  // dead events too: a timestamp outside the assumed bounds invalidates the frame's normalisation
         if (live) {
             const int px = static_cast<int>(ey * static_cast<unsigned>(bp.cam_w) + ex);
             cp_async_4_a(a_list_c + pos * 4u, bp.lut_xy + px);
-            sts32_a(a_list_c + kMetaOff + pos * 4u, (viol ? kMetaSkip : static_cast<unsigned>(cc)) | (static_cast<unsigned>(k * kEvThreads + tid) << 16));
+            sts32_a(a_list_c + kMetaOff + pos * 4u, static_cast<unsigned>(cc) | (static_cast<unsigned>(k * kEvThreads + tid) << 16));
             if (CAM) sts32_a(a_list_c + kPixOff + pos * 4u, static_cast<unsigned>(px));
         }
     }
@@ -811,7 +821,7 @@ __global__ void __launch_bounds__(kWsThreads + TW * 32, kBatchCtasPerSm) batch_k
         }
     };
 
-    auto alive_bit = [&](unsigned xy) -> unsigned { return batch_alive_bit(bp, a_alive, xy); };
+    auto alive = [&](unsigned xy, unsigned q) -> bool { return batch_alive(bp, a_alive, xy, q); };
 
     // FRONT half of chunk g of frame f (stage fe): polarity / image / alive tests, bounds check and time column of
     // every event; live events are compacted into the warp's lists and their LUT gathers started; releases the stage.
@@ -856,13 +866,13 @@ __global__ void __launch_bounds__(kWsThreads + TW * 32, kBatchCtasPerSm) batch_k
                     const unsigned ex = xy & 0xffffu, ey = xy >> 16;
                     const bool valid = ((static_cast<unsigned>(raw[j].y) ^ 1u) & pol_mask) == 0u;  // polarity: p == 1, or everything
                     const bool ok = valid && ex < XM_B_CAMW && ey < XM_B_CAMH;
-                    // can a pixel of this 4x4 block ever be an inlier?  (shared-memory bitmap; looked up unconditionally:
-                    // a branch per event costs more than the load, and the masked address is safe for any coordinates)
-                    const unsigned abit = alive_bit(xy);
-                    const bool live = ok & (abit != 0u);
+                    // can a pixel of this block be an inlier at this time column?  (shared-memory table; looked up
+                    // unconditionally: a branch per event costs more than the load, and the clamped index is safe for
+                    // any coordinates; a wrong q of a `bad` event only matters until the general pass redoes the chunk)
                     const long long t_bits = (static_cast<long long>(raw[j].w) << 32) | static_cast<unsigned>(raw[j].z);
                     bool bad;
                     const unsigned q = ic.column(t_bits, bad);
+                    const bool live = ok & alive(xy, q);
                     // dead events too: a timestamp outside the assumed bounds invalidates the frame's normalisation
                     any_bad = any_bad || (ok && bad);
                     oob = oob || (valid && !ok);  // the reference raises IndexError here
@@ -884,7 +894,11 @@ __global__ void __launch_bounds__(kWsThreads + TW * 32, kBatchCtasPerSm) batch_k
                 }
             }
             carry = (kept << 1) | (oob ? kCarryOob : 0u) | (count << 8);
-            if (__any_sync(0xffffffffu, any_bad)) carry = batch_front_general<CAM>(bp, f, a_stage, a_list_c, kEvChunk, a_alive, tid);
+            if (__any_sync(0xffffffffu, any_bad)) {
+                cp_async_wait_all();  // the list is laid out anew: no gather of this pass may land in it afterwards
+                __syncwarp();
+                carry = batch_front_general<CAM>(bp, f, a_stage, a_list_c, kEvChunk, a_alive, tid);
+            }
         } else {
             carry = batch_front_general<CAM>(bp, f, a_stage, a_list_c, left < kEvChunk ? static_cast<int>(left) : kEvChunk, a_alive, tid);
         }

@@ -78,9 +78,9 @@ struct XmCtx {
     double depth_scale = 0.0;
     int* d_lut_xy = nullptr;
     std::vector<int> h_lut_xy;          // host copy of the packed LUT (the alive bitmap is rebuilt when the X-map changes)
-    unsigned* d_alive = nullptr;        // [alive_words] one bit per 4x4 camera-pixel block: some time column can make it an inlier
-    unsigned* d_alive_ones = nullptr;   // all ones (option alive = 0)
-    int alive_wpr = 0, alive_words = 0;  // words per row of blocks, words in total (a power of two)
+    unsigned* d_alive = nullptr;        // the batch kernel's alive table: per camera-pixel block the time columns that can yield inliers (build_alive)
+    unsigned* d_alive_ones = nullptr;   // the same table with every column alive everywhere (option alive = 0)
+    int alive_shift = 3, alive_pitch = 0, alive_qs = 0, alive_entries = 0, alive_words = 0;  // block = 2^shift pixels, entries per row, column quantum 2^qs, u16 entries, 32-bit words
     long long alive_px = 0;             // camera pixels inside alive blocks (diagnostic, option "alive_px")
     int opt_alive = 1;
     int lut_x_min = 0;                  // smallest rectified x of the LUT (lut_safe = lut_x_min > -x_offset)
@@ -361,64 +361,61 @@ int configure_event_kernels(XmCtx* c) {
     return XM_OK;
 }
 
-// One bit per 4x4 block of camera pixels: can ANY time column make an event of a pixel of the block an inlier?
-// Exactly the reference's conditions (x_maps_disparity.py:23-30) evaluated for every value of the pixel's X-map
-// row: 0 <= y_rect < rows - 1 and int16(x_map[y_rect, col] - x_rect - X_OFFSET) >= 0 for some col.
+// The batch kernel's "alive" table (BatchParams::alive): per block of 2^s x 2^s camera pixels the hull of the time
+// columns at which an event of a pixel of the block can be an inlier.  Exactly the reference's conditions
+// (x_maps_disparity.py:23-30) evaluated per pixel against its X-map row: 0 <= y_rect < rows - 1 and
+// int16(x_map[y_rect, col] - x_rect - X_OFFSET) >= 0; first and last such column per pixel (for a monotonic row every
+// column between them is an inlier too; for any other table the hull is merely conservative), union over the block,
+// quantised outwards to 2^qs columns.
 int build_alive(XmCtx* c, const int16_t* h_x_map, int rows, int cols, int x_offset) {
-    // layout: one row of 32-bit words per row of blocks (block (bx, by) = bit bx & 31 of word by * wpr + (bx >> 5)), the
-    // word count rounded up to a power of two: the kernel masks the byte address instead of range-checking the pixel
-    const int bw = (c->cam_w + 3) / 4, bh = (c->cam_h + 3) / 4;
-    const int wpr = (bw + 31) / 32;
-    int words = 4;
-    while (words < wpr * bh) words *= 2;
-    std::vector<std::vector<short>> uniq(rows);
-    {
-        std::vector<unsigned char> seen(65536);
-        for (int y = 0; y < rows; ++y) {
-            std::fill(seen.begin(), seen.end(), 0);
-            const int16_t* row = h_x_map + static_cast<size_t>(y) * cols;
-            for (int x = 0; x < cols; ++x) {
-                const unsigned u = static_cast<unsigned short>(row[x]);
-                if (!seen[u]) {
-                    seen[u] = 1;
-                    uniq[y].push_back(row[x]);
-                }
-            }
-            std::sort(uniq[y].begin(), uniq[y].end(), [](short a, short b) { return a > b; });  // largest first: the usual witness
-        }
-    }
-    std::vector<unsigned> bits(words, 0u);
+    int s = 3;  // smallest block (>= 8 x 8 pixels) whose table stays below 12 KB of shared memory
+    auto blocks = [&](int dim) { return (dim + (1 << s) - 1) >> s; };
+    while (static_cast<long long>(blocks(c->cam_w)) * blocks(c->cam_h) > 6144) ++s;
+    const int bw = blocks(c->cam_w), bh = blocks(c->cam_h), n = bw * bh;
+    int qs = 0;  // (no column may reach 255 units: that value marks dead blocks)
+    while (((cols - 1) >> qs) > 254) ++qs;
+    std::vector<int> lo(n, 1 << 30), hi(n, -1);
     for (int y = 0; y < c->cam_h; ++y)
         for (int x = 0; x < c->cam_w; ++x) {
             const int packed = c->h_lut_xy[static_cast<size_t>(y) * c->cam_w + x];
             const int xcr = static_cast<short>(packed & 0xffff), ycr = packed >> 16;
             if (ycr < 0 || ycr >= rows - 1) continue;
-            bool alive = false;
-            for (short v : uniq[ycr])
-                if (static_cast<short>(v - xcr - x_offset) >= 0) {
-                    alive = true;
-                    break;
-                }
-            if (!alive) continue;
-            bits[(y >> 2) * wpr + (x >> 7)] |= 1u << ((x >> 2) & 31);
+            const int16_t* row = h_x_map + static_cast<size_t>(ycr) * cols;
+            const int k = xcr + x_offset;
+            int first = 0;
+            while (first < cols && static_cast<short>(row[first] - k) < 0) ++first;
+            if (first == cols) continue;  // no column makes this pixel an inlier
+            int last = cols - 1;
+            while (static_cast<short>(row[last] - k) < 0) --last;
+            const int b = (y >> s) * bw + (x >> s);
+            lo[b] = first < lo[b] ? first : lo[b];
+            hi[b] = last > hi[b] ? last : hi[b];
         }
+    const int words = (n * 2 + 3) / 4;
+    std::vector<unsigned short> tab(static_cast<size_t>(words) * 2, 255u), ones(static_cast<size_t>(words) * 2, 0xff00u);
     long long alive_px = 0;
     for (int by = 0; by < bh; ++by)
-        for (int bx = 0; bx < bw; ++bx)
-            if (bits[by * wpr + (bx >> 5)] >> (bx & 31) & 1u) {
-                const int w = std::min(4, c->cam_w - bx * 4), h = std::min(4, c->cam_h - by * 4);
-                alive_px += static_cast<long long>(w) * h;
-            }
+        for (int bx = 0; bx < bw; ++bx) {
+            const int b = by * bw + bx;
+            if (hi[b] < 0) continue;
+            const int lq = lo[b] >> qs, hq = hi[b] >> qs;
+            tab[b] = static_cast<unsigned short>(lq | ((hq - lq) << 8));
+            const int w = std::min(1 << s, c->cam_w - (bx << s)), h = std::min(1 << s, c->cam_h - (by << s));
+            alive_px += static_cast<long long>(w) * h;
+        }
     if (c->alive_words != words) {
         cudaFree(c->d_alive);
         cudaFree(c->d_alive_ones);
         c->d_alive = c->d_alive_ones = nullptr;
         XM_CUDA(cudaMalloc(&c->d_alive, words * sizeof(unsigned)));
         XM_CUDA(cudaMalloc(&c->d_alive_ones, words * sizeof(unsigned)));
-        XM_CUDA(cudaMemset(c->d_alive_ones, 0xff, words * sizeof(unsigned)));
     }
-    XM_CUDA(cudaMemcpy(c->d_alive, bits.data(), words * sizeof(unsigned), cudaMemcpyHostToDevice));
-    c->alive_wpr = wpr;
+    XM_CUDA(cudaMemcpy(c->d_alive, tab.data(), words * sizeof(unsigned), cudaMemcpyHostToDevice));
+    XM_CUDA(cudaMemcpy(c->d_alive_ones, ones.data(), words * sizeof(unsigned), cudaMemcpyHostToDevice));
+    c->alive_shift = s;
+    c->alive_pitch = bw;
+    c->alive_qs = qs;
+    c->alive_entries = n;
     c->alive_words = words;
     c->alive_px = alive_px;
     return XM_OK;
@@ -866,9 +863,11 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     bp.stages = c->opt_stages;
     bp.win_stages = c->opt_batch_win_stages;
     bp.alive = c->opt_alive ? c->d_alive : c->d_alive_ones;
-    bp.alive_row_bytes = c->alive_wpr * 4;
-    bp.alive_mask = static_cast<unsigned>(c->alive_words) * 4u - 4u;
     bp.alive_words = c->alive_words;
+    bp.alive_shift = c->alive_shift;
+    bp.alive_pitch = c->alive_pitch;
+    bp.alive_qs = c->alive_qs;
+    bp.alive_last = static_cast<unsigned>(c->alive_entries - 1);
     bp.epoch0 = epoch0;
     bp.states = c->d_bstate;
     xm::EpilogueParams& q = bp.ep;

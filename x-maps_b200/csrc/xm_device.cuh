@@ -463,6 +463,12 @@ __device__ __forceinline__ int lds_s16_a(unsigned addr) {
     asm volatile("ld.shared.s16 %0, [%1];" : "=r"(r) : "r"(addr));
     return r;
 }
+__device__ __forceinline__ unsigned lds_u16_a(unsigned addr) {
+    unsigned r;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_4_a(unsigned smem_addr, const void* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gmem_src) : "memory");
 }
