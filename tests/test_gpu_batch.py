@@ -320,3 +320,32 @@ def test_exact_rounding_ties_in_every_chunk(small):
         for i, f in enumerate(frames):
             assert np.array_equal(out[i], orc.frame_depth(tables, f, view)), f"view {view} frame {i}"
     assert not eng.status()["fixup_ran"]
+
+
+def test_alive_table_is_conservative_for_a_non_monotonic_x_map():
+    """The alive table keeps, per pixel block, the HULL of the time columns that can yield inliers.  For the reference's
+    X-maps a pixel's inlier columns are one interval; for an arbitrary table they are not -- shuffle the columns of
+    every X-map row differently and the hull must still never drop an inlier."""
+    import dataclasses
+
+    tables, z = load_golden_tables("small")
+    rng = np.random.default_rng(7)
+    xm = tables.x_map.copy()
+    for y in range(xm.shape[0]):
+        xm[y] = xm[y, rng.permutation(xm.shape[1])]
+    t2 = dataclasses.replace(tables, x_map=xm)
+    eng = make_engine(t2, z)
+    try:
+        frames = [orc.synth_events(1300 + i, 40_000, 160, 120) for i in range(3)]
+        stats = {}
+        for flag in (1, 0):
+            eng.set_option("alive", flag)
+            for view in (0, 1):
+                out = eng.frame_batch(frames, view=view).cpu().numpy()
+                for i, f in enumerate(frames):
+                    assert np.array_equal(out[i], orc.frame_depth(t2, f, view)), f"alive {flag} view {view} frame {i}"
+            st = eng.status()
+            stats[flag] = (st["n_valid"], st["n_inliers"])
+        assert stats[0] == stats[1] and stats[1][1] > 0
+    finally:
+        eng.close()
