@@ -248,7 +248,7 @@ __device__ __forceinline__ void batch_tile_groups(const BatchParams& bp, int grp
         if (gtid == 0) {
             const unsigned need = static_cast<unsigned>((bp.frames[f].n + CHUNK - 1) / CHUNK);
             // (back-off: a group leader polls every 0.2 ... 1.6 us; the 3-map ring gives the tiles two frames of slack)
-            for (unsigned ns = XM_POLL_NS0; ld_acquire_u32(&st->blocks_done) < need; ns = min(ns * 2u, static_cast<unsigned>(XM_POLL_NS1))) __nanosleep(ns);
+            spin_until_ge(&st->blocks_done, need, XM_POLL_NS0, XM_POLL_NS1);
             next_ticket = static_cast<int>(atomicAdd(&st->fix_chunk, 1u));
 #ifdef XM_DEBUG_HOOKS
             if (bp.dbg) atomicMin(bp.dbg + f * 4 + 2, global_timer_ns());
@@ -296,7 +296,7 @@ __device__ __forceinline__ void batch_strip_warps(const BatchParams& bp, int lan
     const int n_px = bp.ep.out_w * bp.ep.out_h;
     unsigned* const counter = &bp.states[bp.n_frames].next_tile;
     auto wait_for = [&](const unsigned* c, unsigned need) {
-        for (unsigned ns = XM_POLL_NS0; ld_acquire_u32(c) < need; ns = min(ns * 2u, static_cast<unsigned>(XM_POLL_NS1))) __nanosleep(ns);
+        spin_until_ge(c, need, XM_POLL_NS0, XM_POLL_NS1);
     };
 #ifdef XM_DEBUG_HOOKS  // lane 0's cycles per phase and pass: [pass * 4 + {ticket, wait, work, publish}], [8 + pass] items
     long long acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -787,7 +787,7 @@ __global__ void __launch_bounds__(kWsThreads + TW * 32, kBatchCtasPerSm) batch_k
             if (lane == 0) {
                 const unsigned* done = &bp.states[f - bp.n_maps].next_tile;
                 const unsigned need = static_cast<unsigned>(bp.tile_items);
-                while (ld_acquire_u32(done) < need) __nanosleep(64);
+                spin_until_ge(done, need, 64u, 64u);
             }
             __syncwarp();
         }

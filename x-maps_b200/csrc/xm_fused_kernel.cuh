@@ -35,13 +35,27 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     return v;
 }
 
+// Spin until *p >= need (a counter that only grows), then acquire.  The polls are RELAXED loads: an acquire load is
+// an LDG followed by CCTL.IVALL (invalidate the SM's whole L1), and the batch kernel's epilogue warps polled 350 000
+// times per frame -- an L1 flush every 12 ns per SM (ncu r3r).  One acquire load after the last poll gives the same
+// ordering (a fence instead would also wait for the warp's own REDs and gathers in flight: measured slower).
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void spin_until_ge(const unsigned* p, unsigned need, unsigned ns0, unsigned ns1) {
+    for (unsigned ns = ns0; ld_relaxed_u32(p) < need; ns = min(ns * 2u, ns1)) __nanosleep(ns);
+    (void)ld_acquire_u32(p);
+}
+
 // All CTAs of the grid must be resident (the host sizes the grid with the occupancy API).
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
-        while (ld_acquire_u32(counter) < target) __nanosleep(40);
+        spin_until_ge(counter, target, 40u, 40u);
         __threadfence();
     }
     __syncthreads();
