@@ -138,6 +138,7 @@ struct BatchBoundsParams {
     long long lo[kBatchMax], hi[kBatchMax];
     unsigned given_mask;  // bit f: bounds of frame f are lo[f] / hi[f] (else first / last valid event)
     int polarity;
+    int t_px_scale;
     int n_frames;
     FrameState* states;
 };
@@ -171,9 +172,16 @@ __global__ void __launch_bounds__(64) batch_bounds_kernel(const __grid_constant_
             st->t_lo_bits = p.lo[f];
             st->t_hi_bits = p.hi[f];
         }
-        return;
+    } else {
+        scan_sorted_bounds(p.events[f], p.n[f], p.polarity, threadIdx.x >> 5, threadIdx.x & 31, &st->t_lo_bits);
     }
-    scan_sorted_bounds(p.events[f], p.n[f], p.polarity, threadIdx.x >> 5, threadIdx.x & 31, &st->t_lo_bits);
+    __syncthreads();  // (both branches are uniform per block)
+    if (threadIdx.x == 0) {
+        IntCol ic;
+        ic.init(st->t_lo_bits, st->t_hi_bits, p.t_px_scale);
+        st->ic0 = make_int4(static_cast<int>(ic.lo), static_cast<int>(ic.lo >> 32), static_cast<int>(ic.range), static_cast<int>(ic.scale2));
+        st->ic1 = make_int4(static_cast<int>(ic.d), static_cast<int>(ic.M), ic.sh, ic.ok ? 1 : 0);
+    }
 }
 
 // release fence for the "data, then counter" hand-offs below (lighter than __threadfence(), which is fence.sc)
@@ -797,11 +805,11 @@ __global__ void __launch_bounds__(kWsThreads + TW * 32, kBatchCtasPerSm) batch_k
             if (bp.dbg) atomicMin(bp.dbg + f * 4 + 0, global_timer_ns());
 #endif
             const unsigned a = a_fc + fslot * 48;
-            IntCol ic;
-            ic.init(__ldcg(&st->t_lo_bits), __ldcg(&st->t_hi_bits), bp.t_px_scale);
+            // the frame's time-column constants as batch_bounds_kernel left them (one division per frame, not per warp)
+            const int4 k0 = __ldcg(&st->ic0), k1 = __ldcg(&st->ic1);
             const unsigned long long mp = reinterpret_cast<unsigned long long>(bp.maps[f % bp.n_maps]);
-            sts128_a(a, make_int4(static_cast<int>(ic.lo), static_cast<int>(ic.lo >> 32), static_cast<int>(ic.range), static_cast<int>(ic.scale2)));
-            sts128_a(a + 16, make_int4(static_cast<int>(ic.d), static_cast<int>(ic.M), ic.sh, ic.ok ? 1 : 0));
+            sts128_a(a, k0);
+            sts128_a(a + 16, k1);
             sts128_a(a + 32, make_int4(static_cast<int>(mp), static_cast<int>(mp >> 32),
                                        static_cast<int>((bp.epoch0 + static_cast<unsigned>(f)) << 16), static_cast<int>(bp.frames[f].n)));
         }

@@ -831,6 +831,7 @@ int batch_impl(XmCtx* c, const XmFrameArgs* a, int n, cudaStream_t s) {
     xm::BatchBoundsParams bb;
     memset(&bb, 0, sizeof(bb));
     bb.polarity = polarity;
+    bb.t_px_scale = c->t_px_scale;
     bb.n_frames = n;
     bb.states = c->d_bstate;
     for (int f = 0; f < n; ++f) {

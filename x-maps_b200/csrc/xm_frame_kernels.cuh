@@ -35,7 +35,12 @@ struct FrameState {
     unsigned int fix_chunk;   // fused kernel: chunk scheduler of the fix-up pass
     unsigned int p2_ticket;   // batch kernel, strip epilogue: pass-2 item scheduler
     unsigned int p2_done;     //   ... and finished pass-2 items
+    unsigned int pad_[2];
+    // batch kernel: the frame's integer time-column constants (IntCol), worked out once by batch_bounds_kernel instead
+    // of by every consumer warp (a 64-bit division): lo (2 words), range, 2 * scale | d, M, shift, ok
+    int4 ic0, ic1;
 };
+static_assert(sizeof(FrameState) == 128 && offsetof(FrameState, ic0) == 96, "FrameState layout (16-byte aligned constants)");
 
 constexpr unsigned kStatusTBounds = 0x1u;
 constexpr unsigned kStatusPixelOob = 0x2u;
