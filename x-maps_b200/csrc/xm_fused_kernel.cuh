@@ -45,6 +45,7 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     return v;
 }
 __device__ __forceinline__ void spin_until_ge(const unsigned* p, unsigned need, unsigned ns0, unsigned ns1) {
+    if (ld_acquire_u32(p) >= need) return;  // (already there: one round trip)
     for (unsigned ns = ns0; ld_relaxed_u32(p) < need; ns = min(ns * 2u, ns1)) __nanosleep(ns);
     (void)ld_acquire_u32(p);
 }
